@@ -1,0 +1,682 @@
+// hb_batch.cu -- kernels and the batched C-ABI (include/pyhanabi.h, "Batch*" block).
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 (see hanabi_b200/build.py).
+// There is no CPU fallback: every entry point launches CUDA work on the batch's
+// device and reports failure through its int status + BatchLastError().
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/pyhanabi.h"
+#include "hb_engine.cuh"
+#include "hb_spec.h"
+
+namespace hb {
+
+enum Mode { kModeStep = 0, kModeReset = 1, kModeObserve = 2 };
+constexpr int kBlock = 128;
+constexpr int kMaskStride = 3;   // words per lane for the legal-mask bit row
+constexpr int kNumStats = 32;    // [0] episodes [1] sum score [2] sum length [3..28] score histogram
+constexpr int kDumpLen = 272;    // canonical unpacked state, see oracle/oracle_api.h
+
+struct KArgs {
+  Spec spec;
+  uint4* state;
+  uint32_t* mt;
+  int64_t N;
+  uint64_t full_deck;
+  const int32_t* actions;
+  const uint8_t* which;
+  int32_t* rewards;
+  uint8_t* dones;
+  int32_t* scores;
+  int32_t* cur_player;
+  uint8_t* obs;
+  int64_t obs_pitch;
+  uint8_t* mask;
+  unsigned long long* stats;
+  int auto_reset;
+  int sampler_mode;
+  int observer;
+  int obs_stride;  // words per lane of the observation bit row (odd)
+};
+
+template <class V, int MODE>
+__global__ void __launch_bounds__(kBlock) k_main(const __grid_constant__ KArgs a) {
+  extern __shared__ uint32_t smem[];
+  __shared__ int s_stats[kNumStats];
+  const V v(a.spec);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t g = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  const int64_t tile0 = g - lane;  // first game of this warp's tile
+  const bool valid = g < a.N;
+  if (MODE == kModeStep) {
+    if (threadIdx.x < kNumStats) s_stats[threadIdx.x] = 0;
+    __syncthreads();
+  }
+  if (tile0 >= a.N) {
+    if (MODE == kModeStep) __syncthreads();
+    return;
+  }
+  Game G;
+  if (valid) load_game(a.state, a.N, g, v, G);
+  else load_game(a.state, a.N, tile0, v, G);  // keep the lane well-defined; never stored
+
+  if (MODE == kModeStep) {
+    int reward = 0, done_out = 0, score_out = 0, illegal = 0;
+    bool moved = false, term = false;
+    int ep_len = 0;
+    if (valid) {
+      if (G.done) {
+        done_out = 1;  // finished game, no auto-reset: the step is a no-op
+        score_out = score_of(v, G);
+      } else {
+        const int uid = a.actions[g];
+        const uint64_t legal = legal_bits(v, G);
+        if (uid < 0 || uid >= a.spec.max_moves || !((legal >> uid) & 1ull)) {
+          illegal = 1;
+          G.err = 1;
+          score_out = score_of(v, G);
+        } else {
+          const int before = score_of(v, G);
+          apply_move(v, G, uid);
+          score_out = score_of(v, G);
+          reward = score_out - before;  // rl_env.py:363
+          term = is_terminal(v, G);
+          done_out = term ? 1 : 0;
+          ep_len = G.eplen;
+          moved = true;
+        }
+      }
+    }
+    deal_loop(v, a.spec, G, moved, term && a.auto_reset, g, a.mt, a.full_deck, lane,
+              a.sampler_mode);
+    if (valid) {
+      if (term && !a.auto_reset) G.done = 1;
+      if (a.rewards) a.rewards[g] = reward;
+      if (a.dones) a.dones[g] = (uint8_t)done_out;
+      if (a.scores) a.scores[g] = score_out;
+    }
+    (void)illegal;
+    // episode statistics: warp aggregate -> CTA shared counters -> one global atomic per CTA
+    const unsigned tm = __ballot_sync(kFull, term);
+    if (tm) {
+      const int ssum = __reduce_add_sync(kFull, term ? score_out : 0);
+      const int lsum = __reduce_add_sync(kFull, term ? ep_len : 0);
+      if (lane == 0) {
+        atomicAdd(&s_stats[0], __popc(tm));
+        atomicAdd(&s_stats[1], ssum);
+        atomicAdd(&s_stats[2], lsum);
+      }
+      if (term) atomicAdd(&s_stats[3 + (score_out > 25 ? 25 : score_out)], 1);
+    }
+  } else if (MODE == kModeReset) {
+    const bool restart = valid && (a.which == nullptr || a.which[g] != 0);
+    if (restart) { G.done = 0; G.err = 0; }
+    deal_loop(v, a.spec, G, restart, restart, g, a.mt, a.full_deck, lane, a.sampler_mode);
+  }
+
+  if (valid && a.cur_player) a.cur_player[g] = G.cur;
+  if (valid && MODE != kModeObserve) store_game(a.state, a.N, g, v, G);
+
+  const int n_valid = (int)((a.N - tile0) < 32 ? (a.N - tile0) : 32);
+  uint32_t* obs_rows = smem + (size_t)warp * 32 * (a.obs_stride + kMaskStride);
+  uint32_t* mask_rows = obs_rows + 32 * a.obs_stride;
+  if (a.obs) {
+    const int observer = a.observer < 0 ? G.cur : a.observer;
+    encode_obs(v, a.spec, G, observer, obs_rows + lane * a.obs_stride);
+  }
+  if (a.mask) {
+    const uint64_t lb = legal_bits(v, G);
+    mask_rows[lane * kMaskStride] = (uint32_t)lb;
+    mask_rows[lane * kMaskStride + 1] = (uint32_t)(lb >> 32);
+  }
+  __syncwarp();
+  if (a.obs)
+    expand_tile(obs_rows, a.obs_stride, a.spec.obs_size, a.obs + tile0 * a.obs_pitch, a.obs_pitch,
+                n_valid, lane);
+  if (a.mask)
+    expand_tile(mask_rows, kMaskStride, a.spec.max_moves, a.mask + tile0 * a.spec.max_moves,
+                a.spec.max_moves, n_valid, lane);
+
+  if (MODE == kModeStep) {
+    __syncthreads();
+    if (a.stats && threadIdx.x < kNumStats && s_stats[threadIdx.x] != 0)
+      atomicAdd(&a.stats[threadIdx.x], (unsigned long long)s_stats[threadIdx.x]);
+  }
+}
+
+// std::mt19937::seed(value) per game; index = 624 forces a block regeneration on
+// first use, as libstdc++ does.
+__global__ void k_seed(uint32_t* mt, const int32_t* seeds, int64_t N) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= N) return;
+  uint32_t* my = mt + g * (int64_t)kMtN;
+  uint32_t x = (uint32_t)seeds[g];
+  my[0] = x;
+  for (int i = 1; i < kMtN; ++i) {
+    x = 1812433253u * (x ^ (x >> 30)) + (uint32_t)i;
+    my[i] = x;
+  }
+}
+
+__global__ void k_blank(uint4* state, int64_t N, int ncols) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= N) return;
+  for (int c = 0; c < ncols; ++c) state[(int64_t)c * N + g] = make_uint4(0, 0, 0, 0);
+  // mt index 624: first draw regenerates the block
+  state[(int64_t)(ncols - 1) * N + g] = make_uint4(0, (uint32_t)kMtN << 6, 0, 0);
+}
+
+// Packed state -> canonical unpacked dump (oracle/oracle_api.h layout).
+__global__ void k_unpack(KArgs a, int32_t* out) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= a.N) return;
+  const DView v(a.spec);
+  Game G;
+  load_game(a.state, a.N, g, v, G);
+  int32_t* d = out + g * (int64_t)kDumpLen;
+  for (int i = 0; i < kDumpLen; ++i) d[i] = 0;
+  const int C = a.spec.C, R = a.spec.R;
+  d[0] = G.cur; d[1] = G.info; d[2] = G.life; d[3] = G.deck_size;
+  d[4] = score_of(v, G);
+  d[5] = G.life < 1 ? 1 : (score_of(v, G) >= C * R ? 3 : (G.turns <= 0 ? 2 : 0));
+  for (int c = 0; c < C; ++c) d[6 + c] = (G.fw >> (3 * c)) & 7;
+  for (int p = 0; p < kMaxPlayers; ++p) {
+    const int n = p < a.spec.P ? (int)((G.hw[p] >> 16) & 15) : 0;
+    if (p < a.spec.P) d[11 + p] = n;
+    for (int i = 0; i < 8; ++i) {
+      const bool have = i < n;
+      const uint32_t f = have ? G.cards[p] >> (6 * i) : 0;
+      d[16 + p * 8 + i] = have ? (int)(f & 7) * R + (int)((f >> 3) & 7) : -1;
+      const int cm = have ? (G.cpl[p] >> (5 * i)) & 31 : 0, rm = have ? (G.rpl[p] >> (5 * i)) & 31 : 0;
+      d[56 + p * 8 + i] = cm;
+      d[96 + p * 8 + i] = rm;
+      d[136 + p * 8 + i] = (have && ((G.hw[p] >> i) & 1)) ? 31 - __clz(cm) : -1;
+      d[176 + p * 8 + i] = (have && ((G.hw[p] >> (8 + i)) & 1)) ? 31 - __clz(rm) : -1;
+    }
+  }
+  for (int c = 0; c < C; ++c)
+    for (int r = 0; r < R; ++r) {
+      const int k = c * R + r;
+      d[216 + k] = (int)((G.deck >> (2 * k)) & 3);
+      const int off = c * a.spec.per_color + DiscardRankOffset(r);
+      d[241 + k] = __popcll((G.disc >> off) & ((1ull << InstancesOfRank(R, r)) - 1ull));
+    }
+}
+
+// Canonical dump -> packed state (keeps each game's RNG position).  The dump does
+// not carry turns_to_play / last action; they arrive in `extra[g*2+{0,1}]`
+// (turns_to_play, packed last-action record or 0).
+__global__ void k_pack(KArgs a, const int32_t* in, const int32_t* extra) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= a.N) return;
+  const DView v(a.spec);
+  Game G;
+  load_game(a.state, a.N, g, v, G);
+  const int32_t* d = in + g * (int64_t)kDumpLen;
+  const int C = a.spec.C, R = a.spec.R;
+  G.cur = d[0] < 0 ? 0 : d[0]; G.info = d[1]; G.life = d[2]; G.deck_size = d[3];
+  G.fw = 0;
+  for (int c = 0; c < C; ++c) G.fw |= (uint32_t)d[6 + c] << (3 * c);
+  for (int p = 0; p < kMaxPlayers; ++p) {
+    G.cards[p] = G.cpl[p] = G.rpl[p] = G.hw[p] = 0;
+    if (p >= a.spec.P) continue;
+    const int n = d[11 + p];
+    G.hw[p] = (uint32_t)n << 16;
+    for (int i = 0; i < n; ++i) {
+      const int id = d[16 + p * 8 + i];
+      G.cards[p] |= (uint32_t)((id / R) | ((id % R) << 3)) << (6 * i);
+      G.cpl[p] |= (uint32_t)d[56 + p * 8 + i] << (5 * i);
+      G.rpl[p] |= (uint32_t)d[96 + p * 8 + i] << (5 * i);
+      if (d[136 + p * 8 + i] >= 0) G.hw[p] |= 1u << i;
+      if (d[176 + p * 8 + i] >= 0) G.hw[p] |= 1u << (8 + i);
+    }
+  }
+  G.deck = 0; G.disc = 0;
+  for (int c = 0; c < C; ++c)
+    for (int r = 0; r < R; ++r) {
+      const int k = c * R + r;
+      G.deck |= (uint64_t)d[216 + k] << (2 * k);
+      const int off = c * a.spec.per_color + DiscardRankOffset(r);
+      G.disc |= ((1ull << d[241 + k]) - 1ull) << off;
+    }
+  G.turns = extra ? extra[g * 2] : a.spec.P;
+  G.last = extra ? (uint32_t)extra[g * 2 + 1] : 0u;
+  G.done = 0; G.err = 0; G.eplen = 0;
+  G.done = is_terminal(v, G) ? 1 : 0;
+  store_game(a.state, a.N, g, v, G);
+}
+
+// Test hook: the deal sampler alone on caller-provided decks and RNG words.
+__global__ void k_deal_test(Spec spec, const uint64_t* decks, const int32_t* sizes,
+                            const uint32_t* lo, const uint32_t* hi, int n, int mode,
+                            int32_t* out_type, int32_t* out_amb) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const DView v(spec);
+  bool amb = false;
+  int type = pick_fast(v, decks[i], sizes[i], lo[i], hi[i], amb);
+  if (mode == 1 || (mode == 0 && amb)) type = pick_exact(v, decks[i], sizes[i], lo[i], hi[i]);
+  if (deck_types(decks[i]) < 2) type = (63 - __clzll((long long)decks[i])) >> 1;
+  out_type[i] = type;
+  if (out_amb) out_amb[i] = amb ? 1 : 0;
+}
+
+}  // namespace hb
+
+// ============================================================== host side
+namespace {
+
+thread_local std::string g_last_error;
+}  // namespace
+
+// Shared with hb_policy.cu / hb_host.cu: records the text BatchLastError() returns.
+int HbFail(const std::string& msg) {
+  g_last_error = msg;
+  return 1;
+}
+
+namespace {
+int Fail(const std::string& msg) { return HbFail(msg); }
+int CudaFail(const char* what, cudaError_t e) {
+  return Fail(std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define HB_CUDA(expr)                                   \
+  do {                                                  \
+    cudaError_t e__ = (expr);                           \
+    if (e__ != cudaSuccess) return CudaFail(#expr, e__); \
+  } while (0)
+
+struct Batch {
+  hb::Spec spec;
+  int device = 0;
+  int64_t N = 0;
+  int ncols = 0;
+  uint4* state = nullptr;
+  uint32_t* mt = nullptr;
+  unsigned long long* stats = nullptr;      // active stats buffer
+  unsigned long long* own_stats = nullptr;  // library-owned fallback
+  uint64_t full_deck = 0;
+  int sampler_mode = 0;
+  int force_generic = 0;
+  int obs_stride = 0;
+  size_t smem_bytes = 0;
+  // pinned/pipelined host path
+  cudaStream_t h_streams[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t h_events[3] = {nullptr, nullptr, nullptr};
+  void* d_host_stage = nullptr;
+  size_t d_host_stage_bytes = 0;
+};
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) ok = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+const char* FindParam(int n, const char** kv, const char* key) {
+  const char* v = nullptr;
+  for (int i = 0; i + 1 < n; i += 2)
+    if (kv[i] && std::strcmp(kv[i], key) == 0) v = kv[i + 1];
+  return v;
+}
+int IntParam(int n, const char** kv, const char* key, int dflt) {
+  const char* v = FindParam(n, kv, key);  // ParameterValue<int>: std::stoi (hanabi_lib/util.cc:37-47)
+  return v ? (int)std::strtol(v, nullptr, 10) : dflt;
+}
+bool BoolParam(int n, const char** kv, const char* key, bool dflt) {
+  const char* v = FindParam(n, kv, key);  // ParameterValue<bool> (hanabi_lib/util.cc:74-86)
+  if (!v) return dflt;
+  return !std::strcmp(v, "1") || !std::strcmp(v, "true") || !std::strcmp(v, "True");
+}
+
+// HanabiGame ctor defaults, hanabi_lib/hanabi_game.cc:20-47.
+int ParseSpec(int n, const char** kv, hb::Spec* s) {
+  std::memset(s, 0, sizeof(*s));
+  s->P = IntParam(n, kv, "players", 2);
+  s->C = IntParam(n, kv, "colors", hb::kMaxColors);
+  s->R = IntParam(n, kv, "ranks", hb::kMaxRanks);
+  s->H = IntParam(n, kv, "hand_size", s->P < 4 ? 5 : 4);
+  s->IT = IntParam(n, kv, "max_information_tokens", 8);
+  s->LT = IntParam(n, kv, "max_life_tokens", 3);
+  s->random_start = BoolParam(n, kv, "random_start_player", false) ? 1 : 0;
+  s->obs_type = IntParam(n, kv, "observation_type", hb::kCardKnowledge);
+  return hb::FinishSpec(s);
+}
+
+hb::KArgs BaseArgs(const Batch* b) {
+  hb::KArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.spec = b->spec;
+  a.state = b->state;
+  a.mt = b->mt;
+  a.N = b->N;
+  a.full_deck = b->full_deck;
+  a.stats = b->stats;
+  a.sampler_mode = b->sampler_mode;
+  a.observer = -1;
+  a.obs_stride = b->obs_stride;
+  return a;
+}
+
+template <class V, int MODE>
+cudaError_t LaunchOne(const Batch* b, const hb::KArgs& a, cudaStream_t stream) {
+  const unsigned grid = (unsigned)((b->N + hb::kBlock - 1) / hb::kBlock);
+  hb::k_main<V, MODE><<<grid, hb::kBlock, b->smem_bytes, stream>>>(a);
+  return cudaGetLastError();
+}
+
+template <int MODE>
+cudaError_t Launch(const Batch* b, const hb::KArgs& a, cudaStream_t stream) {
+  const hb::Spec& s = b->spec;
+  if (!b->force_generic) {
+#define HB_CASE(P_, H_, C_, R_, IT_, LT_)                                                      \
+  if (s.P == P_ && s.H == H_ && s.C == C_ && s.R == R_ && s.IT == IT_ && s.LT == LT_)          \
+    return LaunchOne<hb::SView<P_, H_, C_, R_, IT_, LT_>, MODE>(b, a, stream);
+    HB_CASE(2, 5, 5, 5, 8, 3)  // Hanabi-Full 2p
+    HB_CASE(3, 5, 5, 5, 8, 3)  // Hanabi-Full 3p
+    HB_CASE(4, 4, 5, 5, 8, 3)  // Hanabi-Full 4p
+    HB_CASE(5, 4, 5, 5, 8, 3)  // Hanabi-Full 5p
+    HB_CASE(2, 2, 2, 5, 3, 1)  // Hanabi-Small 2p
+    HB_CASE(4, 2, 2, 5, 3, 1)  // Hanabi-Small 4p
+    HB_CASE(2, 2, 1, 5, 3, 1)  // Hanabi-Very-Small 2p
+#undef HB_CASE
+  }
+  return LaunchOne<hb::DView, MODE>(b, a, stream);
+}
+
+Batch* AsBatch(void* p) { return static_cast<Batch*>(p); }
+
+}  // namespace
+
+// ============================================================== C ABI
+extern "C" {
+
+const char* BatchLastError(void) { return g_last_error.c_str(); }
+
+int NewBatch(pyhanabi_batch_t* out, int list_length, const char** param_list, int num_games,
+             int device, const int32_t* seeds) {
+  if (!out) return Fail("NewBatch: null handle");
+  out->batch = nullptr;
+  if (num_games <= 0) return Fail("NewBatch: num_games must be positive");
+  if (!seeds) return Fail("NewBatch: seeds must point to num_games int32 values (host memory)");
+  Batch* b = new Batch;
+  int rc = ParseSpec(list_length, param_list, &b->spec);
+  if (rc != 0) {
+    delete b;
+    return Fail(std::string("NewBatch: ") + hb::SpecError(rc));
+  }
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0) {
+    delete b;
+    return Fail(std::string("NewBatch: no CUDA device available (") + cudaGetErrorString(e) +
+                "); the batched engine has no CPU fallback");
+  }
+  if (device < 0 || device >= count) {
+    delete b;
+    return Fail("NewBatch: device index out of range");
+  }
+  b->device = device;
+  b->N = num_games;
+  b->ncols = b->spec.P + 2;
+  for (int c = 0; c < b->spec.C; ++c)
+    for (int r = 0; r < b->spec.R; ++r)
+      b->full_deck |= (uint64_t)hb::InstancesOfRank(b->spec.R, r) << (2 * (c * b->spec.R + r));
+  b->obs_stride = ((b->spec.obs_size + 31) / 32) | 1;
+  b->smem_bytes = (size_t)(hb::kBlock / 32) * 32 * (b->obs_stride + hb::kMaskStride) * sizeof(uint32_t);
+  DeviceGuard guard(device);
+  if (!guard.ok) { delete b; return Fail("NewBatch: cudaSetDevice failed"); }
+  int32_t* d_seeds = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(b->state); cudaFree(b->mt); cudaFree(b->own_stats); cudaFree(d_seeds);
+    delete b;
+  };
+#define HB_TRY(expr)                                                           \
+  do {                                                                         \
+    cudaError_t e__ = (expr);                                                  \
+    if (e__ != cudaSuccess) { cleanup(); return CudaFail("NewBatch: " #expr, e__); } \
+  } while (0)
+  HB_TRY(cudaMalloc(&b->state, sizeof(uint4) * (size_t)b->ncols * (size_t)b->N));
+  HB_TRY(cudaMalloc(&b->mt, sizeof(uint32_t) * (size_t)hb::kMtN * (size_t)b->N));
+  HB_TRY(cudaMalloc(&b->own_stats, sizeof(unsigned long long) * hb::kNumStats));
+  HB_TRY(cudaMemset(b->own_stats, 0, sizeof(unsigned long long) * hb::kNumStats));
+  b->stats = b->own_stats;
+  HB_TRY(cudaMalloc(&d_seeds, sizeof(int32_t) * (size_t)b->N));
+  HB_TRY(cudaMemcpy(d_seeds, seeds, sizeof(int32_t) * (size_t)b->N, cudaMemcpyHostToDevice));
+  const unsigned grid = (unsigned)((b->N + 127) / 128);
+  hb::k_seed<<<grid, 128>>>(b->mt, d_seeds, b->N);
+  hb::k_blank<<<grid, 128>>>(b->state, b->N, b->ncols);
+  HB_TRY(cudaGetLastError());
+  HB_TRY(cudaDeviceSynchronize());
+  cudaFree(d_seeds);
+  d_seeds = nullptr;
+#undef HB_TRY
+  out->batch = b;
+  return 0;
+}
+
+void DeleteBatch(pyhanabi_batch_t* h) {
+  if (!h || !h->batch) return;
+  Batch* b = AsBatch(h->batch);
+  DeviceGuard guard(b->device);
+  for (int i = 0; i < 3; ++i) {
+    if (b->h_streams[i]) cudaStreamDestroy(b->h_streams[i]);
+    if (b->h_events[i]) cudaEventDestroy(b->h_events[i]);
+  }
+  cudaFree(b->d_host_stage);
+  cudaFree(b->state);
+  cudaFree(b->mt);
+  cudaFree(b->own_stats);
+  delete b;
+  h->batch = nullptr;
+}
+
+#define HB_BATCH(h)                                              \
+  if (!(h) || !(h)->batch) return Fail("null batch handle");     \
+  Batch* b = AsBatch((h)->batch);                                \
+  DeviceGuard guard__(b->device);                                \
+  if (!guard__.ok) return Fail("cudaSetDevice failed")
+
+int BatchObservationSize(pyhanabi_batch_t* h) { return (h && h->batch) ? AsBatch(h->batch)->spec.obs_size : -1; }
+int BatchMaxMoves(pyhanabi_batch_t* h) { return (h && h->batch) ? AsBatch(h->batch)->spec.max_moves : -1; }
+int BatchNumGames(pyhanabi_batch_t* h) { return (h && h->batch) ? (int)AsBatch(h->batch)->N : -1; }
+int BatchNumPlayers(pyhanabi_batch_t* h) { return (h && h->batch) ? AsBatch(h->batch)->spec.P : -1; }
+int BatchDevice(pyhanabi_batch_t* h) { return (h && h->batch) ? AsBatch(h->batch)->device : -1; }
+
+int BatchReset(pyhanabi_batch_t* h, const uint8_t* which, void* stream) {
+  HB_BATCH(h);
+  hb::KArgs a = BaseArgs(b);
+  a.which = which;
+  HB_CUDA(Launch<hb::kModeReset>(b, a, (cudaStream_t)stream));
+  return 0;
+}
+
+int BatchStep(pyhanabi_batch_t* h, const int32_t* actions, int32_t* rewards, uint8_t* dones,
+              int32_t* scores, int auto_reset, void* stream) {
+  HB_BATCH(h);
+  if (!actions) return Fail("BatchStep: actions is null");
+  hb::KArgs a = BaseArgs(b);
+  a.actions = actions; a.rewards = rewards; a.dones = dones; a.scores = scores;
+  a.auto_reset = auto_reset;
+  HB_CUDA(Launch<hb::kModeStep>(b, a, (cudaStream_t)stream));
+  return 0;
+}
+
+int BatchEncode(pyhanabi_batch_t* h, int observer, uint8_t* obs, int64_t row_pitch, void* stream) {
+  HB_BATCH(h);
+  if (!obs) return Fail("BatchEncode: obs is null");
+  if (row_pitch < b->spec.obs_size) return Fail("BatchEncode: row_pitch smaller than the observation");
+  if (observer >= b->spec.P) return Fail("BatchEncode: observer out of range");
+  hb::KArgs a = BaseArgs(b);
+  a.obs = obs; a.obs_pitch = row_pitch; a.observer = observer;
+  HB_CUDA(Launch<hb::kModeObserve>(b, a, (cudaStream_t)stream));
+  return 0;
+}
+
+int BatchLegalMask(pyhanabi_batch_t* h, uint8_t* mask, void* stream) {
+  HB_BATCH(h);
+  if (!mask) return Fail("BatchLegalMask: mask is null");
+  hb::KArgs a = BaseArgs(b);
+  a.mask = mask;
+  HB_CUDA(Launch<hb::kModeObserve>(b, a, (cudaStream_t)stream));
+  return 0;
+}
+
+int BatchCurPlayer(pyhanabi_batch_t* h, int32_t* cur_player, void* stream) {
+  HB_BATCH(h);
+  if (!cur_player) return Fail("BatchCurPlayer: cur_player is null");
+  hb::KArgs a = BaseArgs(b);
+  a.cur_player = cur_player;
+  HB_CUDA(Launch<hb::kModeObserve>(b, a, (cudaStream_t)stream));
+  return 0;
+}
+
+// Observation + legal mask + current player of the state as it stands (no move).
+int BatchObserve(pyhanabi_batch_t* h, int observer, uint8_t* obs, int64_t row_pitch, uint8_t* mask,
+                 int32_t* cur_player, void* stream) {
+  HB_BATCH(h);
+  if (obs && row_pitch < b->spec.obs_size) return Fail("BatchObserve: row_pitch smaller than the observation");
+  if (observer >= b->spec.P) return Fail("BatchObserve: observer out of range");
+  hb::KArgs a = BaseArgs(b);
+  a.obs = obs; a.obs_pitch = row_pitch; a.observer = observer; a.mask = mask; a.cur_player = cur_player;
+  HB_CUDA(Launch<hb::kModeObserve>(b, a, (cudaStream_t)stream));
+  return 0;
+}
+
+int BatchStepEncode(pyhanabi_batch_t* h, const int32_t* actions, int32_t* rewards, uint8_t* dones,
+                    uint8_t* obs, int64_t row_pitch, uint8_t* mask, int32_t* cur_player,
+                    int auto_reset, void* stream) {
+  HB_BATCH(h);
+  if (!actions) return Fail("BatchStepEncode: actions is null");
+  if (obs && row_pitch < b->spec.obs_size) return Fail("BatchStepEncode: row_pitch smaller than the observation");
+  hb::KArgs a = BaseArgs(b);
+  a.actions = actions; a.rewards = rewards; a.dones = dones;
+  a.obs = obs; a.obs_pitch = row_pitch; a.mask = mask; a.cur_player = cur_player;
+  a.auto_reset = auto_reset;
+  HB_CUDA(Launch<hb::kModeStep>(b, a, (cudaStream_t)stream));
+  return 0;
+}
+
+// Same as BatchStepEncode plus the post-move score of every game (the score of
+// the finished episode when done[i] is set).
+int BatchStepEncodeScores(pyhanabi_batch_t* h, const int32_t* actions, int32_t* rewards,
+                          uint8_t* dones, int32_t* scores, uint8_t* obs, int64_t row_pitch,
+                          uint8_t* mask, int32_t* cur_player, int auto_reset, void* stream) {
+  HB_BATCH(h);
+  if (!actions) return Fail("BatchStepEncodeScores: actions is null");
+  if (obs && row_pitch < b->spec.obs_size) return Fail("BatchStepEncodeScores: row_pitch smaller than the observation");
+  hb::KArgs a = BaseArgs(b);
+  a.actions = actions; a.rewards = rewards; a.dones = dones; a.scores = scores;
+  a.obs = obs; a.obs_pitch = row_pitch; a.mask = mask; a.cur_player = cur_player;
+  a.auto_reset = auto_reset;
+  HB_CUDA(Launch<hb::kModeStep>(b, a, (cudaStream_t)stream));
+  return 0;
+}
+
+int64_t BatchStateBytes(pyhanabi_batch_t* h) {
+  if (!h || !h->batch) return -1;
+  Batch* b = AsBatch(h->batch);
+  return 64 + (int64_t)sizeof(uint4) * b->ncols * b->N + (int64_t)sizeof(uint32_t) * hb::kMtN * b->N;
+}
+
+int BatchGetState(pyhanabi_batch_t* h, void* host_blob, int64_t nbytes) {
+  HB_BATCH(h);
+  if (nbytes < BatchStateBytes(h)) return Fail("BatchGetState: blob too small, see BatchStateBytes");
+  HB_CUDA(cudaDeviceSynchronize());
+  int64_t header[8] = {0x4842323030ll, b->N, b->spec.P, b->ncols, b->spec.obs_size, b->spec.max_moves, 0, 0};
+  std::memcpy(host_blob, header, 64);
+  char* p = static_cast<char*>(host_blob) + 64;
+  const size_t sb = sizeof(uint4) * (size_t)b->ncols * (size_t)b->N;
+  HB_CUDA(cudaMemcpy(p, b->state, sb, cudaMemcpyDeviceToHost));
+  HB_CUDA(cudaMemcpy(p + sb, b->mt, sizeof(uint32_t) * (size_t)hb::kMtN * (size_t)b->N, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int BatchSetState(pyhanabi_batch_t* h, const void* host_blob, int64_t nbytes) {
+  HB_BATCH(h);
+  if (nbytes < BatchStateBytes(h)) return Fail("BatchSetState: blob too small, see BatchStateBytes");
+  int64_t header[8];
+  std::memcpy(header, host_blob, 64);
+  if (header[0] != 0x4842323030ll || header[1] != b->N || header[2] != b->spec.P ||
+      header[4] != b->spec.obs_size || header[5] != b->spec.max_moves)
+    return Fail("BatchSetState: blob does not match this batch (games / rules differ)");
+  HB_CUDA(cudaDeviceSynchronize());
+  const char* p = static_cast<const char*>(host_blob) + 64;
+  const size_t sb = sizeof(uint4) * (size_t)b->ncols * (size_t)b->N;
+  HB_CUDA(cudaMemcpy(b->state, p, sb, cudaMemcpyHostToDevice));
+  HB_CUDA(cudaMemcpy(b->mt, p + sb, sizeof(uint32_t) * (size_t)hb::kMtN * (size_t)b->N, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int BatchUnpackState(pyhanabi_batch_t* h, int32_t* dump, void* stream) {
+  HB_BATCH(h);
+  if (!dump) return Fail("BatchUnpackState: dump is null");
+  hb::KArgs a = BaseArgs(b);
+  const unsigned grid = (unsigned)((b->N + 127) / 128);
+  hb::k_unpack<<<grid, 128, 0, (cudaStream_t)stream>>>(a, dump);
+  HB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int BatchPackState(pyhanabi_batch_t* h, const int32_t* dump, const int32_t* extra, void* stream) {
+  HB_BATCH(h);
+  if (!dump) return Fail("BatchPackState: dump is null");
+  hb::KArgs a = BaseArgs(b);
+  const unsigned grid = (unsigned)((b->N + 127) / 128);
+  hb::k_pack<<<grid, 128, 0, (cudaStream_t)stream>>>(a, dump, extra);
+  HB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Episode statistics accumulate into a caller-owned device buffer of 32 int64
+// (e.g. a torch tensor that torch.distributed all-reduces over NCCL); NULL
+// switches back to the library-owned buffer.
+int BatchSetStatsBuffer(pyhanabi_batch_t* h, int64_t* dev_stats) {
+  HB_BATCH(h);
+  b->stats = dev_stats ? reinterpret_cast<unsigned long long*>(dev_stats) : b->own_stats;
+  return 0;
+}
+
+int BatchReadStats(pyhanabi_batch_t* h, int64_t* host_stats, int clear, void* stream) {
+  HB_BATCH(h);
+  cudaStream_t s = (cudaStream_t)stream;
+  HB_CUDA(cudaMemcpyAsync(host_stats, b->stats, sizeof(int64_t) * hb::kNumStats, cudaMemcpyDeviceToHost, s));
+  if (clear) HB_CUDA(cudaMemsetAsync(b->stats, 0, sizeof(int64_t) * hb::kNumStats, s));
+  HB_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+// 0 = integer fast path with exact fp64 fallback (default), 1 = always the exact
+// fp64 restatement, 2 = fast path only (tests).  `generic` != 0 forces the
+// runtime-parameter kernels even for the pre-instantiated rule sets (tests).
+int BatchSetDebug(pyhanabi_batch_t* h, int sampler_mode, int generic) {
+  HB_BATCH(h);
+  b->sampler_mode = sampler_mode;
+  b->force_generic = generic;
+  return 0;
+}
+
+int BatchDebugDeal(pyhanabi_batch_t* h, const uint64_t* decks, const int32_t* sizes,
+                   const uint32_t* lo, const uint32_t* hi, int n, int mode, int32_t* out_type,
+                   int32_t* out_ambiguous, void* stream) {
+  HB_BATCH(h);
+  hb::k_deal_test<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(b->spec, decks, sizes, lo, hi, n,
+                                                                    mode, out_type, out_ambiguous);
+  HB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,732 @@
+// hb_engine.cuh -- device-side batched Hanabi engine (sm_100a).
+//
+// One thread owns one game; a warp owns a tile of 32 games and provides the
+// cooperative services (mt19937 block regeneration, bit->byte expansion of the
+// observation tile with 128-bit stores).  The whole game lives in registers in
+// packed form; see DESIGN.md "Data layout in HBM".
+//
+// Reference behaviour restated here (paths relative to
+// /root/reference/hanabi_learning_environment/hanabi_lib/):
+//   apply move / advance / score / terminal   hanabi_state.cc:104-144,221-275,359-377
+//   legal moves                               hanabi_state.cc:146-219,288-304
+//   hints on card knowledge                   hanabi_hand.cc:24-42,96-126
+//   deals                                     hanabi_state.cc:229-241,277-286,313-325
+//                                             hanabi_game.cc:106-112,138-145 (+ libstdc++ <random>)
+//   observation view + canonical encoding     hanabi_observation.cc:34-93,
+//                                             canonical_encoders.cc:62-451
+#ifndef HB_ENGINE_CUH_
+#define HB_ENGINE_CUH_
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "hb_spec.h"
+
+namespace hb {
+
+#define HB_DEV __device__ __forceinline__
+constexpr unsigned kFull = 0xffffffffu;
+
+// ------------------------------------------------------------------ spec views
+// Static view: every rule parameter that shapes the bit layout is a compile-time
+// constant so the encoder unrolls into straight-line shifts on register words.
+template <int P_, int H_, int C_, int R_, int IT_, int LT_>
+struct SView {
+  static constexpr bool kStatic = true;
+  static constexpr int kP = P_, kH = H_, kC = C_, kR = R_;
+  HB_DEV explicit SView(const Spec&) {}
+  HB_DEV constexpr int P() const { return P_; }
+  HB_DEV constexpr int H() const { return H_; }
+  HB_DEV constexpr int C() const { return C_; }
+  HB_DEV constexpr int R() const { return R_; }
+  HB_DEV constexpr int IT() const { return IT_; }
+  HB_DEV constexpr int LT() const { return LT_; }
+  HB_DEV constexpr int per_color() const { return R_ == 1 ? 3 : 2 * R_; }
+  HB_DEV constexpr int deck_max() const { return per_color() * C_; }
+  HB_DEV constexpr int bpc() const { return C_ * R_; }
+};
+// Dynamic view: any legal parameter set, loop bounds are the layout maxima.
+struct DView {
+  static constexpr bool kStatic = false;
+  static constexpr int kP = kMaxPlayers, kH = kMaxHand, kC = kMaxColors, kR = kMaxRanks;
+  const Spec& s;
+  HB_DEV explicit DView(const Spec& sp) : s(sp) {}
+  HB_DEV int P() const { return s.P; }
+  HB_DEV int H() const { return s.H; }
+  HB_DEV int C() const { return s.C; }
+  HB_DEV int R() const { return s.R; }
+  HB_DEV int IT() const { return s.IT; }
+  HB_DEV int LT() const { return s.LT; }
+  HB_DEV int per_color() const { return s.per_color; }
+  HB_DEV int deck_max() const { return s.deck_max; }
+  HB_DEV int bpc() const { return s.bits_per_card; }
+};
+
+// ------------------------------------------------------------------- the game
+// Packed HBM layout: (P + 2) columns of uint4, column-major over games
+// (state[col * N + game]) so a warp reads/writes 512 contiguous bytes per column.
+//   column p < P  : x = cards   (6-bit slots: colour | rank << 3, slot 0 = oldest card)
+//                   y = colour-plausible masks (5-bit slots)
+//                   z = rank-plausible masks   (5-bit slots)
+//                   w = colour-hinted flags [0,8) | rank-hinted flags [8,16) | hand size [16,20)
+//   column P      : x,y = deck counts (2 bits per card type), z,w = discard thermometers
+//                   (exactly the bit layout of the encoder's discard section)
+//   column P + 1  : x = fireworks 5x3 | info 5 | life 4 | cur 3 | turns_to_play 3 | done | error
+//                   y = deck size 6 | mt19937 index 10 | episode length 12
+//                   z = last non-deal action record, w = spare
+struct Game {
+  uint32_t cards[kMaxPlayers];
+  uint32_t cpl[kMaxPlayers];
+  uint32_t rpl[kMaxPlayers];
+  uint32_t hw[kMaxPlayers];
+  uint64_t deck;
+  uint64_t disc;
+  uint32_t fw;  // 3 bits per colour
+  int info, life, cur, turns, done, err;
+  int deck_size, mti, eplen;
+  uint32_t last;
+  uint32_t spare;
+};
+
+// last-action record fields
+constexpr int kLaValid = 0, kLaTypeSh = 1, kLaActorSh = 3, kLaOffSh = 6, kLaValSh = 9,
+              kLaIdxSh = 12, kLaColSh = 15, kLaRankSh = 18, kLaRevealSh = 21, kLaScoredSh = 26,
+              kLaInfoSh = 27;
+
+HB_DEV int hand_size(const Game& G, int p_static) { return (G.hw[p_static] >> 16) & 15; }
+
+template <class V>
+HB_DEV void load_game(const uint4* __restrict__ st, int64_t N, int64_t g, V v, Game& G) {
+#pragma unroll
+  for (int p = 0; p < V::kP; ++p) {
+    if (p < v.P()) {
+      uint4 c = st[(int64_t)p * N + g];
+      G.cards[p] = c.x; G.cpl[p] = c.y; G.rpl[p] = c.z; G.hw[p] = c.w;
+    } else {
+      G.cards[p] = 0; G.cpl[p] = 0; G.rpl[p] = 0; G.hw[p] = 0;
+    }
+  }
+  uint4 a = st[(int64_t)v.P() * N + g];
+  G.deck = (uint64_t)a.x | ((uint64_t)a.y << 32);
+  G.disc = (uint64_t)a.z | ((uint64_t)a.w << 32);
+  uint4 b = st[(int64_t)(v.P() + 1) * N + g];
+  G.fw = b.x & 0x7fffu;
+  G.info = (b.x >> 15) & 31;
+  G.life = (b.x >> 20) & 15;
+  G.cur = (b.x >> 24) & 7;
+  G.turns = (b.x >> 27) & 7;
+  G.done = (b.x >> 30) & 1;
+  G.err = (b.x >> 31) & 1;
+  G.deck_size = b.y & 63;
+  G.mti = (b.y >> 6) & 1023;
+  G.eplen = (b.y >> 16) & 4095;
+  G.last = b.z;
+  G.spare = b.w;
+}
+
+template <class V>
+HB_DEV void store_game(uint4* __restrict__ st, int64_t N, int64_t g, V v, const Game& G) {
+#pragma unroll
+  for (int p = 0; p < V::kP; ++p) {
+    if (p < v.P()) st[(int64_t)p * N + g] = make_uint4(G.cards[p], G.cpl[p], G.rpl[p], G.hw[p]);
+  }
+  st[(int64_t)v.P() * N + g] = make_uint4((uint32_t)G.deck, (uint32_t)(G.deck >> 32),
+                                          (uint32_t)G.disc, (uint32_t)(G.disc >> 32));
+  uint32_t x = G.fw | ((uint32_t)G.info << 15) | ((uint32_t)G.life << 20) |
+               ((uint32_t)G.cur << 24) | ((uint32_t)G.turns << 27) | ((uint32_t)G.done << 30) |
+               ((uint32_t)G.err << 31);
+  uint32_t y = (uint32_t)G.deck_size | ((uint32_t)G.mti << 6) |
+               ((uint32_t)(G.eplen > 4095 ? 4095 : G.eplen) << 16);
+  st[(int64_t)(v.P() + 1) * N + g] = make_uint4(x, y, G.last, G.spare);
+}
+
+// Register-array access with a runtime player index: a predicated select chain
+// keeps the arrays in registers (no local memory).
+template <class V>
+HB_DEV uint32_t sel(const uint32_t (&a)[kMaxPlayers], int p) {
+  uint32_t r = a[0];
+#pragma unroll
+  for (int i = 1; i < V::kP; ++i) r = (p == i) ? a[i] : r;
+  return r;
+}
+template <class V>
+HB_DEV void put(uint32_t (&a)[kMaxPlayers], int p, uint32_t val) {
+#pragma unroll
+  for (int i = 0; i < V::kP; ++i) a[i] = (p == i) ? val : a[i];
+}
+
+// -------------------------------------------------------------------- mt19937
+HB_DEV uint32_t mt_temper(uint32_t z) {
+  z ^= (z >> 11);
+  z ^= (z << 7) & 0x9d2c5680u;
+  z ^= (z << 15) & 0xefc60000u;
+  z ^= (z >> 18);
+  return z;
+}
+
+// Whole-warp in-place regeneration of one game's 624-word block (the standard
+// genrand block step).  Within a 32-word slice every lane loads before any lane
+// stores; slices run in ascending order so that words k >= 227 see the new
+// values of words k - 227, exactly like the sequential loop.
+HB_DEV void mt_twist_warp(uint32_t* mt, int lane) {
+  for (int base = 0; base < kMtN; base += 32) {
+    const int k = base + lane;
+    uint32_t nv = 0;
+    if (k < kMtN) {
+      const int k1 = (k + 1 == kMtN) ? 0 : k + 1;
+      const int km = (k + kMtM >= kMtN) ? k + kMtM - kMtN : k + kMtM;
+      uint32_t a = __ldcg(mt + k), b = __ldcg(mt + k1), c = __ldcg(mt + km);
+      uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
+      nv = c ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+    }
+    __syncwarp();
+    if (k < kMtN) __stcg(mt + k, nv);
+    __syncwarp();
+  }
+}
+
+// Warp-convergent service: every lane asks for need in {0,1,2} consecutive
+// words of ITS game's stream.  Lanes whose block is exhausted get it regenerated
+// by the whole warp.  Must be called by all 32 lanes.
+HB_DEV void warp_fetch_words(uint32_t* mt_all, int64_t g, int& mti, int need, int lane,
+                             uint32_t& w0, uint32_t& w1) {
+  uint32_t* my = mt_all + g * (int64_t)kMtN;
+  int got = 0;
+  if (need >= 1 && mti < kMtN) { w0 = mt_temper(__ldcg(my + mti)); ++mti; got = 1; }
+  if (need >= 2 && got == 1 && mti < kMtN) { w1 = mt_temper(__ldcg(my + mti)); ++mti; got = 2; }
+  unsigned tw = __ballot_sync(kFull, got < need);
+  while (tw) {
+    const int src = __ffs(tw) - 1;
+    tw &= tw - 1;
+    const long long gs = __shfl_sync(kFull, (long long)g, src);
+    mt_twist_warp(mt_all + gs * (int64_t)kMtN, lane);
+  }
+  if (got < need) {
+    mti = 0;
+    if (got == 0) { w0 = mt_temper(__ldcg(my + mti)); ++mti; got = 1; }
+    if (need >= 2 && got == 1) { w1 = mt_temper(__ldcg(my + mti)); ++mti; }
+  }
+}
+
+// ------------------------------------------------------------- deal sampling
+// The reference draws a card with libstdc++'s std::discrete_distribution over
+// doubles count/deck_size (hanabi_state.cc:277-280,313-325; hanabi_game.cc:106-112;
+// bits/random.tcc:2655-2712,3346-3385).  Mathematically that is "card number
+// floor(u * deck_size) of the type-sorted deck".  pick_fast evaluates this in
+// exact 128-bit integer arithmetic and reports `ambiguous` when u*deck_size lies
+// within 2^-32 of an integer -- the only place where fp64 rounding in the
+// reference could decide differently (its total error is < 2^-46).  Ambiguous
+// draws are re-done by pick_exact, an operation-for-operation fp64 restatement.
+constexpr uint64_t kGuard = 1ull << 32;
+
+template <class V>
+HB_DEV int pick_fast(V v, uint64_t deck, int deck_size, uint32_t lo, uint32_t hi, bool& ambiguous) {
+  const uint64_t U = ((uint64_t)hi << 32) | lo;
+  const uint64_t q = __umul64hi(U, (uint64_t)deck_size);
+  const uint64_t F = U * (uint64_t)deck_size;
+  ambiguous = (F + kGuard) < 2 * kGuard;
+  int acc = 0, type = 0;
+  const int qi = (int)q;
+#pragma unroll
+  for (int k = 0; k < V::kC * V::kR; ++k) {
+    if (k < v.C() * v.R()) {
+      const int c = (int)((deck >> (2 * k)) & 3);
+      type = (qi >= acc && qi < acc + c) ? k : type;
+      acc += c;
+    }
+  }
+  return type;
+}
+
+template <class V>
+__device__ __noinline__ int pick_exact(V v, uint64_t deck, int deck_size, uint32_t lo, uint32_t hi) {
+  double w[kMaxColors * kMaxRanks];
+  int idx[kMaxColors * kMaxRanks];
+  int n = 0;
+  for (int k = 0; k < v.C() * v.R(); ++k) {
+    const int c = (int)((deck >> (2 * k)) & 3);
+    if (c > 0) {
+      idx[n] = k;
+      w[n] = __ddiv_rn((double)c, (double)deck_size);
+      ++n;
+    }
+  }
+  if (n < 2) return idx[0];
+  double sum = 0.0;
+  for (int k = 0; k < n; ++k) sum = __dadd_rn(sum, w[k]);
+  double cp = 0.0;
+  double u = __dadd_rn(__dmul_rn((double)lo, 1.0), __dmul_rn((double)hi, 4294967296.0));
+  u = __ddiv_rn(u, 18446744073709551616.0);
+  if (u >= 1.0) u = __longlong_as_double(0x3FEFFFFFFFFFFFFFll);  // nextafter(1, 0)
+  int res = n - 1;
+  bool found = false;
+  for (int k = 0; k < n; ++k) {
+    const double p = __ddiv_rn(w[k], sum);
+    cp = (k == 0) ? p : __dadd_rn(cp, p);
+    const double c = (k == n - 1) ? 1.0 : cp;
+    if (!found && !(c < u)) { res = k; found = true; }
+  }
+  return idx[res];
+}
+
+// Number of distinct card types left in the deck (>= 2 means the reference
+// consumes two RNG words for the draw, else none: random.tcc:2660-2664,2696-2697).
+HB_DEV int deck_types(uint64_t deck) {
+  const uint64_t nz = (deck | (deck >> 1)) & 0x5555555555555555ull;
+  return __popcll(nz);
+}
+
+// Lemire's nearly-divisionless bounded integer as libstdc++ uses it for
+// uniform_int_distribution on a 32-bit URNG (bits/uniform_int_dist.h:256-282).
+// Returns true when the word is accepted.
+HB_DEV bool lemire_accept(uint32_t word, uint32_t range, uint32_t& out) {
+  const uint64_t product = (uint64_t)word * (uint64_t)range;
+  const uint32_t low = (uint32_t)product;
+  out = (uint32_t)(product >> 32);
+  if (low < range) {
+    const uint32_t threshold = (0u - range) % range;
+    if (low < threshold) return false;
+  }
+  return true;
+}
+
+// -------------------------------------------------------------------- rules
+template <class V>
+HB_DEV bool needs_deal(V v, const Game& G) {
+  bool short_hand = false;
+#pragma unroll
+  for (int p = 0; p < V::kP; ++p)
+    if (p < v.P()) short_hand |= hand_size(G, p) < v.H();
+  return G.deck_size > 0 && short_hand;
+}
+
+// HanabiState::ApplyMove(kDeal) for card type `type` (hanabi_state.cc:229-241).
+template <class V>
+HB_DEV void deal_card(V v, Game& G, int type, int obs_type) {
+  const int color = type / v.R(), rank = type - color * v.R();
+  bool placed = false;
+#pragma unroll
+  for (int p = 0; p < V::kP; ++p) {
+    if (p < v.P()) {
+      const int n = hand_size(G, p);
+      if (!placed && n < v.H()) {  // PlayerToDeal: lowest index with a short hand
+        placed = true;
+        G.cards[p] |= (uint32_t)(color | (rank << 3)) << (6 * n);
+        uint32_t cm = (1u << v.C()) - 1u, rm = (1u << v.R()) - 1u, flags = 0;
+        if (obs_type == kSeer) {  // hanabi_state.cc:233-236
+          cm = 1u << color; rm = 1u << rank; flags = (1u << n) | (1u << (8 + n));
+        }
+        G.cpl[p] |= cm << (5 * n);
+        G.rpl[p] |= rm << (5 * n);
+        G.hw[p] = (G.hw[p] | flags) + (1u << 16);
+      }
+    }
+  }
+  G.deck -= 1ull << (2 * type);
+  G.deck_size -= 1;
+}
+
+template <class V>
+HB_DEV int score_of(V v, const Game& G) {  // hanabi_state.cc:359-364
+  if (G.life <= 0) return 0;
+  int s = 0;
+#pragma unroll
+  for (int c = 0; c < V::kC; ++c)
+    if (c < v.C()) s += (G.fw >> (3 * c)) & 7;
+  return s;
+}
+
+template <class V>
+HB_DEV bool is_terminal(V v, const Game& G) {  // hanabi_state.cc:366-377
+  return G.life < 1 || score_of(v, G) >= v.C() * v.R() || G.turns <= 0;
+}
+
+// HanabiState::LegalMoves(cur) as a bitmask over move uids
+// (hanabi_state.cc:166-219,288-304; uid layout hanabi_game.cc:79-95).
+template <class V>
+HB_DEV uint64_t legal_bits(V v, const Game& G) {
+  const int n = (int)((sel<V>(G.hw, G.cur) >> 16) & 15);
+  const uint64_t hm = (1ull << n) - 1ull;
+  uint64_t bits = (G.info < v.IT() ? hm : 0ull) | (hm << v.H());
+  if (G.info > 0) {
+#pragma unroll
+    for (int p = 0; p < V::kP; ++p) {
+      if (p < v.P() && p != G.cur) {
+        int off = p - G.cur;
+        off += off < 0 ? v.P() : 0;
+        const int m = hand_size(G, p);
+        uint32_t cm = 0, rm = 0;
+#pragma unroll
+        for (int i = 0; i < V::kH; ++i) {
+          if (i < m) {
+            const uint32_t f = G.cards[p] >> (6 * i);
+            cm |= 1u << (f & 7);
+            rm |= 1u << ((f >> 3) & 7);
+          }
+        }
+        bits |= (uint64_t)cm << (2 * v.H() + (off - 1) * v.C());
+        bits |= (uint64_t)rm << (2 * v.H() + (v.P() - 1) * v.C() + (off - 1) * v.R());
+      }
+    }
+  }
+  return bits;
+}
+
+HB_DEV uint32_t drop_slot(uint32_t w, int idx, int width) {
+  const uint32_t low = (1u << (width * idx)) - 1u;
+  return (w & low) | ((w >> width) & ~low);
+}
+
+// HanabiState::ApplyMove for a player move (hanabi_state.cc:221-275), followed by
+// the turn hand-over of AdvanceToNextPlayer (:104-111; pending deals are resolved
+// by the caller's deal loop before anybody observes the state).
+template <class V>
+HB_DEV void apply_move(V v, Game& G, int uid) {
+  const int cur = G.cur;
+  const int P = v.P(), H = v.H(), C = v.C(), R = v.R();
+  if (G.deck_size == 0) G.turns -= 1;
+  uint32_t la = 1u | ((uint32_t)cur << kLaActorSh);
+  if (uid < 2 * H) {
+    const bool is_play = uid >= H;
+    const int idx = is_play ? uid - H : uid;
+    const uint32_t hand = sel<V>(G.cards, cur);
+    const int color = (hand >> (6 * idx)) & 7, rank = (hand >> (6 * idx + 3)) & 7;
+    bool to_discard = true, scored = false, token = false;
+    if (is_play) {
+      const int top = (G.fw >> (3 * color)) & 7;
+      if (rank == top) {  // AddToFireworks :132-144
+        G.fw += 1u << (3 * color);
+        scored = true;
+        to_discard = false;
+        if (top + 1 == R && G.info < v.IT()) { G.info += 1; token = true; }
+      } else {
+        G.life -= 1;
+      }
+    } else {
+      if (G.info < v.IT()) { G.info += 1; token = true; }  // IncrementInformationTokens
+    }
+    if (to_discard) {
+      const int off = color * v.per_color() + DiscardRankOffset(rank);
+      const int cnt = __popcll((G.disc >> off) & 7ull & ((1ull << InstancesOfRank(R, rank)) - 1ull));
+      G.disc |= 1ull << (off + cnt);
+    }
+    // RemoveFromHand (hanabi_hand.cc:87-94): later cards shift down.
+    put<V>(G.cards, cur, drop_slot(hand, idx, 6));
+    put<V>(G.cpl, cur, drop_slot(sel<V>(G.cpl, cur), idx, 5));
+    put<V>(G.rpl, cur, drop_slot(sel<V>(G.rpl, cur), idx, 5));
+    const uint32_t hw = sel<V>(G.hw, cur);
+    const uint32_t ch = drop_slot(hw & 0xffu, idx, 1), rh = drop_slot((hw >> 8) & 0xffu, idx, 1);
+    put<V>(G.hw, cur, ch | (rh << 8) | ((hw & 0xf0000u) - (1u << 16)));
+    la |= (uint32_t)(is_play ? kLaPlay : kLaDiscard) << kLaTypeSh;
+    la |= (uint32_t)idx << kLaIdxSh | (uint32_t)color << kLaColSh | (uint32_t)rank << kLaRankSh;
+    la |= (uint32_t)scored << kLaScoredSh | (uint32_t)token << kLaInfoSh;
+  } else {
+    int u = uid - 2 * H;
+    const bool is_rank = u >= (P - 1) * C;
+    if (is_rank) u -= (P - 1) * C;
+    const int span = is_rank ? R : C;
+    const int offm1 = u / span, val = u - offm1 * span;
+    int t = cur + offm1 + 1;
+    t -= t >= P ? P : 0;
+    G.info -= 1;
+    const uint32_t hand = sel<V>(G.cards, t);
+    const uint32_t hw = sel<V>(G.hw, t);
+    const int n = (hw >> 16) & 15;
+    uint32_t mm = 0, M = 0;
+#pragma unroll
+    for (int i = 0; i < V::kH; ++i) {
+      if (i < n) {
+        const uint32_t f = hand >> (6 * i);
+        const int cv = is_rank ? ((f >> 3) & 7) : (f & 7);
+        if (cv == val) { mm |= 1u << i; M |= 31u << (5 * i); }
+      }
+    }
+    // RevealColor/RevealRank (hanabi_hand.cc:96-126): matching cards become
+    // exactly {val} and are flagged hinted; the others lose val.
+    const uint32_t all = (1u << val) * 0x108421u;
+    if (is_rank) {
+      put<V>(G.rpl, t, (sel<V>(G.rpl, t) & ~all & ~M) | (all & M));
+      put<V>(G.hw, t, hw | (mm << 8));
+    } else {
+      put<V>(G.cpl, t, (sel<V>(G.cpl, t) & ~all & ~M) | (all & M));
+      put<V>(G.hw, t, hw | mm);
+    }
+    la |= (uint32_t)(is_rank ? kLaRevealRank : kLaRevealColor) << kLaTypeSh;
+    la |= (uint32_t)(offm1 + 1) << kLaOffSh | (uint32_t)val << kLaValSh | mm << kLaRevealSh;
+  }
+  G.last = la;
+  G.cur = cur + 1 == P ? 0 : cur + 1;
+  G.eplen += 1;
+}
+
+// Fresh game before any deal (HanabiState ctor, hanabi_state.cc:90-102).
+template <class V>
+HB_DEV void init_fresh(V v, Game& G, uint64_t full_deck, int start_player) {
+#pragma unroll
+  for (int p = 0; p < V::kP; ++p) { G.cards[p] = 0; G.cpl[p] = 0; G.rpl[p] = 0; G.hw[p] = 0; }
+  G.deck = full_deck;
+  G.disc = 0;
+  G.fw = 0;
+  G.info = v.IT();
+  G.life = v.LT();
+  G.cur = start_player;
+  G.turns = v.P();
+  G.done = 0;
+  G.deck_size = v.deck_max();
+  G.eplen = 0;
+  G.last = 0;
+}
+
+// Warp-convergent: deals until no lane's game is waiting for a card.  Lanes
+// with `restart` set first finish the deals of the old game (the reference
+// deals before it looks at IsTerminal, rl_env.py:357-361), then start a new
+// game on the same RNG stream (one std::mt19937 per HanabiGame,
+// hanabi_game.h:114) and deal its P*H cards.
+template <class V>
+HB_DEV void deal_loop(V v, const Spec& spec, Game& G, bool active, bool restart, int64_t g,
+                      uint32_t* mt_all, uint64_t full_deck, int lane, int sampler_mode) {
+  for (;;) {
+    bool need = active && needs_deal(v, G);
+    int fresh_need_start = 0;
+    if (active && !need && restart) {
+      restart = false;
+      init_fresh(v, G, full_deck, 0);
+      fresh_need_start = spec.random_start ? 1 : 0;
+      need = needs_deal(v, G) && !fresh_need_start;
+    }
+    // Random start player: one bounded draw before the first deal
+    // (hanabi_game.cc:138-145), re-drawn on the (2^-30 rare) Lemire rejection.
+    unsigned sp = __ballot_sync(kFull, fresh_need_start != 0);
+    while (sp) {
+      uint32_t w0 = 0, w1 = 0;
+      warp_fetch_words(mt_all, g, G.mti, fresh_need_start, lane, w0, w1);
+      if (fresh_need_start) {
+        uint32_t val;
+        if (lemire_accept(w0, (uint32_t)v.P(), val)) {
+          G.cur = (int)val;
+          fresh_need_start = 0;
+          need = needs_deal(v, G);
+        }
+      }
+      sp = __ballot_sync(kFull, fresh_need_start != 0);
+    }
+    if (!__any_sync(kFull, need || (active && restart))) break;
+    const bool multi = need && deck_types(G.deck) >= 2;
+    uint32_t lo = 0, hi = 0;
+    warp_fetch_words(mt_all, g, G.mti, multi ? 2 : 0, lane, lo, hi);
+    if (need) {
+      int type;
+      if (multi) {
+        bool amb = false;
+        type = pick_fast(v, G.deck, G.deck_size, lo, hi, amb);
+        if (sampler_mode == 1 || (amb && sampler_mode != 2))
+          type = pick_exact(v, G.deck, G.deck_size, lo, hi);
+      } else {
+        type = (63 - __clzll((long long)G.deck)) >> 1;
+      }
+      deal_card(v, G, type, spec.obs_type);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ encoding
+// Streaming bit writer into one shared-memory row of 32-bit words (bit j of the
+// observation is bit j & 31 of word j >> 5).  With a static view every width and
+// hence every shift is a compile-time constant.
+struct BitWriter {
+  uint32_t* row;
+  uint64_t acc;
+  int nbits, wi;
+  HB_DEV explicit BitWriter(uint32_t* r) : row(r), acc(0), nbits(0), wi(0) {}
+  HB_DEV void put(uint32_t value, int width) {  // width in [0, 32]
+    acc |= (uint64_t)value << nbits;
+    nbits += width;
+    if (nbits >= 32) {
+      row[wi++] = (uint32_t)acc;
+      acc >>= 32;
+      nbits -= 32;
+    }
+  }
+  HB_DEV void put64(uint64_t value, int width) {  // width in [0, 64]
+    const int w0 = width < 32 ? width : 32;
+    put((uint32_t)(value & ((1ull << w0) - 1ull)), w0);
+    put((uint32_t)(value >> 32), width - w0);
+  }
+  HB_DEV void zeros(int width) {
+    while (width > 32) { put(0u, 32); width -= 32; }
+    put(0u, width);
+  }
+  HB_DEV void flush() {
+    if (nbits > 0) row[wi++] = (uint32_t)acc;
+  }
+};
+
+// CanonicalObservationEncoder::Encode for `observer` with the HanabiObservation
+// view folded in.  Writes obs_size bits to `row`.
+template <class V>
+HB_DEV void encode_obs(V v, const Spec& spec, const Game& G, int observer, uint32_t* row) {
+  const int P = v.P(), H = v.H(), C = v.C(), R = v.R(), bpc = v.bpc();
+  BitWriter bw(row);
+  // --- hands (canonical_encoders.cc:62-105)
+  uint32_t short_bits = 0;
+#pragma unroll
+  for (int q = 0; q < V::kP; ++q) {
+    if (q < P) {
+      int p = observer + q;
+      p -= p >= P ? P : 0;
+      const uint32_t hand = sel<V>(G.cards, p);
+      const int n = (int)((sel<V>(G.hw, p) >> 16) & 15);
+      short_bits |= (uint32_t)(n < H) << q;
+      if (q >= 1) {
+#pragma unroll
+        for (int i = 0; i < V::kH; ++i) {
+          if (i < H) {
+            const uint32_t f = hand >> (6 * i);
+            const int id = (int)(f & 7) * R + (int)((f >> 3) & 7);
+            bw.put(i < n ? (1u << id) : 0u, bpc);
+          }
+        }
+      }
+    }
+  }
+  bw.put(short_bits, P);
+  // --- board (canonical_encoders.cc:123-167)
+  bw.put64((1ull << G.deck_size) - 1ull, v.deck_max() - P * H);
+#pragma unroll
+  for (int c = 0; c < V::kC; ++c) {
+    if (c < C) {
+      const int top = (G.fw >> (3 * c)) & 7;
+      bw.put(top > 0 ? (1u << (top - 1)) : 0u, R);
+    }
+  }
+  bw.put((1u << G.info) - 1u, v.IT());
+  bw.put((1u << G.life) - 1u, v.LT());
+  // --- discards (canonical_encoders.cc:188-211): stored in this very layout
+  bw.put64(G.disc, v.deck_max());
+  // --- last action (canonical_encoders.cc:236-338; observer-relative actor as
+  //     hanabi_observation.cc:34-49)
+  {
+    const uint32_t la = G.last;
+    const bool valid = la & 1u;
+    const int type = (la >> kLaTypeSh) & 3;
+    int rel = (int)((la >> kLaActorSh) & 7) - observer;
+    rel += rel < 0 ? P : 0;
+    const bool is_hint = valid && type >= kLaRevealColor;
+    const bool is_card = valid && type <= kLaDiscard;
+    bw.put(valid ? (1u << rel) : 0u, P);
+    bw.put(valid ? (1u << type) : 0u, 4);
+    int tgt = rel + (int)((la >> kLaOffSh) & 7);
+    tgt -= tgt >= P ? P : 0;
+    bw.put(is_hint ? (1u << tgt) : 0u, P);
+    const int val = (la >> kLaValSh) & 7;
+    bw.put((valid && type == kLaRevealColor) ? (1u << val) : 0u, C);
+    bw.put((valid && type == kLaRevealRank) ? (1u << val) : 0u, R);
+    bw.put(is_hint ? ((la >> kLaRevealSh) & 31u) : 0u, H);
+    bw.put(is_card ? (1u << ((la >> kLaIdxSh) & 7)) : 0u, H);
+    const int id = (int)((la >> kLaColSh) & 7) * R + (int)((la >> kLaRankSh) & 7);
+    bw.put(is_card ? (1u << id) : 0u, bpc);
+    bw.put((valid && type == kLaPlay) ? ((la >> kLaScoredSh) & 3u) : 0u, 2);
+  }
+  // --- card knowledge (canonical_encoders.cc:366-419), absent for kMinimal
+  if (spec.obs_type != kMinimal) {
+#pragma unroll
+    for (int q = 0; q < V::kP; ++q) {
+      if (q < P) {
+        int p = observer + q;
+        p -= p >= P ? P : 0;
+        const uint32_t cpl = sel<V>(G.cpl, p), rpl = sel<V>(G.rpl, p), hw = sel<V>(G.hw, p);
+        const int n = (int)((hw >> 16) & 15);
+#pragma unroll
+        for (int i = 0; i < V::kH; ++i) {
+          if (i < H) {
+            const uint32_t cm = (cpl >> (5 * i)) & 31u, rm = (rpl >> (5 * i)) & 31u;
+            uint32_t plaus = 0;
+#pragma unroll
+            for (int c = 0; c < V::kC; ++c)
+              if (c < C) plaus |= ((cm >> c) & 1u) ? (rm << (c * R)) : 0u;
+            const bool have = i < n;
+            bw.put(have ? plaus : 0u, bpc);
+            bw.put((have && ((hw >> i) & 1u)) ? cm : 0u, C);
+            bw.put((have && ((hw >> (8 + i)) & 1u)) ? rm : 0u, R);
+          }
+        }
+      }
+    }
+  }
+  bw.flush();
+}
+
+// 4 bits -> 4 bytes of 0/1 (little-endian byte i = bit i).
+HB_DEV uint32_t nibble_to_bytes(uint32_t n) { return ((n & 15u) * 0x00204081u) & 0x01010101u; }
+
+// Reads `count` (<= 16) bits starting at bit `o` of a row.
+HB_DEV uint32_t row_bits16(const uint32_t* row, int o, int words) {
+  const int w = o >> 5, sh = o & 31;
+  const uint32_t lo = row[w];
+  const uint32_t hi = (w + 1 < words) ? row[w + 1] : 0u;
+  return __funnelshift_r(lo, hi, sh) & 0xffffu;
+}
+
+// Warp-cooperative expansion of a tile of bit rows (one row per game, `stride`
+// words apart in shared memory, `dim` valid bits each) into bytes of 0/1 in
+// global memory.  Dense rows (pitch == dim) make the tile one contiguous,
+// 16-byte aligned byte range, written with 128-bit stores so a warp covers 512
+// contiguous bytes per instruction.
+HB_DEV void expand_tile(const uint32_t* rows, int stride, int dim, uint8_t* out, int64_t pitch,
+                        int n_valid, int lane) {
+  const int words = (dim + 31) >> 5;
+  if (pitch == dim && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) {
+    const int total = n_valid * dim;
+    const int full_chunks = total >> 4;
+    int g = 0, o = lane * 16;
+    while (o >= dim) { o -= dim; ++g; }
+    const int dq = 512 / dim, dr = 512 - dq * dim;
+    for (int k = lane; k < full_chunks; k += 32) {
+      const int avail = dim - o;
+      uint32_t bits = row_bits16(rows + g * stride, o, words);
+      if (avail < 16) {
+        bits &= (1u << avail) - 1u;
+        bits |= (rows[(g + 1) * stride] << avail) & 0xffffu;
+      }
+      uint4 val;
+      val.x = nibble_to_bytes(bits);
+      val.y = nibble_to_bytes(bits >> 4);
+      val.z = nibble_to_bytes(bits >> 8);
+      val.w = nibble_to_bytes(bits >> 12);
+      *reinterpret_cast<uint4*>(out + (int64_t)k * 16) = val;
+      g += dq;
+      o += dr;
+      if (o >= dim) { o -= dim; ++g; }
+    }
+    // ragged tail of a partial tile
+    for (int b = (full_chunks << 4) + lane; b < total; b += 32) {
+      const int gg = b / dim, oo = b - gg * dim;
+      out[b] = (uint8_t)((rows[gg * stride + (oo >> 5)] >> (oo & 31)) & 1u);
+    }
+  } else if ((pitch & 15) == 0 && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) {
+    const int chunks = (dim + 15) >> 4;
+    for (int idx = lane; idx < n_valid * chunks; idx += 32) {
+      const int g = idx / chunks, j = idx - g * chunks;
+      const int o = j * 16, avail = dim - o;
+      uint32_t bits = row_bits16(rows + g * stride, o, words);
+      uint8_t* dst = out + (int64_t)g * pitch + o;
+      if (avail >= 16) {
+        uint4 val;
+        val.x = nibble_to_bytes(bits);
+        val.y = nibble_to_bytes(bits >> 4);
+        val.z = nibble_to_bytes(bits >> 8);
+        val.w = nibble_to_bytes(bits >> 12);
+        *reinterpret_cast<uint4*>(dst) = val;
+      } else {
+        for (int i = 0; i < avail; ++i) dst[i] = (uint8_t)((bits >> i) & 1u);
+      }
+    }
+  } else {
+    for (int g = 0; g < n_valid; ++g)
+      for (int o = lane; o < dim; o += 32)
+        out[(int64_t)g * pitch + o] = (uint8_t)((rows[g * stride + (o >> 5)] >> (o & 31)) & 1u);
+  }
+}
+
+}  // namespace hb
+#endif  // HB_ENGINE_CUH_

@@ -1,0 +1,293 @@
+// hb_policy.cu -- fused actor/learner-side kernels on the same batch:
+//   BatchSelectAction          legal-mask-aware epsilon-greedy / argmax
+//                              (agents/rainbow_copy/dqn_agent.py:387-420, :200;
+//                               rainbow_agent.py:163-172 for the C51 q-values)
+//   BatchProjectDistribution   Rainbow's C51 categorical projection
+//                              (agents/rainbow_copy/rainbow_agent.py:252-404)
+//   BatchC51TargetDistribution _build_target_distribution fused end to end
+//                              (agents/rainbow_copy/rainbow_agent.py:181-213)
+// fp32 throughout; no tensor cores (there is no dense contraction here).
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/pyhanabi.h"
+
+namespace hbp {
+
+constexpr unsigned kFull = 0xffffffffu;
+
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+// Counter-based policy randomness keyed (seed, step, game): reproducible and
+// independent of launch geometry.  The reference uses Python's `random` and
+// numpy's global RNG (dqn_agent.py:409-412), which cannot be reproduced on a
+// device; only the distribution is matched (uniform over legal moves with
+// probability epsilon).
+__device__ __forceinline__ uint64_t policy_bits(uint64_t seed, uint64_t step, uint64_t game) {
+  return mix64(mix64(seed ^ (step * 0xD1B54A32D192ED03ull)) ^ (game * 0x8CB92BA72F3D8DD7ull));
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(kFull, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+  return v;
+}
+
+// q-values given: one thread per game.
+__global__ void k_select_q(const float* __restrict__ q, const uint8_t* __restrict__ mask, int n,
+                           int A, float epsilon, uint64_t seed, uint64_t step,
+                           int32_t* __restrict__ actions) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  const uint8_t* m = mask + (int64_t)g * A;
+  int n_legal = 0;
+  for (int a = 0; a < A; ++a) n_legal += m[a] != 0;
+  if (n_legal == 0) { actions[g] = -1; return; }
+  const uint64_t bits = policy_bits(seed, step, (uint64_t)g);
+  const float u = (float)(bits >> 40) * (1.0f / 16777216.0f);  // 24-bit uniform in [0,1)
+  int choice = -1;
+  if (u <= epsilon && epsilon > 0.0f) {  // random.random() <= epsilon
+    int k = (int)(((bits & 0xffffffffull) * (uint64_t)n_legal) >> 32);
+    for (int a = 0; a < A; ++a)
+      if (m[a] != 0 && k-- == 0) { choice = a; break; }
+  } else {
+    // argmax_a(q[a] + legal[a]) with legal in {0, -inf}: first maximal index (tf.argmax).
+    float best = -CUDART_INF_F;
+    const float* row = q + (int64_t)g * A;
+    for (int a = 0; a < A; ++a) {
+      const float val = m[a] != 0 ? row[a] : -CUDART_INF_F;
+      if (choice < 0 ? (m[a] != 0) : (val > best)) { best = val; choice = a; }
+    }
+  }
+  actions[g] = choice;
+}
+
+// C51 logits given: one warp per game.  q[a] = sum_i support[i] * softmax(logits[a,:])[i].
+__global__ void k_select_c51(const float* __restrict__ logits, const float* __restrict__ support,
+                             const uint8_t* __restrict__ mask, int n, int A, int atoms,
+                             float epsilon, uint64_t seed, uint64_t step,
+                             int32_t* __restrict__ actions, float* __restrict__ q_out) {
+  const int lane = threadIdx.x & 31;
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (g >= n) return;
+  const uint8_t* m = mask + (int64_t)g * A;
+  const uint64_t bits = policy_bits(seed, step, (uint64_t)g);
+  const float u = (float)(bits >> 40) * (1.0f / 16777216.0f);
+  int n_legal = 0;
+  for (int a = lane; a < A; a += 32) n_legal += m[a] != 0;
+  n_legal = __reduce_add_sync(kFull, n_legal);
+  if (n_legal == 0) { if (lane == 0) actions[g] = -1; return; }
+  const bool explore = (u <= epsilon && epsilon > 0.0f);
+  int choice = -1;
+  if (explore && q_out == nullptr) {
+    int k = (int)(((bits & 0xffffffffull) * (uint64_t)n_legal) >> 32);
+    for (int a = 0; a < A; ++a)
+      if (m[a] != 0 && k-- == 0) { choice = a; break; }
+  } else {
+    float best = -CUDART_INF_F;
+    for (int a = 0; a < A; ++a) {
+      const bool legal = m[a] != 0;
+      if (!legal && q_out == nullptr) continue;  // warp-uniform: skip the read entirely
+      const float* row = logits + ((int64_t)g * A + a) * atoms;
+      float mx = -CUDART_INF_F;
+      for (int i = lane; i < atoms; i += 32) mx = fmaxf(mx, row[i]);
+      mx = warp_max(mx);
+      float se = 0.f, sw = 0.f;
+      for (int i = lane; i < atoms; i += 32) {
+        const float e = expf(row[i] - mx);
+        se += e;
+        sw += e * support[i];
+      }
+      se = warp_sum(se);
+      sw = warp_sum(sw);
+      const float qa = sw / se;
+      if (q_out && lane == 0) q_out[(int64_t)g * A + a] = qa;
+      if (legal && (choice < 0 || qa > best)) { best = qa; choice = a; }
+    }
+    if (explore) {
+      int k = (int)(((bits & 0xffffffffull) * (uint64_t)n_legal) >> 32);
+      choice = -1;
+      for (int a = 0; a < A; ++a)
+        if (m[a] != 0 && k-- == 0) { choice = a; break; }
+    }
+  }
+  if (lane == 0) actions[g] = choice;
+}
+
+// project_distribution, one warp per batch row, op for op in fp32:
+//   clip(supports, vmin, vmax) -> |.-z_i| -> 1 - x/dz -> clip[0,1] -> * w -> sum_j (index order)
+__device__ __forceinline__ void project_row(const float* s_sup, const float* s_w, const float* z,
+                                            int N, float* out_row, int lane) {
+  const float vmin = z[0], vmax = z[N - 1];
+  const float dz = z[1] - z[0];
+  for (int i = lane; i < N; i += 32) {
+    const float zi = z[i];
+    float acc = 0.f;
+    for (int j = 0; j < N; ++j) {
+      const float sj = fminf(fmaxf(s_sup[j], vmin), vmax);
+      const float quotient = __fsub_rn(1.0f, __fdiv_rn(fabsf(__fsub_rn(sj, zi)), dz));
+      const float cq = fminf(fmaxf(quotient, 0.0f), 1.0f);
+      acc = __fadd_rn(acc, __fmul_rn(cq, s_w[j]));
+    }
+    out_row[i] = acc;
+  }
+}
+
+__global__ void k_project(const float* __restrict__ supports, const float* __restrict__ weights,
+                          const float* __restrict__ z, float* __restrict__ out, int B, int N) {
+  extern __shared__ float sm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  float* s_sup = sm + (size_t)warp * 2 * N;
+  float* s_w = s_sup + N;
+  if (b >= B) return;
+  for (int j = lane; j < N; j += 32) {
+    s_sup[j] = supports[(int64_t)b * N + j];
+    s_w[j] = weights[(int64_t)b * N + j];
+  }
+  __syncwarp();
+  project_row(s_sup, s_w, z, N, out + (int64_t)b * N, lane);
+}
+
+// _build_target_distribution: softmax(next logits) -> q -> masked argmax ->
+// gather that action's probabilities -> supports = r + gamma^n (1 - terminal) z
+// -> projection.  One warp per batch row, nothing round-trips through HBM.
+__global__ void k_c51_target(const float* __restrict__ rewards, const uint8_t* __restrict__ terminals,
+                             const float* __restrict__ next_logits,
+                             const uint8_t* __restrict__ next_mask, const float* __restrict__ z,
+                             float cumulative_gamma, float* __restrict__ out,
+                             int32_t* __restrict__ argmax_out, int B, int A, int N) {
+  extern __shared__ float sm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  float* s_sup = sm + (size_t)warp * 2 * N;
+  float* s_w = s_sup + N;
+  if (b >= B) return;
+  const uint8_t* m = next_mask + (int64_t)b * A;
+  int choice = -1;
+  float best = -CUDART_INF_F;
+  for (int a = 0; a < A; ++a) {
+    if (m[a] == 0) continue;
+    const float* row = next_logits + ((int64_t)b * A + a) * N;
+    float mx = -CUDART_INF_F;
+    for (int i = lane; i < N; i += 32) mx = fmaxf(mx, row[i]);
+    mx = warp_max(mx);
+    float se = 0.f, sw = 0.f;
+    for (int i = lane; i < N; i += 32) {
+      const float e = expf(row[i] - mx);
+      se += e;
+      sw += e * z[i];
+    }
+    se = warp_sum(se);
+    sw = warp_sum(sw);
+    const float qa = sw / se;
+    if (choice < 0 || qa > best) { best = qa; choice = a; }
+  }
+  if (choice < 0) choice = 0;  // no legal next action (terminal rows): any row, gamma term is 0
+  if (argmax_out && lane == 0) argmax_out[b] = choice;
+  {
+    const float* row = next_logits + ((int64_t)b * A + choice) * N;
+    float mx = -CUDART_INF_F;
+    for (int i = lane; i < N; i += 32) mx = fmaxf(mx, row[i]);
+    mx = warp_max(mx);
+    float se = 0.f;
+    for (int i = lane; i < N; i += 32) se += expf(row[i] - mx);
+    se = warp_sum(se);
+    const float g = cumulative_gamma * (1.0f - (terminals[b] ? 1.0f : 0.0f));
+    const float r = rewards[b];
+    for (int i = lane; i < N; i += 32) {
+      s_w[i] = expf(row[i] - mx) / se;
+      s_sup[i] = r + g * z[i];
+    }
+  }
+  __syncwarp();
+  project_row(s_sup, s_w, z, N, out + (int64_t)b * N, lane);
+}
+
+}  // namespace hbp
+
+int HbFail(const std::string& msg);  // hb_batch.cu
+namespace {
+int PFail(const std::string& s) { return HbFail(s); }
+}  // namespace
+
+extern "C" {
+
+int BatchSelectAction(const float* q_or_logits, int num_atoms, const float* support,
+                      const uint8_t* mask, int n, int num_actions, float epsilon, uint64_t seed,
+                      uint64_t step, int32_t* actions, void* stream) {
+  if (!mask || !actions) return PFail("BatchSelectAction: mask/actions is null");
+  if (n <= 0 || num_actions <= 0) return PFail("BatchSelectAction: bad sizes");
+  if (!q_or_logits && epsilon < 1.0f) return PFail("BatchSelectAction: values are required unless epsilon >= 1");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (num_atoms <= 0 || !q_or_logits) {
+    hbp::k_select_q<<<(n + 255) / 256, 256, 0, s>>>(q_or_logits, mask, n, num_actions,
+                                                   q_or_logits ? epsilon : 2.0f, seed, step, actions);
+  } else {
+    if (!support) return PFail("BatchSelectAction: support is null");
+    const int64_t threads = (int64_t)n * 32;
+    hbp::k_select_c51<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(
+        q_or_logits, support, mask, n, num_actions, num_atoms, epsilon, seed, step, actions, nullptr);
+  }
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : PFail(std::string("BatchSelectAction: ") + cudaGetErrorString(e));
+}
+
+// C51 q-values q[n, A] = sum_i support_i softmax(logits[n, a, :])_i (all actions).
+int BatchC51QValues(const float* logits, const float* support, const uint8_t* mask, int n,
+                    int num_actions, int num_atoms, float* q_out, int32_t* greedy_actions,
+                    void* stream) {
+  if (!logits || !support || !mask || !q_out || !greedy_actions) return PFail("BatchC51QValues: null argument");
+  const int64_t threads = (int64_t)n * 32;
+  hbp::k_select_c51<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      logits, support, mask, n, num_actions, num_atoms, 0.0f, 0, 0, greedy_actions, q_out);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : PFail(std::string("BatchC51QValues: ") + cudaGetErrorString(e));
+}
+
+int BatchProjectDistribution(const float* supports, const float* weights,
+                             const float* target_support, float* out, int batch, int num_dims,
+                             void* stream) {
+  if (!supports || !weights || !target_support || !out) return PFail("BatchProjectDistribution: null argument");
+  if (batch <= 0 || num_dims < 2) return PFail("BatchProjectDistribution: need batch > 0 and num_dims >= 2");
+  const int warps = 4;
+  const size_t smem = (size_t)warps * 2 * num_dims * sizeof(float);
+  if (smem > 48 * 1024) return PFail("BatchProjectDistribution: num_dims too large");
+  hbp::k_project<<<(batch + warps - 1) / warps, warps * 32, smem, (cudaStream_t)stream>>>(
+      supports, weights, target_support, out, batch, num_dims);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : PFail(std::string("BatchProjectDistribution: ") + cudaGetErrorString(e));
+}
+
+int BatchC51TargetDistribution(const float* rewards, const uint8_t* terminals,
+                               const float* next_logits, const uint8_t* next_legal_mask,
+                               const float* support, float cumulative_gamma, float* out,
+                               int32_t* next_argmax, int batch, int num_actions, int num_atoms,
+                               void* stream) {
+  if (!rewards || !terminals || !next_logits || !next_legal_mask || !support || !out)
+    return PFail("BatchC51TargetDistribution: null argument");
+  if (batch <= 0 || num_atoms < 2) return PFail("BatchC51TargetDistribution: bad sizes");
+  const int warps = 4;
+  const size_t smem = (size_t)warps * 2 * num_atoms * sizeof(float);
+  if (smem > 48 * 1024) return PFail("BatchC51TargetDistribution: num_atoms too large");
+  hbp::k_c51_target<<<(batch + warps - 1) / warps, warps * 32, smem, (cudaStream_t)stream>>>(
+      rewards, terminals, next_logits, next_legal_mask, support, cumulative_gamma, out, next_argmax,
+      batch, num_actions, num_atoms);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : PFail(std::string("BatchC51TargetDistribution: ") + cudaGetErrorString(e));
+}
+
+}  // extern "C"

@@ -1,0 +1,92 @@
+// hb_spec.h -- game rule parameters shared by host and device code.
+//
+// Mirrors the parameter surface of the reference's HanabiGame constructor
+// (hanabi_learning_environment/hanabi_lib/hanabi_game.cc:29-67): same keys,
+// same defaults, same bounds.  Section lengths follow
+// hanabi_lib/canonical_encoders.cc:52-55,107-112,169,213-223,340-343,423-431 and
+// MaxMoves follows hanabi_lib/hanabi_game.cc:69-72.
+#ifndef HB_SPEC_H_
+#define HB_SPEC_H_
+
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define HB_HD __host__ __device__ __forceinline__
+#else
+#define HB_HD inline
+#endif
+
+namespace hb {
+
+constexpr int kMaxPlayers = 5;
+constexpr int kMaxColors = 5;
+constexpr int kMaxRanks = 5;
+constexpr int kMaxHand = 5;      // packed layout: 6-bit card slots, 5-bit knowledge slots
+constexpr int kMaxInfo = 31;     // 5-bit field
+constexpr int kMaxLife = 15;     // 4-bit field
+constexpr int kMtN = 624;
+constexpr int kMtM = 397;
+
+// Observation types, hanabi_lib/hanabi_game.h:39.
+enum ObsType { kMinimal = 0, kCardKnowledge = 1, kSeer = 2 };
+// Last-action move kinds in the order the encoder one-hots them
+// (hanabi_lib/canonical_encoders.cc:258-269), not the HanabiMove::Type enum order.
+enum LaType { kLaPlay = 0, kLaDiscard = 1, kLaRevealColor = 2, kLaRevealRank = 3 };
+
+struct Spec {
+  int32_t P, C, R, H, IT, LT;
+  int32_t obs_type, random_start;
+  int32_t deck_max, per_color, bits_per_card;
+  int32_t obs_size, max_moves;
+  int32_t hands_len, board_len, discard_len, last_len, know_len;
+};
+
+HB_HD int InstancesOfRank(int R, int rank) {  // hanabi_game.cc:126-136
+  return rank == 0 ? 3 : (rank == R - 1 ? 1 : 2);
+}
+// Bit offset of rank r inside one colour's discard thermometer block.
+HB_HD int DiscardRankOffset(int rank) { return rank == 0 ? 0 : 2 * rank + 1; }
+
+// Fills the derived fields.  Returns 0 on success, else an error code whose
+// text hb::SpecError() returns.
+inline int FinishSpec(Spec* s) {
+  if (s->P < 2 || s->P > kMaxPlayers) return 1;
+  if (s->C < 1 || s->C > kMaxColors) return 2;
+  if (s->R < 1 || s->R > kMaxRanks) return 3;
+  if (s->H < 1 || s->H > kMaxHand) return 4;
+  if (s->IT < 0 || s->IT > kMaxInfo) return 5;
+  if (s->LT < 1 || s->LT > kMaxLife) return 6;
+  if (s->obs_type < 0 || s->obs_type > 2) return 7;
+  s->per_color = 0;
+  for (int r = 0; r < s->R; ++r) s->per_color += InstancesOfRank(s->R, r);
+  s->deck_max = s->per_color * s->C;
+  if (s->H * s->P > s->deck_max) return 8;
+  s->bits_per_card = s->C * s->R;
+  s->hands_len = (s->P - 1) * s->H * s->bits_per_card + s->P;
+  s->board_len = s->deck_max - s->P * s->H + s->C * s->R + s->IT + s->LT;
+  s->discard_len = s->deck_max;
+  s->last_len = s->P + 4 + s->P + s->C + s->R + s->H + s->H + s->bits_per_card + 2;
+  s->know_len = s->P * s->H * (s->bits_per_card + s->C + s->R);
+  s->obs_size = s->hands_len + s->board_len + s->discard_len + s->last_len +
+                (s->obs_type == kMinimal ? 0 : s->know_len);
+  s->max_moves = 2 * s->H + (s->P - 1) * s->C + (s->P - 1) * s->R;
+  return 0;
+}
+
+inline const char* SpecError(int code) {
+  switch (code) {
+    case 0: return "ok";
+    case 1: return "players must be in [2,5] (hanabi_game.cc:33)";
+    case 2: return "colors must be in [1,5] (hanabi_game.cc:35)";
+    case 3: return "ranks must be in [1,5] (hanabi_game.cc:37)";
+    case 4: return "hand_size must be in [1,5] for the packed batch layout";
+    case 5: return "max_information_tokens must be in [0,31] for the packed batch layout";
+    case 6: return "max_life_tokens must be in [1,15] for the packed batch layout";
+    case 7: return "observation_type must be 0 (minimal), 1 (card knowledge) or 2 (seer)";
+    case 8: return "hand_size * players exceeds the deck (hanabi_game.cc:58)";
+    default: return "bad game parameters";
+  }
+}
+
+}  // namespace hb
+#endif  // HB_SPEC_H_

@@ -1,0 +1,158 @@
+// include/pyhanabi.h -- C-ABI of the B200-native batched Hanabi engine.
+//
+// Drop-in replacement for the reference's
+// hanabi_learning_environment/pyhanabi.h (the file its cffi binding text-parses,
+// hanabi_learning_environment/pyhanabi.py:42-74): the same single
+// `extern "C" { ... } /* extern "C" */` block of plain C declarations, loaded in
+// cffi ABI mode, extended with the batched entry points ("Batch*") that replace
+// the per-game hot path
+//   StateApplyMove / StateDealRandomCard / StateLegalMoves / StateScore /
+//   StateEndOfGameStatus / NewObservation / EncodeObservation
+//   (reference pyhanabi.h:115,117,127,130,125,157,189; driven one game at a time
+//    from rl_env.HanabiEnv.step, rl_env.py:343-366)
+// for thousands of games per call.
+//
+// Conventions of the batched block
+//   * int status: 0 = ok, non-zero = failure, text from BatchLastError()
+//     (the reference aborts on bad input, hanabi_lib/util.h:53-61; a batch must
+//     not take the process down for one bad game).
+//   * Every pointer argument is DEVICE memory owned by the caller (e.g. a torch
+//     tensor's data_ptr()) unless the comment says "host".  `stream` is a
+//     cudaStream_t (torch.cuda.current_stream().cuda_stream) or NULL; calls are
+//     asynchronous on it.
+//   * Game i uses its own std::mt19937 stream seeded with seeds[i], exactly like
+//     one reference HanabiGame per environment (hanabi_lib/hanabi_game.cc:48-51,
+//     hanabi_lib/hanabi_game.h:114); episodes of a slot continue that stream.
+//   * Move uids are the reference's (hanabi_lib/hanabi_game.cc:79-95,154-183).
+//   * An illegal action leaves that game unchanged (reward 0, done 0) and sets
+//     its error flag instead of aborting (hanabi_lib/hanabi_state.cc:222).
+//   * There is no CPU fallback: without a CUDA device NewBatch fails.
+
+#ifndef __PYHANABI_H__
+#define __PYHANABI_H__
+
+/* C++ header, like the reference's: everything between the two marker lines
+ * below must stay plain C declarations (no preprocessor lines) because the cffi
+ * binding feeds that text to ffi.cdef(). */
+#include <stdint.h>
+
+extern "C" {
+
+/* ===== batched engine (new) ============================================== */
+
+typedef struct PyHanabiBatch {
+  /* Points to the device-resident batch of games. */
+  void* batch;
+} pyhanabi_batch_t;
+
+/* Same key/value parameter list as NewGame (reference pyhanabi.h:142,
+ * pyhanabi.cc:514-526; keys hanabi_lib/hanabi_game.cc:29-47) except "seed":
+ * seeds is a HOST array of num_games int32. */
+int NewBatch(pyhanabi_batch_t* batch, int list_length, const char** param_list,
+             int num_games, int device, const int32_t* seeds);
+void DeleteBatch(pyhanabi_batch_t* batch);
+const char* BatchLastError(void);
+
+int BatchObservationSize(pyhanabi_batch_t* batch); /* ObservationShape, pyhanabi.h:187 */
+int BatchMaxMoves(pyhanabi_batch_t* batch);        /* MaxMoves, pyhanabi.h:154 */
+int BatchNumGames(pyhanabi_batch_t* batch);
+int BatchNumPlayers(pyhanabi_batch_t* batch);      /* NumPlayers, pyhanabi.h:144 */
+int BatchDevice(pyhanabi_batch_t* batch);
+
+/* rl_env.HanabiEnv.reset (rl_env.py:210-217) for the games with which[i] != 0
+ * (NULL = all): new initial state, cards dealt until a player is to act. */
+int BatchReset(pyhanabi_batch_t* batch, const uint8_t* which, void* stream);
+
+/* rl_env.HanabiEnv.step (rl_env.py:343-366) for every game: apply move uid
+ * actions[i], deal, reward = score delta, done = IsTerminal; with auto_reset a
+ * finished game is re-dealt in the same call.  rewards/dones/scores may be NULL. */
+int BatchStep(pyhanabi_batch_t* batch, const int32_t* actions, int32_t* rewards,
+              uint8_t* dones, int32_t* scores, int auto_reset, void* stream);
+
+/* CanonicalObservationEncoder::Encode (hanabi_lib/canonical_encoders.cc:433-451)
+ * of every game for `observer` (-1 = the player to act), one byte per bit into
+ * obs[i * row_pitch + j].  row_pitch == BatchObservationSize gives the dense
+ * learner input and the fastest (128-bit store) path. */
+int BatchEncode(pyhanabi_batch_t* batch, int observer, uint8_t* obs,
+                int64_t row_pitch, void* stream);
+
+/* HanabiState::LegalMoves of the player to act (hanabi_lib/hanabi_state.cc:288-304)
+ * as mask[i * BatchMaxMoves + uid] = 1 if legal else 0. */
+int BatchLegalMask(pyhanabi_batch_t* batch, uint8_t* mask, void* stream);
+int BatchCurPlayer(pyhanabi_batch_t* batch, int32_t* cur_player, void* stream);
+/* BatchEncode + BatchLegalMask + BatchCurPlayer in one launch; any output may be NULL. */
+int BatchObserve(pyhanabi_batch_t* batch, int observer, uint8_t* obs,
+                 int64_t row_pitch, uint8_t* mask, int32_t* cur_player, void* stream);
+
+/* The fused hot path: BatchStep followed by the next player's observation,
+ * legal mask and index, one kernel.  Outputs may be NULL. */
+int BatchStepEncode(pyhanabi_batch_t* batch, const int32_t* actions, int32_t* rewards,
+                    uint8_t* dones, uint8_t* obs, int64_t row_pitch, uint8_t* mask,
+                    int32_t* cur_player, int auto_reset, void* stream);
+int BatchStepEncodeScores(pyhanabi_batch_t* batch, const int32_t* actions,
+                          int32_t* rewards, uint8_t* dones, int32_t* scores, uint8_t* obs,
+                          int64_t row_pitch, uint8_t* mask, int32_t* cur_player,
+                          int auto_reset, void* stream);
+
+/* Checkpoint / restore of the whole batch including every game's RNG stream
+ * (HOST blobs of BatchStateBytes bytes). */
+int64_t BatchStateBytes(pyhanabi_batch_t* batch);
+int BatchGetState(pyhanabi_batch_t* batch, void* host_blob, int64_t nbytes);
+int BatchSetState(pyhanabi_batch_t* batch, const void* host_blob, int64_t nbytes);
+
+/* Inspection / injection of game states as int32[num_games][272] device arrays
+ * (field layout in DESIGN.md; the accessors StateFireworks, StateGetHandCard,
+ * ... of reference pyhanabi.h:118-131 in bulk).  extra = int32[num_games][2]
+ * {turns_to_play, packed last action} or NULL. */
+int BatchUnpackState(pyhanabi_batch_t* batch, int32_t* dump, void* stream);
+int BatchPackState(pyhanabi_batch_t* batch, const int32_t* dump, const int32_t* extra,
+                   void* stream);
+
+/* Episode statistics {episodes, sum score, sum length, histogram[26]} as 32
+ * int64, accumulated on the device by every step; dev_stats is a caller-owned
+ * device buffer (to be all-reduced over NCCL) or NULL for the internal one. */
+int BatchSetStatsBuffer(pyhanabi_batch_t* batch, int64_t* dev_stats);
+int BatchReadStats(pyhanabi_batch_t* batch, int64_t* host_stats, int clear, void* stream);
+
+/* ===== fused actor / learner kernels on the same batch ==================== */
+
+/* Legal-mask-aware epsilon-greedy (DQNAgent._select_action,
+ * agents/rainbow_copy/dqn_agent.py:387-420): with probability epsilon a uniform
+ * legal move, else argmax_a(q[a] + legal[a]) with the first maximal index
+ * (dqn_agent.py:200).  num_atoms == 0: q_or_logits is q[n][num_actions];
+ * num_atoms > 0: logits[n][num_actions][num_atoms] of a C51 head and
+ * q[a] = sum_i support[i] * softmax(logits[a,:])[i] (rainbow_agent.py:163-172).
+ * mask[n][num_actions] is 1 for legal moves.  q_or_logits may be NULL when
+ * epsilon >= 1 (uniform random legal policy).  Randomness is a counter-based
+ * generator keyed (seed, step, game). */
+int BatchSelectAction(const float* q_or_logits, int num_atoms, const float* support,
+                      const uint8_t* mask, int n, int num_actions, float epsilon,
+                      uint64_t seed, uint64_t step, int32_t* actions, void* stream);
+int BatchC51QValues(const float* logits, const float* support, const uint8_t* mask, int n,
+                    int num_actions, int num_atoms, float* q_out, int32_t* greedy_actions,
+                    void* stream);
+/* project_distribution (agents/rainbow_copy/rainbow_agent.py:252-404):
+ * supports[batch][num_dims], weights[batch][num_dims], target_support[num_dims]
+ * -> out[batch][num_dims], fp32. */
+int BatchProjectDistribution(const float* supports, const float* weights,
+                             const float* target_support, float* out, int batch,
+                             int num_dims, void* stream);
+/* _build_target_distribution (rainbow_agent.py:181-213) fused: softmax of the
+ * target net's next_logits[batch][num_actions][num_atoms], masked argmax,
+ * supports = rewards + cumulative_gamma * (1 - terminals) * support, projection.
+ * next_argmax may be NULL. */
+int BatchC51TargetDistribution(const float* rewards, const uint8_t* terminals,
+                               const float* next_logits, const uint8_t* next_legal_mask,
+                               const float* support, float cumulative_gamma, float* out,
+                               int32_t* next_argmax, int batch, int num_actions,
+                               int num_atoms, void* stream);
+
+/* Test hooks. */
+int BatchSetDebug(pyhanabi_batch_t* batch, int sampler_mode, int generic);
+int BatchDebugDeal(pyhanabi_batch_t* batch, const uint64_t* decks, const int32_t* sizes,
+                   const uint32_t* lo, const uint32_t* hi, int n, int mode,
+                   int32_t* out_type, int32_t* out_ambiguous, void* stream);
+
+} /* extern "C" */
+
+#endif

@@ -1,0 +1,262 @@
+"""GPU parity tests: the CUDA engine, called through the C-ABI (cffi), against the
+CPU oracle on identical seeds and move sequences.  Bit-exact: observation bytes,
+legal masks, rewards, done flags, scores, current player and the whole unpacked
+state."""
+import functools
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests import common
+from tests.common import CONFIGS, GpuBatch
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def traces():
+  return np.load(os.path.join(GOLDEN, "rl_env_traces.npz"))
+
+
+def _checker(params, n, seeds):
+  """The unmodified reference where it was built, else the C restatement."""
+  return O.CpuBatch("ref" if O.have_ref() else "oracle", params, n, seeds)
+
+
+@pytest.mark.parametrize("name", sorted(CONFIGS))
+def test_gpu_replays_reference_rl_env_traces(traces, name):
+  for seed in (1234, 7):
+    common.replay_golden(GpuBatch, traces, name, seed)
+
+
+@pytest.mark.parametrize("name", sorted(CONFIGS))
+def test_random_policy_lockstep(name):
+  n = 1000  # not a multiple of 32: exercises the ragged last tile
+  seeds = common.seeds_for(n, base=1)
+  cpu = _checker(CONFIGS[name], n, seeds)
+  gpu = GpuBatch(CONFIGS[name], n, seeds)
+  cpu.reset(); gpu.reset()
+  eps, _ = common.lockstep(cpu, gpu, 96, np.random.default_rng(10), False, CONFIGS[name],
+                           dump_every=16, check_all_observers_every=32)
+  assert eps > 100
+
+
+@pytest.mark.parametrize("name", ["full2", "full4", "full5", "small2", "seer3", "dealt_out"])
+def test_keep_alive_policy_lockstep(name):
+  n = 256
+  seeds = common.seeds_for(n, base=9000)
+  cpu = _checker(CONFIGS[name], n, seeds)
+  gpu = GpuBatch(CONFIGS[name], n, seeds)
+  cpu.reset(); gpu.reset()
+  eps, max_score = common.lockstep(cpu, gpu, 300, np.random.default_rng(11), True, CONFIGS[name],
+                                   dump_every=20, check_all_observers_every=50)
+  assert eps > 0
+  if name == "full2":
+    assert max_score >= 15
+
+
+def test_full2_at_survey_size():
+  """SURVEY.md section 8d parity run: 4096 games x 256 steps, Hanabi-Full 2p."""
+  n = 4096
+  seeds = common.seeds_for(n, base=1)
+  cpu = O.CpuBatch("oracle", CONFIGS["full2"], n, seeds)
+  gpu = GpuBatch(CONFIGS["full2"], n, seeds)
+  cpu.reset(); gpu.reset()
+  rng = np.random.default_rng(12)
+  eps = 0
+  for t in range(256):
+    mask = cpu.legal_mask()
+    keep = (t // 64) % 2 == 1
+    if t % 8 == 0:
+      common.assert_same(mask, gpu.legal_mask(), "mask @%d" % t)
+      common.assert_same(cpu.encode(), gpu.encode(), "obs @%d" % t)
+    if t % 64 == 0:
+      common.assert_same(cpu.dump(), gpu.dump(), "dump @%d" % t)
+    dump = cpu.dump() if keep else None
+    actions = common.choose_actions(dump, mask, rng, False, 5, 5) if not keep else \
+        common.choose_actions(dump, mask, rng, True, 5, 5)
+    ra, rb = cpu.step(actions), gpu.step(actions)
+    for k, w in enumerate(("reward", "done", "score")):
+      common.assert_same(ra[k], rb[k], "%s @%d" % (w, t))
+    eps += int(ra[1].sum())
+  common.assert_same(cpu.dump(), gpu.dump(), "final dump")
+  assert eps > 10000
+
+
+@pytest.mark.parametrize("name", ["full2", "full5", "ppo_sweep"])
+def test_split_kernels_and_padded_pitch(name):
+  """BatchStep + BatchObserve (unfused) and obs rows with a 16-byte padded pitch
+  and with an odd pitch give the same bytes as the fused dense path."""
+  n = 200
+  seeds = common.seeds_for(n, base=77)
+  cpu = O.CpuBatch("oracle", CONFIGS[name], n, seeds)
+  cpu.reset()
+  obs_size = cpu.obs_size
+  variants = [GpuBatch(CONFIGS[name], n, seeds, fused=False),
+              GpuBatch(CONFIGS[name], n, seeds, pitch=(obs_size + 15) // 16 * 16 + 16),
+              GpuBatch(CONFIGS[name], n, seeds, pitch=obs_size + 3)]
+  for g in variants:
+    g.reset()
+  rng = np.random.default_rng(13)
+  for t in range(40):
+    mask = cpu.legal_mask()
+    want = cpu.encode()
+    for g in variants:
+      common.assert_same(want, g.encode(), "obs @%d" % t)
+      common.assert_same(mask, g.legal_mask(), "mask @%d" % t)
+      if g.pitch != obs_size:  # padding bytes must be left untouched
+        assert (g.t_obs.cpu().numpy()[:, obs_size:] == 7).all()
+    actions = common.choose_actions(None, mask, rng, False, 5, 5)
+    ra = cpu.step(actions)
+    for g in variants:
+      rb = g.step(actions)
+      common.assert_same(ra[0], rb[0], "reward")
+      common.assert_same(ra[1], rb[1], "done")
+
+
+@pytest.mark.parametrize("name", ["full2", "small4"])
+def test_generic_kernels_and_exact_sampler(name):
+  """The runtime-parameter kernels (used for rule sets without a static
+  instantiation) and the always-exact fp64 sampler reproduce the same games."""
+  n = 160
+  seeds = common.seeds_for(n, base=31)
+  cpu = O.CpuBatch("oracle", CONFIGS[name], n, seeds)
+  gen = GpuBatch(CONFIGS[name], n, seeds)
+  gen.b.set_debug(sampler_mode=0, generic=True)
+  exact = GpuBatch(CONFIGS[name], n, seeds)
+  exact.b.set_debug(sampler_mode=1, generic=False)
+  cpu.reset(); gen.reset(); exact.reset()
+  rng = np.random.default_rng(14)
+  for t in range(80):
+    mask = cpu.legal_mask()
+    want = cpu.encode()
+    for g in (gen, exact):
+      common.assert_same(want, g.encode(), "obs @%d" % t)
+      common.assert_same(mask, g.legal_mask(), "mask @%d" % t)
+    actions = common.choose_actions(None, mask, rng, False, 5, 5)
+    ra = cpu.step(actions)
+    for g in (gen, exact):
+      rb = g.step(actions)
+      common.assert_same(ra[0], rb[0], "reward")
+      common.assert_same(ra[1], rb[1], "done")
+  common.assert_same(cpu.dump(), gen.dump(), "dump (generic kernels)")
+  common.assert_same(cpu.dump(), exact.dump(), "dump (exact sampler)")
+
+
+def test_deal_sampler_at_boundaries():
+  """Fast integer sampler + exact fallback vs libstdc++ (via oracle/_ref) or the
+  C restatement, at and around every cumulative-probability boundary."""
+  import torch
+  from tests.test_oracle import adversarial_draws
+  cases = adversarial_draws(np.random.default_rng(6), n_random=20000)
+  kind = "ref" if O.have_ref() else "oracle"
+  want = np.asarray([O.deal_from_counts(kind, c, lo, hi) for c, lo, hi in cases], np.int32)
+  decks = np.zeros(len(cases), np.uint64)
+  for k in range(25):
+    decks |= np.asarray([int(c[k]) for c, _, _ in cases], np.uint64) << np.uint64(2 * k)
+  sizes = np.asarray([int(c.sum()) for c, _, _ in cases], np.int32)
+  lo = np.asarray([c[1] for c in cases], np.uint32)
+  hi = np.asarray([c[2] for c in cases], np.uint32)
+  g = GpuBatch(CONFIGS["full2"], 32, common.seeds_for(32))
+  dev = g.b.device
+  t = lambda a: torch.as_tensor(a.view(np.int64) if a.dtype == np.uint64 else a.view(np.int32),
+                                device=dev)
+  for mode in (0, 1):
+    got, amb = g.b.debug_deal(t(decks), t(sizes), t(lo), t(hi), mode)
+    common.assert_same(want, got.cpu().numpy(), "deal sampler mode %d" % mode)
+  assert int(amb.sum()) > 1000  # the boundary cases do take the exact fallback
+  fast, _ = g.b.debug_deal(t(decks), t(sizes), t(lo), t(hi), 2)
+  clear = amb.cpu().numpy() == 0
+  common.assert_same(want[clear], fast.cpu().numpy()[clear], "fast path outside the guard band")
+
+
+def test_reference_golden_vector_on_gpu():
+  import torch
+  from tests.test_oracle import _fixture_dump
+  fix = json.load(open(os.path.join(GOLDEN, "gui_fixture_2p.json")))
+  g = GpuBatch(CONFIGS["full2"], 1, [1])
+  g.reset()
+  dump = torch.as_tensor(_fixture_dump(fix)[None, :], device=g.b.device)
+  extra = torch.as_tensor(np.asarray([[2, 0]], np.int32), device=g.b.device)
+  g.b.pack_state(dump, extra)
+  for p in range(2):
+    want = np.asarray(fix["players"][p]["vectorized"], np.uint8)
+    common.assert_same(want, g.encode(p)[0], "golden vector of player %d" % p)
+  g._fresh = False
+  assert np.flatnonzero(g.legal_mask()[0]).tolist() == fix["players"][0]["legal_moves_as_int"]
+  common.assert_same(_fixture_dump(fix)[:6], g.dump()[0][:6], "dump header")
+
+
+def test_state_roundtrip_and_determinism():
+  """BatchGetState/BatchSetState restore games AND their RNG streams."""
+  n = 300
+  p = CONFIGS["full3"]
+  g = GpuBatch(p, n, common.seeds_for(n, base=5))
+  g.reset()
+  rng = np.random.default_rng(15)
+  for _ in range(20):
+    g.step(common.choose_actions(None, g.legal_mask(), rng, False, 5, 5))
+  blob = g.b.get_state()
+  script = []
+  for _ in range(30):
+    a = common.choose_actions(None, g.legal_mask(), rng, False, 5, 5)
+    script.append((a, g.step(a), g.encode().copy()))
+  g.b.set_state(blob)
+  g._fresh = False
+  for a, res, obs in script:
+    got = g.step(a)
+    common.assert_same(res[0], got[0], "reward after restore")
+    common.assert_same(res[1], got[1], "done after restore")
+    common.assert_same(obs, g.encode(), "obs after restore")
+
+
+def test_no_auto_reset_illegal_actions_and_partial_reset():
+  import torch
+  n = 100
+  p = CONFIGS["small2"]
+  seeds = common.seeds_for(n, base=3)
+  cpu = O.CpuBatch("oracle", p, n, seeds)
+  gpu = GpuBatch(p, n, seeds)
+  cpu.reset(); gpu.reset()
+  common.lockstep(cpu, gpu, 50, np.random.default_rng(16), False, p, auto_reset=False)
+  r = gpu.step(np.zeros(n, np.int32), auto_reset=False)
+  assert r[1].all() and (r[0] == 0).all()
+  which = (np.arange(n) % 3 == 0).astype(np.uint8)
+  cpu.reset(which); gpu.reset(which)
+  common.assert_same(cpu.dump(), gpu.dump(), "dump after partial reset")
+  cpu.reset(); gpu.reset()
+  before = gpu.dump()
+  bad = np.full(n, 999, np.int32)
+  r = gpu.step(bad)
+  assert (r[0] == 0).all() and (r[1] == 0).all()
+  common.assert_same(before, gpu.dump(), "illegal actions leave the games unchanged")
+  del torch
+
+
+def test_episode_statistics():
+  n = 512
+  p = CONFIGS["small2"]
+  seeds = common.seeds_for(n, base=21)
+  cpu = O.CpuBatch("oracle", p, n, seeds)
+  gpu = GpuBatch(p, n, seeds)
+  cpu.reset(); gpu.reset()
+  gpu.b.read_stats(clear=True)
+  rng = np.random.default_rng(17)
+  episodes = score_sum = 0
+  hist = np.zeros(26, np.int64)
+  for _ in range(60):
+    a = common.choose_actions(None, cpu.legal_mask(), rng, False, 5, 2)
+    r = cpu.step(a)
+    gpu.step(a)
+    d = r[1] != 0
+    episodes += int(d.sum())
+    score_sum += int(r[2][d].sum())
+    np.add.at(hist, r[2][d], 1)
+  st = gpu.b.read_stats()
+  assert st["episodes"] == episodes and st["score_sum"] == score_sum
+  assert st["score_hist"] == hist.tolist()
+  assert st["length_sum"] > episodes
