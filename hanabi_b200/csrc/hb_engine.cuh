@@ -682,11 +682,20 @@ HB_DEV void expand_tile(const uint32_t* rows, int stride, int dim, uint8_t* out,
     while (o >= dim) { o -= dim; ++g; }
     const int dq = 512 / dim, dr = 512 - dq * dim;
     for (int k = lane; k < full_chunks; k += 32) {
-      const int avail = dim - o;
+      // 16 output bytes = 16 consecutive bits of the tile's bit stream; they may
+      // straddle rows (several rows when dim < 16, e.g. an 11-move legal mask).
       uint32_t bits = row_bits16(rows + g * stride, o, words);
-      if (avail < 16) {
-        bits &= (1u << avail) - 1u;
-        bits |= (rows[(g + 1) * stride] << avail) & 0xffffu;
+      int filled = dim - o;
+      if (filled < 16) {
+        bits &= (1u << filled) - 1u;
+        int gg = g + 1;
+        do {
+          uint32_t nxt = row_bits16(rows + gg * stride, 0, words);
+          if (dim < 16) nxt &= (1u << dim) - 1u;
+          bits |= (nxt << filled) & 0xffffu;
+          filled += dim;
+          ++gg;
+        } while (filled < 16);
       }
       uint4 val;
       val.x = nibble_to_bytes(bits);
