@@ -1,0 +1,346 @@
+#!/usr/bin/env python
+"""bench.py -- Hanabi env-steps/sec (step + encode + legal mask) on B200.
+
+A "step" is one pass of the hot path over one batch of games: every game takes
+one move of a uniform-random-legal policy (BatchSelectAction, counter-based RNG
+keyed (7, step, game)), the move is applied, cards are dealt from the game's own
+mt19937 stream, finished games are re-dealt (auto-reset), and the next player's
+canonical observation (uint8 [games, obs_dim]), legal mask, reward, done flag
+and player index are written (BatchStepEncode).  Workload = BASELINE.json
+configs[0]/north_star: Hanabi-Full 2-player, 658-dim observation.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--games G] [--impl reference]
+
+One process per GPU; under torchrun the ranks shard the games (no collective on
+the step path) and one tiny NCCL all-reduce aggregates the episode statistics.
+Rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "hanabi_full_2p": dict(players=2),
+    "hanabi_full_4p": dict(players=4),
+    "hanabi_full_5p": dict(players=5),
+    "hanabi_small_2p": dict(players=2, colors=2, ranks=5, hand_size=2, max_information_tokens=3,
+                            max_life_tokens=1),
+}
+# Algorithmic bytes per env-step (SURVEY.md section 8d / BASELINE.md section 4):
+# obs_dim + A (uint8 mask) + 4 (reward) + 1 (done) + 4 (action) + 2 * S (packed state r+w).
+ALGO_BYTES = {"hanabi_full_2p": 815, "hanabi_full_4p": 1248, "hanabi_full_5p": 1529,
+              "hanabi_small_2p": 255}
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only without MEASURED_PEAKS.json
+
+
+def parse_args():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--gpus", type=int, default=1)
+  ap.add_argument("--steps", type=int, default=2000)
+  ap.add_argument("--warmup", type=int, default=100)
+  ap.add_argument("--games", type=int, default=1 << 20, help="games per GPU")
+  ap.add_argument("--workload", default="hanabi_full_2p", choices=sorted(WORKLOADS))
+  ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+  ap.add_argument("--e2e-steps", type=int, default=12)
+  ap.add_argument("--e2e-games", type=int, default=1 << 18)
+  ap.add_argument("--cpu-seconds", type=float, default=12.0)
+  ap.add_argument("--no-cpu-baseline", action="store_true")
+  return ap.parse_args()
+
+
+# ------------------------------------------------------------ clock sampling
+class ClockSampler(object):
+  """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+  def __init__(self, index):
+    self.samples = []
+    self.reasons = set()
+    self.max_mhz = None
+    self._stop = threading.Event()
+    self._thread = None
+    try:
+      import pynvml
+      pynvml.nvmlInit()
+      self.nv = pynvml
+      self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+      self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+    except Exception:  # pylint: disable=broad-except
+      self.nv = None
+
+  def _sample(self):
+    nv = self.nv
+    try:
+      self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+      r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+      names = {
+          "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+          "hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+          "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+          "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+          "hw_power_brake_slowdown": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80),
+      }
+      for name, bit in names.items():
+        if r & bit:
+          self.reasons.add(name)
+    except Exception:  # pylint: disable=broad-except
+      pass
+
+  def start(self):
+    if self.nv is None:
+      return
+    def run():
+      while not self._stop.is_set():
+        self._sample()
+        time.sleep(0.004)
+    self._thread = threading.Thread(target=run, daemon=True)
+    self._thread.start()
+
+  def stop(self):
+    if self.nv is None:
+      return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+    self._sample()
+    self._stop.set()
+    if self._thread:
+      self._thread.join()
+    s = sorted(self.samples)
+    return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz,
+            "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# --------------------------------------------------------------- CPU baseline
+def cpu_reference_rate(workload, seconds, threads=None):
+  """Times the reference's own CPU engine (oracle/_ref, unmodified sources) -- or
+  the C port when it was not built -- on this box's host cores: random-legal
+  rollout with auto-reset, current-player observation + legal mask per step."""
+  import numpy as np
+  from oracle import oracle as O
+  threads = threads or os.cpu_count() or 1
+  kind = "ref" if O.have_ref() else "oracle"
+  if kind == "oracle":
+    threads = 1
+  n = 512 * threads
+  b = O.CpuBatch(kind, WORKLOADS[workload], n, (np.arange(n) + 1).astype(np.int32))
+  b.reset()
+  t0 = time.perf_counter()
+  b.rollout(8, threads)  # warm-up + calibration
+  per_pass = max((time.perf_counter() - t0) / 8, 1e-6)
+  steps = max(8, int(seconds / per_pass))
+  t0 = time.perf_counter()
+  total, episodes, score_sum = b.rollout(steps, threads)
+  dt = time.perf_counter() - t0
+  return {"value": total / dt, "unit": "env-steps/s", "cores": threads,
+          "kind": "reference" if kind == "ref" else "port",
+          "sample": "%d games x %d steps, random-legal policy, auto-reset, %.1f s" % (n, steps, dt)}
+
+
+def run_reference_arm(args, rank):
+  """--impl reference: the reference's CPU implementation of the path, all host threads."""
+  if rank != 0:
+    return
+  import numpy as np
+  from oracle import oracle as O
+  threads = os.cpu_count() or 1
+  kind = "ref" if O.have_ref() else "oracle"
+  if kind == "oracle":
+    threads = 1
+  n = 256 * threads  # bounded sample of the workload per step
+  b = O.CpuBatch(kind, WORKLOADS[args.workload], n, (np.arange(n) + 1).astype(np.int32))
+  b.reset()
+  steps = min(args.steps, 4000)
+  b.rollout(max(args.warmup, 3), threads)
+  t0 = time.perf_counter()
+  total, _, _ = b.rollout(steps, threads)
+  dt = time.perf_counter() - t0
+  value = total / dt
+  sample = "%d games x %d steps per run (bounded sample of %s), random-legal policy" % (
+      n, steps, args.workload)
+  line = {
+      "impl": "reference", "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s",
+      "n_gpus": args.gpus, "steps": steps, "warmup": max(args.warmup, 3),
+      "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+      "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+      "config": {"workload": args.workload, "games_per_step": n, "policy": "uniform random legal",
+                 "note": "reference C++ engine (oracle/_ref) on host cores"},
+      "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": threads,
+                       "kind": "reference" if kind == "ref" else "port", "sample": sample},
+      "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0,
+              "d2h_bytes_per_step": 0},
+      "gpu_launches": 0,
+  }
+  print(json.dumps(line), flush=True)
+
+
+# -------------------------------------------------------------------- GPU arm
+def main():
+  args = parse_args()
+  rank = int(os.environ.get("RANK", "0"))
+  local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+  world = int(os.environ.get("WORLD_SIZE", "1"))
+  if args.impl == "reference":
+    run_reference_arm(args, rank)
+    return
+
+  import numpy as np
+  import torch
+  from hanabi_b200 import pyhanabi as ph
+
+  if not torch.cuda.is_available():
+    raise SystemExit("bench.py needs a CUDA device; the engine has no CPU fallback")
+  torch.cuda.set_device(local_rank)
+  dev = torch.device("cuda", local_rank)
+  dist = None
+  if world > 1:
+    import torch.distributed as dist
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    dist.init_process_group("nccl", device_id=dev)
+
+  params = WORKLOADS[args.workload]
+  n = args.games
+  seeds = (np.arange(n, dtype=np.int64) + 1 + rank * n).astype(np.int32)  # seed_i = 1 + global index
+  batch = ph.HanabiBatch(params, n, seeds, device=local_rank)
+  D, A = batch.obs_size, batch.max_moves
+  obs = torch.empty((n, D), dtype=torch.uint8, device=dev)
+  mask = torch.empty((n, A), dtype=torch.uint8, device=dev)
+  cur = torch.empty(n, dtype=torch.int32, device=dev)
+  rew = torch.empty(n, dtype=torch.int32, device=dev)
+  done = torch.empty(n, dtype=torch.uint8, device=dev)
+  act = torch.empty(n, dtype=torch.int32, device=dev)
+  stats = torch.zeros(32, dtype=torch.int64, device=dev)
+  batch.set_stats_buffer(stats)
+  batch.reset()
+  batch.observe(obs, mask, cur)
+
+  def one_step(t):
+    ph.select_action(None, mask, 1.0, seed=7, step=t, out=act)
+    batch.step_encode(act, rew, done, obs, mask, cur)
+
+  W = max(args.warmup, 3)
+  K = args.steps
+  for t in range(W):
+    one_step(t)
+  stats.zero_()
+  torch.cuda.synchronize()
+  if dist:
+    dist.barrier()
+    torch.cuda.synchronize()
+
+  sampler = ClockSampler(local_rank)
+  ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(K)]
+  sampler.start()
+  ev0.record()
+  for t in range(K):
+    ph.select_action(None, mask, 1.0, seed=7, step=W + t, out=act)
+    k_ev[t][0].record()
+    batch.step_encode(act, rew, done, obs, mask, cur)
+    k_ev[t][1].record()
+  if dist:
+    dist.all_reduce(stats)  # the only collective: 256 bytes of episode statistics
+  ev1.record()
+  torch.cuda.synchronize()
+  clocks = sampler.stop()
+  elapsed_ms = ev0.elapsed_time(ev1)
+  kernel_ms = sum(a.elapsed_time(b) for a, b in k_ev) / K
+  if dist:
+    tmax = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(tmax.item())
+    dist.barrier()
+  value = world * n * K / (elapsed_ms * 1e-3)
+
+  # ---- e2e: the same step through the C-ABI with HOST buffers (pinned); the
+  # timed region holds the host policy, the action upload, the kernel and the
+  # download of observation, mask, reward, done and player index.
+  ne = min(args.e2e_games, n)
+  e2e = None
+  if args.e2e_steps > 0:
+    hb = ph.HanabiBatch(params, ne, seeds[:ne], device=local_rank)
+    pin = lambda *shape, dt: torch.empty(shape, dtype=dt).pin_memory()
+    h_obs, h_mask = pin(ne, D, dt=torch.uint8), pin(ne, A, dt=torch.uint8)
+    h_cur, h_rew = pin(ne, dt=torch.int32), pin(ne, dt=torch.int32)
+    h_done, h_act = pin(ne, dt=torch.uint8), pin(ne, dt=torch.int32)
+    hb.reset_host(h_obs, h_mask, h_cur)
+    gen = torch.Generator().manual_seed(7 + rank)
+
+    def host_policy():
+      # uniform random legal move per game on the host (torch CPU ops)
+      w = torch.rand((ne, A), generator=gen) * h_mask + h_mask
+      h_act.copy_(w.argmax(dim=1).to(torch.int32))
+
+    def host_step():
+      host_policy()
+      hb.step_encode_host(h_act, h_rew, h_done, h_obs, h_mask, h_cur)
+
+    for _ in range(3):
+      host_step()
+    if dist:
+      dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+      host_step()
+    dt = time.perf_counter() - t0
+    if dist:
+      tm = torch.tensor([dt], dtype=torch.float64, device=dev)
+      dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+      dt = float(tm.item())
+    e2e = {"value": world * ne * args.e2e_steps / dt, "unit": "env-steps/s",
+           "h2d_bytes_per_step": ne * 4, "d2h_bytes_per_step": ne * (D + A + 4 + 1 + 4),
+           "games_per_step": ne, "steps": args.e2e_steps,
+           "note": "BatchStepEncodeHost with pinned host buffers; host random-legal policy inside "
+                   "the timed region"}
+    del hb
+
+  if rank != 0:
+    if dist:
+      dist.destroy_process_group()
+    return
+
+  peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+  if os.path.exists(peaks_path):
+    peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+  else:
+    peak, peak_src = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+  algo = ALGO_BYTES[args.workload]
+  achieved = algo * n / (kernel_ms * 1e-3) / 1e9
+  traffic = None
+  tpath = os.path.join(ROOT, "profiles", "traffic.json")
+  if os.path.exists(tpath):
+    tj = json.load(open(tpath))
+    if tj.get("workload") == args.workload and tj.get("games") == n:
+      traffic = tj.get("dram_bytes_per_launch")
+  st = stats.cpu().tolist()
+  line = {
+      "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world,
+      "steps": K, "warmup": W, "ms_per_step": elapsed_ms / K, "higher_is_better": True,
+      "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+      "config": {"workload": args.workload, "games_per_gpu": n, "obs_dim": D, "num_moves": A,
+                 "policy": "uniform random legal (BatchSelectAction, epsilon=1)",
+                 "auto_reset": True, "seeds": "1 + global game index",
+                 "l2": "outputs per step (%.0f MB) exceed the 126 MB L2" % (n * (D + A) / 1e6),
+                 "parallelism": "games sharded over %d GPU(s), no step-path collective" % world},
+      "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                   "frac": achieved / peak, "traffic": traffic, "kernel": "k_main<step>",
+                   "kernel_ms": kernel_ms, "algorithmic_bytes_per_env_step": algo,
+                   "peak_source": peak_src},
+      "e2e": e2e,
+      "gpu_launches": 2 * K,
+      "clocks": clocks,
+      "episodes": {"count": st[0], "mean_score": st[1] / max(st[0], 1),
+                   "mean_length": st[2] / max(st[0], 1)},
+  }
+  if not args.no_cpu_baseline:
+    line["cpu_baseline"] = cpu_reference_rate(args.workload, args.cpu_seconds)
+  print(json.dumps(line), flush=True)
+  if dist:
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+  main()

@@ -29,6 +29,7 @@ struct KArgs {
   uint4* state;
   uint32_t* mt;
   int64_t N;
+  int64_t g_begin, g_end;  // range of games this launch covers (g_begin % 32 == 0)
   uint64_t full_deck;
   const int32_t* actions;
   const uint8_t* which;
@@ -52,14 +53,14 @@ __global__ void __launch_bounds__(kBlock) k_main(const __grid_constant__ KArgs a
   __shared__ int s_stats[kNumStats];
   const V v(a.spec);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t g = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  const int64_t g = a.g_begin + (int64_t)blockIdx.x * kBlock + threadIdx.x;
   const int64_t tile0 = g - lane;  // first game of this warp's tile
-  const bool valid = g < a.N;
+  const bool valid = g < a.g_end;
   if (MODE == kModeStep) {
     if (threadIdx.x < kNumStats) s_stats[threadIdx.x] = 0;
     __syncthreads();
   }
-  if (tile0 >= a.N) {
+  if (tile0 >= a.g_end) {
     if (MODE == kModeStep) __syncthreads();
     return;
   }
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(kBlock) k_main(const __grid_constant__ KArgs a
   if (valid && a.cur_player) a.cur_player[g] = G.cur;
   if (valid && MODE != kModeObserve) store_game(a.state, a.N, g, v, G);
 
-  const int n_valid = (int)((a.N - tile0) < 32 ? (a.N - tile0) : 32);
+  const int n_valid = (int)((a.g_end - tile0) < 32 ? (a.g_end - tile0) : 32);
   uint32_t* obs_rows = smem + (size_t)warp * 32 * (a.obs_stride + kMaskStride);
   uint32_t* mask_rows = obs_rows + 32 * a.obs_stride;
   if (a.obs) {
@@ -310,8 +311,14 @@ struct Batch {
   // pinned/pipelined host path
   cudaStream_t h_streams[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t h_events[3] = {nullptr, nullptr, nullptr};
-  void* d_host_stage = nullptr;
-  size_t d_host_stage_bytes = 0;
+  // device staging for the host-buffer entry point, allocated on first use
+  int32_t* d_actions = nullptr;
+  int32_t* d_rewards = nullptr;
+  int32_t* d_scores = nullptr;
+  int32_t* d_cur = nullptr;
+  uint8_t* d_dones = nullptr;
+  uint8_t* d_obs = nullptr;
+  uint8_t* d_mask = nullptr;
 };
 
 struct DeviceGuard {
@@ -363,6 +370,8 @@ hb::KArgs BaseArgs(const Batch* b) {
   a.state = b->state;
   a.mt = b->mt;
   a.N = b->N;
+  a.g_begin = 0;
+  a.g_end = b->N;
   a.full_deck = b->full_deck;
   a.stats = b->stats;
   a.sampler_mode = b->sampler_mode;
@@ -373,7 +382,8 @@ hb::KArgs BaseArgs(const Batch* b) {
 
 template <class V, int MODE>
 cudaError_t LaunchOne(const Batch* b, const hb::KArgs& a, cudaStream_t stream) {
-  const unsigned grid = (unsigned)((b->N + hb::kBlock - 1) / hb::kBlock);
+  const unsigned grid = (unsigned)((a.g_end - a.g_begin + hb::kBlock - 1) / hb::kBlock);
+  (void)b;
   hb::k_main<V, MODE><<<grid, hb::kBlock, b->smem_bytes, stream>>>(a);
   return cudaGetLastError();
 }
@@ -476,7 +486,8 @@ void DeleteBatch(pyhanabi_batch_t* h) {
     if (b->h_streams[i]) cudaStreamDestroy(b->h_streams[i]);
     if (b->h_events[i]) cudaEventDestroy(b->h_events[i]);
   }
-  cudaFree(b->d_host_stage);
+  cudaFree(b->d_actions); cudaFree(b->d_rewards); cudaFree(b->d_scores); cudaFree(b->d_cur);
+  cudaFree(b->d_dones); cudaFree(b->d_obs); cudaFree(b->d_mask);
   cudaFree(b->state);
   cudaFree(b->mt);
   cudaFree(b->own_stats);
@@ -583,6 +594,95 @@ int BatchStepEncodeScores(pyhanabi_batch_t* h, const int32_t* actions, int32_t* 
   a.obs = obs; a.obs_pitch = row_pitch; a.mask = mask; a.cur_player = cur_player;
   a.auto_reset = auto_reset;
   HB_CUDA(Launch<hb::kModeStep>(b, a, (cudaStream_t)stream));
+  return 0;
+}
+
+// The fused hot path with HOST buffers (pinned memory recommended): the games
+// are cut into chunks that flow through three internal streams so that the
+// action upload, the kernel and the result download of neighbouring chunks
+// overlap.  Synchronous: the host buffers are complete on return.  `stream` is
+// the stream whose earlier work on this batch must finish first (may be NULL).
+int BatchStepEncodeHost(pyhanabi_batch_t* h, const int32_t* actions, int32_t* rewards,
+                        uint8_t* dones, int32_t* scores, uint8_t* obs, int64_t row_pitch,
+                        uint8_t* mask, int32_t* cur_player, int auto_reset, void* stream) {
+  HB_BATCH(h);
+  if (!actions) return Fail("BatchStepEncodeHost: actions is null");
+  if (obs && row_pitch < b->spec.obs_size) return Fail("BatchStepEncodeHost: row_pitch smaller than the observation");
+  const size_t N = (size_t)b->N;
+  const int D = b->spec.obs_size, A = b->spec.max_moves;
+  if (!b->h_streams[0]) {
+    for (int i = 0; i < 3; ++i) {
+      HB_CUDA(cudaStreamCreateWithFlags(&b->h_streams[i], cudaStreamNonBlocking));
+      HB_CUDA(cudaEventCreateWithFlags(&b->h_events[i], cudaEventDisableTiming));
+    }
+    HB_CUDA(cudaMalloc(&b->d_actions, N * sizeof(int32_t)));
+    HB_CUDA(cudaMalloc(&b->d_rewards, N * sizeof(int32_t)));
+    HB_CUDA(cudaMalloc(&b->d_scores, N * sizeof(int32_t)));
+    HB_CUDA(cudaMalloc(&b->d_cur, N * sizeof(int32_t)));
+    HB_CUDA(cudaMalloc(&b->d_dones, N));
+    HB_CUDA(cudaMalloc(&b->d_obs, N * (size_t)D));
+    HB_CUDA(cudaMalloc(&b->d_mask, N * (size_t)A));
+  }
+  HB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  int nchunks = (int)((N + 32767) / 32768);
+  if (nchunks > 12) nchunks = 12;
+  if (nchunks < 1) nchunks = 1;
+  size_t cs = (N + nchunks - 1) / nchunks;
+  cs = (cs + 127) / 128 * 128;
+  int c = 0;
+  for (size_t g0 = 0; g0 < N; g0 += cs, ++c) {
+    const size_t g1 = g0 + cs < N ? g0 + cs : N;
+    const size_t n = g1 - g0;
+    cudaStream_t s = b->h_streams[c % 3];
+    HB_CUDA(cudaMemcpyAsync(b->d_actions + g0, actions + g0, n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    hb::KArgs a = BaseArgs(b);
+    a.g_begin = (int64_t)g0; a.g_end = (int64_t)g1;
+    a.actions = b->d_actions; a.rewards = b->d_rewards; a.dones = b->d_dones; a.scores = b->d_scores;
+    a.obs = obs ? b->d_obs : nullptr; a.obs_pitch = D; a.mask = mask ? b->d_mask : nullptr;
+    a.cur_player = b->d_cur; a.auto_reset = auto_reset;
+    HB_CUDA(Launch<hb::kModeStep>(b, a, s));
+    if (obs) {
+      if (row_pitch == D)
+        HB_CUDA(cudaMemcpyAsync(obs + g0 * (size_t)D, b->d_obs + g0 * (size_t)D, n * (size_t)D, cudaMemcpyDeviceToHost, s));
+      else
+        HB_CUDA(cudaMemcpy2DAsync(obs + g0 * (size_t)row_pitch, (size_t)row_pitch, b->d_obs + g0 * (size_t)D,
+                                  (size_t)D, (size_t)D, n, cudaMemcpyDeviceToHost, s));
+    }
+    if (mask) HB_CUDA(cudaMemcpyAsync(mask + g0 * (size_t)A, b->d_mask + g0 * (size_t)A, n * (size_t)A, cudaMemcpyDeviceToHost, s));
+    if (rewards) HB_CUDA(cudaMemcpyAsync(rewards + g0, b->d_rewards + g0, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    if (dones) HB_CUDA(cudaMemcpyAsync(dones + g0, b->d_dones + g0, n, cudaMemcpyDeviceToHost, s));
+    if (scores) HB_CUDA(cudaMemcpyAsync(scores + g0, b->d_scores + g0, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    if (cur_player) HB_CUDA(cudaMemcpyAsync(cur_player + g0, b->d_cur + g0, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  }
+  for (int i = 0; i < 3; ++i) HB_CUDA(cudaStreamSynchronize(b->h_streams[i]));
+  return 0;
+}
+
+// rl_env.HanabiEnv.reset with HOST result buffers (observation, legal mask and
+// current player of every game after the deal).  Synchronous.
+int BatchResetHost(pyhanabi_batch_t* h, uint8_t* obs, int64_t row_pitch, uint8_t* mask,
+                   int32_t* cur_player, void* stream) {
+  HB_BATCH(h);
+  const size_t N = (size_t)b->N;
+  const int D = b->spec.obs_size, A = b->spec.max_moves;
+  if (obs && row_pitch < D) return Fail("BatchResetHost: row_pitch smaller than the observation");
+  cudaStream_t s = (cudaStream_t)stream;
+  uint8_t *d_obs = nullptr, *d_mask = nullptr;
+  int32_t* d_cur = nullptr;
+  hb::KArgs a = BaseArgs(b);
+  HB_CUDA(Launch<hb::kModeReset>(b, a, s));
+  if (obs) HB_CUDA(cudaMallocAsync(&d_obs, N * (size_t)D, s));
+  if (mask) HB_CUDA(cudaMallocAsync(&d_mask, N * (size_t)A, s));
+  if (cur_player) HB_CUDA(cudaMallocAsync(&d_cur, N * sizeof(int32_t), s));
+  a.obs = d_obs; a.obs_pitch = D; a.mask = d_mask; a.cur_player = d_cur;
+  HB_CUDA(Launch<hb::kModeObserve>(b, a, s));
+  if (obs) HB_CUDA(cudaMemcpy2DAsync(obs, (size_t)row_pitch, d_obs, (size_t)D, (size_t)D, N, cudaMemcpyDeviceToHost, s));
+  if (mask) HB_CUDA(cudaMemcpyAsync(mask, d_mask, N * (size_t)A, cudaMemcpyDeviceToHost, s));
+  if (cur_player) HB_CUDA(cudaMemcpyAsync(cur_player, d_cur, N * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  if (d_obs) HB_CUDA(cudaFreeAsync(d_obs, s));
+  if (d_mask) HB_CUDA(cudaFreeAsync(d_mask, s));
+  if (d_cur) HB_CUDA(cudaFreeAsync(d_cur, s));
+  HB_CUDA(cudaStreamSynchronize(s));
   return 0;
 }
 

@@ -236,6 +236,46 @@ class HanabiBatch(object):
         self._p(cur_player, torch.int32, n, "int32_t*"), int(bool(auto_reset)), self._stream()),
            "BatchStepEncodeScores")
 
+  # -- host-buffer verbs (CPU tensors, ideally pinned); synchronous
+  def _h(self, t, dtype, numel, ctype):
+    if t is None:
+      return ffi.NULL
+    if t.is_cuda or t.dtype != dtype or not t.is_contiguous() or t.numel() < numel:
+      raise ValueError("expected a contiguous CPU tensor of dtype %s with >= %d elements" %
+                       (dtype, numel))
+    return ffi.cast(ctype, t.data_ptr())
+
+  def _h_obs(self, obs):
+    if obs is None:
+      return ffi.NULL, 0
+    torch = self._torch
+    if (obs.is_cuda or obs.dtype != torch.uint8 or obs.dim() != 2 or obs.stride(1) != 1 or
+        obs.shape[0] < self.num_games or obs.shape[1] < self.obs_size):
+      raise ValueError("obs must be a CPU uint8 [num_games, >=obs_size] tensor")
+    return ffi.cast("uint8_t*", obs.data_ptr()), int(obs.stride(0))
+
+  def step_encode_host(self, actions, rewards=None, dones=None, obs=None, mask=None,
+                       cur_player=None, scores=None, auto_reset=True):
+    torch = self._torch
+    n = self.num_games
+    optr, pitch = self._h_obs(obs)
+    _check(lib.BatchStepEncodeHost(
+        self._c, self._h(actions, torch.int32, n, "int32_t*"),
+        self._h(rewards, torch.int32, n, "int32_t*"), self._h(dones, torch.uint8, n, "uint8_t*"),
+        self._h(scores, torch.int32, n, "int32_t*"), optr, pitch,
+        self._h(mask, torch.uint8, n * self.max_moves, "uint8_t*"),
+        self._h(cur_player, torch.int32, n, "int32_t*"), int(bool(auto_reset)), self._stream()),
+           "BatchStepEncodeHost")
+
+  def reset_host(self, obs=None, mask=None, cur_player=None):
+    torch = self._torch
+    n = self.num_games
+    optr, pitch = self._h_obs(obs)
+    _check(lib.BatchResetHost(self._c, optr, pitch,
+                              self._h(mask, torch.uint8, n * self.max_moves, "uint8_t*"),
+                              self._h(cur_player, torch.int32, n, "int32_t*"), self._stream()),
+           "BatchResetHost")
+
   # -- state I/O
   def state_bytes(self):
     return int(lib.BatchStateBytes(self._c))

@@ -94,6 +94,17 @@ int BatchStepEncodeScores(pyhanabi_batch_t* batch, const int32_t* actions,
                           int64_t row_pitch, uint8_t* mask, int32_t* cur_player,
                           int auto_reset, void* stream);
 
+/* The same two verbs with HOST buffers (pinned memory recommended), for callers
+ * that keep their data on the CPU like the reference's trainers do: uploads the
+ * actions, runs the fused kernel and downloads the results, chunked over
+ * internal streams so copies and compute overlap.  Synchronous.  Any output
+ * may be NULL. */
+int BatchStepEncodeHost(pyhanabi_batch_t* batch, const int32_t* actions, int32_t* rewards,
+                        uint8_t* dones, int32_t* scores, uint8_t* obs, int64_t row_pitch,
+                        uint8_t* mask, int32_t* cur_player, int auto_reset, void* stream);
+int BatchResetHost(pyhanabi_batch_t* batch, uint8_t* obs, int64_t row_pitch, uint8_t* mask,
+                   int32_t* cur_player, void* stream);
+
 /* Checkpoint / restore of the whole batch including every game's RNG stream
  * (HOST blobs of BatchStateBytes bytes). */
 int64_t BatchStateBytes(pyhanabi_batch_t* batch);
