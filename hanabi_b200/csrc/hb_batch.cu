@@ -20,7 +20,7 @@ namespace hb {
 
 enum Mode { kModeStep = 0, kModeReset = 1, kModeObserve = 2 };
 constexpr int kBlock = 128;
-constexpr int kMaskStride = 3;   // words per lane for the legal-mask bit row
+constexpr int kStreamPad = 2;    // readable pad words after each packed bit stream
 constexpr int kNumStats = 32;    // [0] episodes [1] sum score [2] sum length [3..28] score histogram
 constexpr int kDumpLen = 272;    // canonical unpacked state, see oracle/oracle_api.h
 
@@ -30,7 +30,6 @@ struct KArgs {
   uint32_t* mt;
   int64_t N;
   int64_t g_begin, g_end;  // range of games this launch covers (g_begin % 32 == 0)
-  uint64_t full_deck;
   const int32_t* actions;
   const uint8_t* which;
   int32_t* rewards;
@@ -44,7 +43,7 @@ struct KArgs {
   int auto_reset;
   int sampler_mode;
   int observer;
-  int obs_stride;  // words per lane of the observation bit row (odd)
+  int warp_smem_words;  // shared-memory words per warp: obs stream + mask stream + pads
 };
 
 template <class V, int MODE>
@@ -95,8 +94,10 @@ __global__ void __launch_bounds__(kBlock) k_main(const __grid_constant__ KArgs a
         }
       }
     }
-    deal_loop(v, a.spec, G, moved, term && a.auto_reset, g, a.mt, a.full_deck, lane,
-              a.sampler_mode);
+    // the deal that follows a play/discard (also for a game that just ended: the
+    // reference deals before it looks at IsTerminal), then the re-deal of finished games
+    deal_loop(v, a.spec, G, moved, false, g, a.mt, lane, a.sampler_mode);
+    restart_games(v, a.spec, G, term && a.auto_reset, g, a.mt, lane, a.sampler_mode);
     if (valid) {
       if (term && !a.auto_reset) G.done = 1;
       if (a.rewards) a.rewards[g] = reward;
@@ -119,31 +120,27 @@ __global__ void __launch_bounds__(kBlock) k_main(const __grid_constant__ KArgs a
   } else if (MODE == kModeReset) {
     const bool restart = valid && (a.which == nullptr || a.which[g] != 0);
     if (restart) { G.done = 0; G.err = 0; }
-    deal_loop(v, a.spec, G, restart, restart, g, a.mt, a.full_deck, lane, a.sampler_mode);
+    restart_games(v, a.spec, G, restart, g, a.mt, lane, a.sampler_mode);
   }
 
   if (valid && a.cur_player) a.cur_player[g] = G.cur;
   if (valid && MODE != kModeObserve) store_game(a.state, a.N, g, v, G);
 
   const int n_valid = (int)((a.g_end - tile0) < 32 ? (a.g_end - tile0) : 32);
-  uint32_t* obs_rows = smem + (size_t)warp * 32 * (a.obs_stride + kMaskStride);
-  uint32_t* mask_rows = obs_rows + 32 * a.obs_stride;
+  uint32_t* obs_stream = smem + (size_t)warp * a.warp_smem_words;
+  uint32_t* mask_stream = obs_stream + a.spec.obs_size + kStreamPad;
   if (a.obs) {
     const int observer = a.observer < 0 ? G.cur : a.observer;
-    encode_obs(v, a.spec, G, observer, obs_rows + lane * a.obs_stride);
+    encode_obs(v, a.spec, G, observer, obs_stream, lane);
   }
-  if (a.mask) {
-    const uint64_t lb = legal_bits(v, G);
-    mask_rows[lane * kMaskStride] = (uint32_t)lb;
-    mask_rows[lane * kMaskStride + 1] = (uint32_t)(lb >> 32);
-  }
+  if (a.mask) pack_mask_stream(mask_stream, a.spec.max_moves, legal_bits(v, G), valid, lane);
   __syncwarp();
   if (a.obs)
-    expand_tile(obs_rows, a.obs_stride, a.spec.obs_size, a.obs + tile0 * a.obs_pitch, a.obs_pitch,
-                n_valid, lane);
+    expand_stream(obs_stream, a.spec.obs_size, a.obs + tile0 * a.obs_pitch, a.obs_pitch, n_valid,
+                  lane);
   if (a.mask)
-    expand_tile(mask_rows, kMaskStride, a.spec.max_moves, a.mask + tile0 * a.spec.max_moves,
-                a.spec.max_moves, n_valid, lane);
+    expand_stream(mask_stream, a.spec.max_moves, a.mask + tile0 * a.spec.max_moves,
+                  a.spec.max_moves, n_valid, lane);
 
   if (MODE == kModeStep) {
     __syncthreads();
@@ -205,9 +202,10 @@ __global__ void k_unpack(KArgs a, int32_t* out) {
   for (int c = 0; c < C; ++c)
     for (int r = 0; r < R; ++r) {
       const int k = c * R + r;
-      d[216 + k] = (int)((G.deck >> (2 * k)) & 3);
       const int off = c * a.spec.per_color + DiscardRankOffset(r);
-      d[241 + k] = __popcll((G.disc >> off) & ((1ull << InstancesOfRank(R, r)) - 1ull));
+      const uint64_t bm = (1ull << InstancesOfRank(R, r)) - 1ull;
+      d[216 + k] = __popcll((G.deck >> off) & bm);
+      d[241 + k] = __popcll((G.disc >> off) & bm);
     }
 }
 
@@ -243,8 +241,8 @@ __global__ void k_pack(KArgs a, const int32_t* in, const int32_t* extra) {
   for (int c = 0; c < C; ++c)
     for (int r = 0; r < R; ++r) {
       const int k = c * R + r;
-      G.deck |= (uint64_t)d[216 + k] << (2 * k);
       const int off = c * a.spec.per_color + DiscardRankOffset(r);
+      G.deck |= ((1ull << d[216 + k]) - 1ull) << off;
       G.disc |= ((1ull << d[241 + k]) - 1ull) << off;
     }
   G.turns = extra ? extra[g * 2] : a.spec.P;
@@ -254,18 +252,31 @@ __global__ void k_pack(KArgs a, const int32_t* in, const int32_t* extra) {
   store_game(a.state, a.N, g, v, G);
 }
 
-// Test hook: the deal sampler alone on caller-provided decks and RNG words.
+// Test hook: the deal sampler alone on caller-provided decks (2-bit counts per
+// card type) and RNG words.  Returns the card type colour * R + rank.
 __global__ void k_deal_test(Spec spec, const uint64_t* decks, const int32_t* sizes,
                             const uint32_t* lo, const uint32_t* hi, int n, int mode,
                             int32_t* out_type, int32_t* out_amb) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const DView v(spec);
+  uint64_t deck = 0;
+  for (int c = 0; c < spec.C; ++c)
+    for (int r = 0; r < spec.R; ++r) {
+      const int cnt = (int)((decks[i] >> (2 * (c * spec.R + r))) & 3);
+      deck |= ((1ull << cnt) - 1ull) << (c * spec.per_color + DiscardRankOffset(r));
+    }
   bool amb = false;
-  int type = pick_fast(v, decks[i], sizes[i], lo[i], hi[i], amb);
-  if (mode == 1 || (mode == 0 && amb)) type = pick_exact(v, decks[i], sizes[i], lo[i], hi[i]);
-  if (deck_types(decks[i]) < 2) type = (63 - __clzll((long long)decks[i])) >> 1;
-  out_type[i] = type;
+  int pos;
+  if (deck_types(spec, deck) < 2) {
+    pos = __ffsll((long long)deck) - 1;
+  } else {
+    pos = pick_fast(deck, sizes[i], lo[i], hi[i], amb);
+    if (mode == 1 || (mode == 0 && amb)) pos = pick_exact(v, deck, sizes[i], lo[i], hi[i]);
+  }
+  int color, rank;
+  card_of_position(v, pos, color, rank);
+  out_type[i] = color * spec.R + rank;
   if (out_amb) out_amb[i] = amb ? 1 : 0;
 }
 
@@ -303,10 +314,9 @@ struct Batch {
   uint32_t* mt = nullptr;
   unsigned long long* stats = nullptr;      // active stats buffer
   unsigned long long* own_stats = nullptr;  // library-owned fallback
-  uint64_t full_deck = 0;
   int sampler_mode = 0;
   int force_generic = 0;
-  int obs_stride = 0;
+  int warp_smem_words = 0;
   size_t smem_bytes = 0;
   // pinned/pipelined host path
   cudaStream_t h_streams[3] = {nullptr, nullptr, nullptr};
@@ -372,11 +382,10 @@ hb::KArgs BaseArgs(const Batch* b) {
   a.N = b->N;
   a.g_begin = 0;
   a.g_end = b->N;
-  a.full_deck = b->full_deck;
   a.stats = b->stats;
   a.sampler_mode = b->sampler_mode;
   a.observer = -1;
-  a.obs_stride = b->obs_stride;
+  a.warp_smem_words = b->warp_smem_words;
   return a;
 }
 
@@ -442,11 +451,8 @@ int NewBatch(pyhanabi_batch_t* out, int list_length, const char** param_list, in
   b->device = device;
   b->N = num_games;
   b->ncols = b->spec.P + 2;
-  for (int c = 0; c < b->spec.C; ++c)
-    for (int r = 0; r < b->spec.R; ++r)
-      b->full_deck |= (uint64_t)hb::InstancesOfRank(b->spec.R, r) << (2 * (c * b->spec.R + r));
-  b->obs_stride = ((b->spec.obs_size + 31) / 32) | 1;
-  b->smem_bytes = (size_t)(hb::kBlock / 32) * 32 * (b->obs_stride + hb::kMaskStride) * sizeof(uint32_t);
+  b->warp_smem_words = b->spec.obs_size + b->spec.max_moves + 2 * hb::kStreamPad;
+  b->smem_bytes = (size_t)(hb::kBlock / 32) * b->warp_smem_words * sizeof(uint32_t);
   DeviceGuard guard(device);
   if (!guard.ok) { delete b; return Fail("NewBatch: cudaSetDevice failed"); }
   int32_t* d_seeds = nullptr;

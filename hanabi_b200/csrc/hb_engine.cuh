@@ -69,8 +69,9 @@ struct DView {
 //                   y = colour-plausible masks (5-bit slots)
 //                   z = rank-plausible masks   (5-bit slots)
 //                   w = colour-hinted flags [0,8) | rank-hinted flags [8,16) | hand size [16,20)
-//   column P      : x,y = deck counts (2 bits per card type), z,w = discard thermometers
-//                   (exactly the bit layout of the encoder's discard section)
+//   column P      : x,y = deck bitmap (one bit per card instance still in the deck),
+//                   z,w = discard thermometers; both in the bit layout of the encoder's
+//                   discard section (colour-major, 3/2/.../1 bits per rank)
 //   column P + 1  : x = fireworks 5x3 | info 5 | life 4 | cur 3 | turns_to_play 3 | done | error
 //                   y = deck size 6 | mt19937 index 10 | episode length 12
 //                   z = last non-deal action record, w = spare
@@ -79,9 +80,9 @@ struct Game {
   uint32_t cpl[kMaxPlayers];
   uint32_t rpl[kMaxPlayers];
   uint32_t hw[kMaxPlayers];
-  uint64_t deck;
-  uint64_t disc;
-  uint32_t fw;  // 3 bits per colour
+  uint64_t deck;  // bit set = that card instance is still in the deck
+  uint64_t disc;  // discard thermometers
+  uint32_t fw;    // 3 bits per colour
   int info, life, cur, turns, done, err;
   int deck_size, mti, eplen;
   uint32_t last;
@@ -212,46 +213,67 @@ HB_DEV void warp_fetch_words(uint32_t* mt_all, int64_t g, int& mti, int need, in
 // The reference draws a card with libstdc++'s std::discrete_distribution over
 // doubles count/deck_size (hanabi_state.cc:277-280,313-325; hanabi_game.cc:106-112;
 // bits/random.tcc:2655-2712,3346-3385).  Mathematically that is "card number
-// floor(u * deck_size) of the type-sorted deck".  pick_fast evaluates this in
-// exact 128-bit integer arithmetic and reports `ambiguous` when u*deck_size lies
-// within 2^-32 of an integer -- the only place where fp64 rounding in the
-// reference could decide differently (its total error is < 2^-46).  Ambiguous
-// draws are re-done by pick_exact, an operation-for-operation fp64 restatement.
+// floor(u * deck_size) of the type-sorted deck".  The deck is kept as a bitmap
+// with one bit per card instance in type order, so that card is simply the
+// q-th set bit.  pick_fast evaluates q in exact 128-bit integer arithmetic and
+// reports `ambiguous` when u*deck_size lies within 2^-32 of an integer -- the
+// only place where fp64 rounding in the reference could decide differently (its
+// accumulated error is < 2^-46).  Ambiguous draws are re-done by pick_exact, an
+// operation-for-operation fp64 restatement of the library code.
 constexpr uint64_t kGuard = 1ull << 32;
 
+// Position of the q-th (0-based) set bit of x; q < popcount(x).
+HB_DEV int select64(uint64_t x, int q) {
+  uint32_t w = (uint32_t)x;
+  int pos = 0;
+  int c = __popc(w);
+  if (q >= c) { q -= c; w = (uint32_t)(x >> 32); pos = 32; }
+  c = __popc(w & 0xffffu);
+  if (q >= c) { q -= c; w >>= 16; pos += 16; }
+  c = __popc(w & 0xffu);
+  if (q >= c) { q -= c; w >>= 8; pos += 8; }
+  c = __popc(w & 0xfu);
+  if (q >= c) { q -= c; w >>= 4; pos += 4; }
+  c = __popc(w & 0x3u);
+  if (q >= c) { q -= c; w >>= 2; pos += 2; }
+  pos += (q >= (int)(w & 1u)) ? 1 : 0;
+  return pos;
+}
+
+// Deck bit position -> (colour, rank).
 template <class V>
-HB_DEV int pick_fast(V v, uint64_t deck, int deck_size, uint32_t lo, uint32_t hi, bool& ambiguous) {
+HB_DEV void card_of_position(V v, int pos, int& color, int& rank) {
+  color = pos / v.per_color();
+  const int o = pos - color * v.per_color();
+  rank = o < 3 ? 0 : (o - 1) >> 1;
+}
+
+// Returns the deck bit position of the drawn card.
+HB_DEV int pick_fast(uint64_t deck, int deck_size, uint32_t lo, uint32_t hi, bool& ambiguous) {
   const uint64_t U = ((uint64_t)hi << 32) | lo;
   const uint64_t q = __umul64hi(U, (uint64_t)deck_size);
   const uint64_t F = U * (uint64_t)deck_size;
   ambiguous = (F + kGuard) < 2 * kGuard;
-  int acc = 0, type = 0;
-  const int qi = (int)q;
-#pragma unroll
-  for (int k = 0; k < V::kC * V::kR; ++k) {
-    if (k < v.C() * v.R()) {
-      const int c = (int)((deck >> (2 * k)) & 3);
-      type = (qi >= acc && qi < acc + c) ? k : type;
-      acc += c;
-    }
-  }
-  return type;
+  return select64(deck, (int)q);
 }
 
 template <class V>
 __device__ __noinline__ int pick_exact(V v, uint64_t deck, int deck_size, uint32_t lo, uint32_t hi) {
   double w[kMaxColors * kMaxRanks];
-  int idx[kMaxColors * kMaxRanks];
+  int first_bit[kMaxColors * kMaxRanks];
   int n = 0;
-  for (int k = 0; k < v.C() * v.R(); ++k) {
-    const int c = (int)((deck >> (2 * k)) & 3);
-    if (c > 0) {
-      idx[n] = k;
-      w[n] = __ddiv_rn((double)c, (double)deck_size);
-      ++n;
+  for (int c = 0; c < v.C(); ++c)
+    for (int r = 0; r < v.R(); ++r) {
+      const int off = c * v.per_color() + DiscardRankOffset(r);
+      const uint64_t block = (deck >> off) & ((1ull << InstancesOfRank(v.R(), r)) - 1ull);
+      const int cnt = __popcll(block);
+      if (cnt > 0) {
+        first_bit[n] = off + __ffsll((long long)block) - 1;
+        w[n] = __ddiv_rn((double)cnt, (double)deck_size);
+        ++n;
+      }
     }
-  }
-  if (n < 2) return idx[0];
+  if (n < 2) return first_bit[0];
   double sum = 0.0;
   for (int k = 0; k < n; ++k) sum = __dadd_rn(sum, w[k]);
   double cp = 0.0;
@@ -266,13 +288,14 @@ __device__ __noinline__ int pick_exact(V v, uint64_t deck, int deck_size, uint32
     const double c = (k == n - 1) ? 1.0 : cp;
     if (!found && !(c < u)) { res = k; found = true; }
   }
-  return idx[res];
+  return first_bit[res];
 }
 
 // Number of distinct card types left in the deck (>= 2 means the reference
 // consumes two RNG words for the draw, else none: random.tcc:2660-2664,2696-2697).
-HB_DEV int deck_types(uint64_t deck) {
-  const uint64_t nz = (deck | (deck >> 1)) & 0x5555555555555555ull;
+HB_DEV int deck_types(const Spec& spec, uint64_t deck) {
+  const uint64_t any2 = deck | (deck >> 1);
+  const uint64_t nz = (any2 & spec.type_m23) | ((deck >> 2) & spec.type_m3) | (deck & spec.type_m1);
   return __popcll(nz);
 }
 
@@ -300,10 +323,12 @@ HB_DEV bool needs_deal(V v, const Game& G) {
   return G.deck_size > 0 && short_hand;
 }
 
-// HanabiState::ApplyMove(kDeal) for card type `type` (hanabi_state.cc:229-241).
+// HanabiState::ApplyMove(kDeal) of the card at deck position `pos`
+// (hanabi_state.cc:229-241).
 template <class V>
-HB_DEV void deal_card(V v, Game& G, int type, int obs_type) {
-  const int color = type / v.R(), rank = type - color * v.R();
+HB_DEV void deal_card(V v, Game& G, int pos, int obs_type) {
+  int color, rank;
+  card_of_position(v, pos, color, rank);
   bool placed = false;
 #pragma unroll
   for (int p = 0; p < V::kP; ++p) {
@@ -322,7 +347,7 @@ HB_DEV void deal_card(V v, Game& G, int type, int obs_type) {
       }
     }
   }
-  G.deck -= 1ull << (2 * type);
+  G.deck &= ~(1ull << pos);
   G.deck_size -= 1;
 }
 
@@ -461,10 +486,10 @@ HB_DEV void apply_move(V v, Game& G, int uid) {
 
 // Fresh game before any deal (HanabiState ctor, hanabi_state.cc:90-102).
 template <class V>
-HB_DEV void init_fresh(V v, Game& G, uint64_t full_deck, int start_player) {
+HB_DEV void init_fresh(V v, const Spec& spec, Game& G, int start_player) {
 #pragma unroll
   for (int p = 0; p < V::kP; ++p) { G.cards[p] = 0; G.cpl[p] = 0; G.rpl[p] = 0; G.hw[p] = 0; }
-  G.deck = full_deck;
+  G.deck = spec.full_deck;
   G.disc = 0;
   G.fw = 0;
   G.info = v.IT();
@@ -484,13 +509,13 @@ HB_DEV void init_fresh(V v, Game& G, uint64_t full_deck, int start_player) {
 // hanabi_game.h:114) and deal its P*H cards.
 template <class V>
 HB_DEV void deal_loop(V v, const Spec& spec, Game& G, bool active, bool restart, int64_t g,
-                      uint32_t* mt_all, uint64_t full_deck, int lane, int sampler_mode) {
+                      uint32_t* mt_all, int lane, int sampler_mode) {
   for (;;) {
     bool need = active && needs_deal(v, G);
     int fresh_need_start = 0;
     if (active && !need && restart) {
       restart = false;
-      init_fresh(v, G, full_deck, 0);
+      init_fresh(v, spec, G, 0);
       fresh_need_start = spec.random_start ? 1 : 0;
       need = needs_deal(v, G) && !fresh_need_start;
     }
@@ -510,39 +535,124 @@ HB_DEV void deal_loop(V v, const Spec& spec, Game& G, bool active, bool restart,
       }
       sp = __ballot_sync(kFull, fresh_need_start != 0);
     }
-    if (!__any_sync(kFull, need || (active && restart))) break;
-    const bool multi = need && deck_types(G.deck) >= 2;
+    if (!__any_sync(kFull, need)) break;
+    const bool multi = need && deck_types(spec, G.deck) >= 2;
     uint32_t lo = 0, hi = 0;
     warp_fetch_words(mt_all, g, G.mti, multi ? 2 : 0, lane, lo, hi);
     if (need) {
-      int type;
+      int pos;
       if (multi) {
         bool amb = false;
-        type = pick_fast(v, G.deck, G.deck_size, lo, hi, amb);
+        pos = pick_fast(G.deck, G.deck_size, lo, hi, amb);
         if (sampler_mode == 1 || (amb && sampler_mode != 2))
-          type = pick_exact(v, G.deck, G.deck_size, lo, hi);
+          pos = pick_exact(v, G.deck, G.deck_size, lo, hi);
       } else {
-        type = (63 - __clzll((long long)G.deck)) >> 1;
+        pos = __ffsll((long long)G.deck) - 1;  // one type left: no RNG words are consumed
       }
-      deal_card(v, G, type, spec.obs_type);
+      deal_card(v, G, pos, spec.obs_type);
     }
   }
 }
 
+// New game for the lanes with `restart` set, unrolled: all 2*P*H RNG words of
+// the initial deal are known to lie inside the current mt19937 block and every
+// draw is a >= 2-type draw (spec.fast_reset), so the loads are independent and
+// the P*H dependent select steps are straight-line code.  Player 0's hand is
+// filled first, then player 1's, ... (PlayerToDeal, hanabi_state.cc:157-164).
+template <class V>
+HB_DEV void reset_fast(V v, const Spec& spec, Game& G, bool restart, int64_t g, uint32_t* mt_all,
+                       int sampler_mode) {
+  if (!restart) return;
+  init_fresh(v, spec, G, 0);
+  const uint32_t* my = mt_all + g * (int64_t)kMtN + G.mti;
+  const int H = v.H();
+  uint64_t deck = G.deck;
+  int n = v.deck_max();
+  const bool seer = spec.obs_type == kSeer;
+#pragma unroll
+  for (int p = 0; p < V::kP; ++p) {
+    if (p < v.P()) {
+      uint32_t cards = 0, cpl = 0, rpl = 0;
+#pragma unroll
+      for (int i = 0; i < V::kH; ++i) {
+        if (i < H) {
+          const int r = p * H + i;
+          const uint32_t lo = mt_temper(__ldcg(my + 2 * r));
+          const uint32_t hi = mt_temper(__ldcg(my + 2 * r + 1));
+          bool amb = false;
+          int pos = pick_fast(deck, n, lo, hi, amb);
+          if (sampler_mode == 1 || (amb && sampler_mode != 2)) pos = pick_exact(v, deck, n, lo, hi);
+          int color, rank;
+          card_of_position(v, pos, color, rank);
+          cards |= (uint32_t)(color | (rank << 3)) << (6 * i);
+          cpl |= (seer ? (1u << color) : ((1u << v.C()) - 1u)) << (5 * i);
+          rpl |= (seer ? (1u << rank) : ((1u << v.R()) - 1u)) << (5 * i);
+          deck &= ~(1ull << pos);
+          --n;
+        }
+      }
+      G.cards[p] = cards;
+      G.cpl[p] = cpl;
+      G.rpl[p] = rpl;
+      const uint32_t all = (1u << H) - 1u;
+      G.hw[p] = ((uint32_t)H << 16) | (seer ? (all | (all << 8)) : 0u);
+    }
+  }
+  G.deck = deck;
+  G.deck_size = n;
+  G.mti += 2 * v.P() * H;
+}
+
+// Warp-convergent restart of the flagged lanes: the unrolled path when every
+// flagged lane qualifies, else the general deal loop.
+template <class V>
+HB_DEV void restart_games(V v, const Spec& spec, Game& G, bool restart, int64_t g,
+                          uint32_t* mt_all, int lane, int sampler_mode) {
+  if (!__any_sync(kFull, restart)) return;
+  const bool lane_ok = !restart || (G.mti + 2 * v.P() * v.H() <= kMtN);
+  if (spec.fast_reset && __all_sync(kFull, lane_ok)) {
+    reset_fast(v, spec, G, restart, g, mt_all, sampler_mode);
+  } else {
+    deal_loop(v, spec, G, restart, restart, g, mt_all, lane, sampler_mode);
+  }
+}
+
 // ------------------------------------------------------------------ encoding
-// Streaming bit writer into one shared-memory row of 32-bit words (bit j of the
-// observation is bit j & 31 of word j >> 5).  With a static view every width and
-// hence every shift is a compile-time constant.
+// A warp's 32 observations form ONE packed bit stream in shared memory: game
+// `lane` owns bits [lane*dim, (lane+1)*dim), bit j of the stream is bit j & 31 of
+// word j >> 5.  With dense output rows (pitch == dim) the stream maps 1:1 onto
+// the tile's bytes, so 16 output bytes are exactly one aligned halfword of it.
+//
+// BitWriter appends fields to the lane's slice.  Fields are first gathered into
+// 32-bit words aligned to the slice start (with a static view every width, hence
+// every shift, is a compile-time constant); each completed word is then shifted
+// by the lane's start offset s0 into stream position with one funnel shift.  A
+// stream word shared by two neighbouring slices is written by the lower lane,
+// which fetches the upper lane's contribution (`head`) with a shuffle.
 struct BitWriter {
-  uint32_t* row;
+  uint32_t* out;  // stream word that holds the first bit of this lane's slice
   uint64_t acc;
-  int nbits, wi;
-  HB_DEV explicit BitWriter(uint32_t* r) : row(r), acc(0), nbits(0), wi(0) {}
-  HB_DEV void put(uint32_t value, int width) {  // width in [0, 32]
+  uint32_t prev, head, last_sh;
+  int nbits, wi, s0;
+  HB_DEV BitWriter(uint32_t* stream, int lane, int dim) : acc(0), prev(0), head(0), last_sh(0),
+                                                           nbits(0), wi(0) {
+    const int start = lane * dim;
+    out = stream + (start >> 5);
+    s0 = start & 31;
+  }
+  HB_DEV void emit(uint32_t word) {
+    const uint32_t sh = __funnelshift_l(prev, word, s0);  // (word << s0) | (prev >> (32 - s0))
+    if (wi == 0 && s0 != 0) head = sh;  // the lower neighbour owns this word
+    else out[wi] = sh;
+    last_sh = sh;
+    prev = word;
+    ++wi;
+  }
+  HB_DEV void put(uint32_t value, int width) {  // width in [0, 32], value < 2^width
     acc |= (uint64_t)value << nbits;
     nbits += width;
     if (nbits >= 32) {
-      row[wi++] = (uint32_t)acc;
+      emit((uint32_t)acc);
       acc >>= 32;
       nbits -= 32;
     }
@@ -552,21 +662,25 @@ struct BitWriter {
     put((uint32_t)(value & ((1ull << w0) - 1ull)), w0);
     put((uint32_t)(value >> 32), width - w0);
   }
-  HB_DEV void zeros(int width) {
-    while (width > 32) { put(0u, 32); width -= 32; }
-    put(0u, width);
-  }
-  HB_DEV void flush() {
-    if (nbits > 0) row[wi++] = (uint32_t)acc;
+  // Ends the slice (dim bits were put).  Must be reached by all 32 lanes.
+  HB_DEV void finish(int lane, int dim) {
+    const int rem = dim & 31;
+    if (rem) emit((uint32_t)acc);               // last, partially filled aligned word
+    const int tail_bits = rem ? rem : 32;       // valid bits of the last aligned word
+    if (s0 + tail_bits > 32) emit(0u);          // its top bits spill into one more stream word
+    const uint32_t next_head = __shfl_down_sync(kFull, head, 1);
+    if (lane != 31 && next_head != 0u) out[wi - 1] = last_sh | next_head;
   }
 };
 
 // CanonicalObservationEncoder::Encode for `observer` with the HanabiObservation
-// view folded in.  Writes obs_size bits to `row`.
+// view folded in.  Writes the lane's obs_size bits into the warp's stream.
+// Warp-convergent (every lane calls it).
 template <class V>
-HB_DEV void encode_obs(V v, const Spec& spec, const Game& G, int observer, uint32_t* row) {
+HB_DEV void encode_obs(V v, const Spec& spec, const Game& G, int observer, uint32_t* stream,
+                       int lane) {
   const int P = v.P(), H = v.H(), C = v.C(), R = v.R(), bpc = v.bpc();
-  BitWriter bw(row);
+  BitWriter bw(stream, lane, spec.obs_size);
   // --- hands (canonical_encoders.cc:62-105)
   uint32_t short_bits = 0;
 #pragma unroll
@@ -653,87 +767,75 @@ HB_DEV void encode_obs(V v, const Spec& spec, const Game& G, int observer, uint3
       }
     }
   }
-  bw.flush();
+  bw.finish(lane, spec.obs_size);
+}
+
+// Legal-move masks of the tile as a packed stream (A bits per game).  The slices
+// are narrower than a word, so they are OR-ed into pre-zeroed words.
+// Warp-convergent.
+HB_DEV void pack_mask_stream(uint32_t* stream, int A, uint64_t bits, bool valid, int lane) {
+  for (int w = lane; w < A + 1; w += 32) stream[w] = 0u;
+  __syncwarp();
+  if (valid) {
+    const int start = lane * A, w0 = start >> 5, sh = start & 31;
+    const uint64_t lo = bits << sh;
+    const uint32_t hi = sh ? (uint32_t)(bits >> (64 - sh)) : 0u;
+    atomicOr(&stream[w0], (uint32_t)lo);
+    if ((uint32_t)(lo >> 32)) atomicOr(&stream[w0 + 1], (uint32_t)(lo >> 32));
+    if (hi) atomicOr(&stream[w0 + 2], hi);
+  }
 }
 
 // 4 bits -> 4 bytes of 0/1 (little-endian byte i = bit i).
 HB_DEV uint32_t nibble_to_bytes(uint32_t n) { return ((n & 15u) * 0x00204081u) & 0x01010101u; }
 
-// Reads `count` (<= 16) bits starting at bit `o` of a row.
-HB_DEV uint32_t row_bits16(const uint32_t* row, int o, int words) {
-  const int w = o >> 5, sh = o & 31;
-  const uint32_t lo = row[w];
-  const uint32_t hi = (w + 1 < words) ? row[w + 1] : 0u;
-  return __funnelshift_r(lo, hi, sh) & 0xffffu;
+HB_DEV uint4 bits16_to_bytes(uint32_t bits) {
+  uint4 val;
+  val.x = nibble_to_bytes(bits);
+  val.y = nibble_to_bytes(bits >> 4);
+  val.z = nibble_to_bytes(bits >> 8);
+  val.w = ((bits >> 12) * 0x00204081u) & 0x01010101u;
+  return val;
 }
 
-// Warp-cooperative expansion of a tile of bit rows (one row per game, `stride`
-// words apart in shared memory, `dim` valid bits each) into bytes of 0/1 in
-// global memory.  Dense rows (pitch == dim) make the tile one contiguous,
-// 16-byte aligned byte range, written with 128-bit stores so a warp covers 512
-// contiguous bytes per instruction.
-HB_DEV void expand_tile(const uint32_t* rows, int stride, int dim, uint8_t* out, int64_t pitch,
-                        int n_valid, int lane) {
-  const int words = (dim + 31) >> 5;
-  if (pitch == dim && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) {
+// Warp-cooperative expansion of a tile's packed bit stream (`dim` bits per game,
+// n_valid games) into bytes of 0/1 in global memory.  Dense rows (pitch == dim):
+// the tile is one contiguous, 16-byte aligned byte range and every 128-bit store
+// is fed by one halfword of the stream, a warp covering 512 contiguous bytes per
+// instruction.  The stream must have one readable pad word after its last word.
+HB_DEV void expand_stream(const uint32_t* stream, int dim, uint8_t* out, int64_t pitch,
+                          int n_valid, int lane) {
+  const bool aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
+  if (pitch == dim && aligned) {
     const int total = n_valid * dim;
     const int full_chunks = total >> 4;
-    int g = 0, o = lane * 16;
-    while (o >= dim) { o -= dim; ++g; }
-    const int dq = 512 / dim, dr = 512 - dq * dim;
-    for (int k = lane; k < full_chunks; k += 32) {
-      // 16 output bytes = 16 consecutive bits of the tile's bit stream; they may
-      // straddle rows (several rows when dim < 16, e.g. an 11-move legal mask).
-      uint32_t bits = row_bits16(rows + g * stride, o, words);
-      int filled = dim - o;
-      if (filled < 16) {
-        bits &= (1u << filled) - 1u;
-        int gg = g + 1;
-        do {
-          uint32_t nxt = row_bits16(rows + gg * stride, 0, words);
-          if (dim < 16) nxt &= (1u << dim) - 1u;
-          bits |= (nxt << filled) & 0xffffu;
-          filled += dim;
-          ++gg;
-        } while (filled < 16);
-      }
-      uint4 val;
-      val.x = nibble_to_bytes(bits);
-      val.y = nibble_to_bytes(bits >> 4);
-      val.z = nibble_to_bytes(bits >> 8);
-      val.w = nibble_to_bytes(bits >> 12);
-      *reinterpret_cast<uint4*>(out + (int64_t)k * 16) = val;
-      g += dq;
-      o += dr;
-      if (o >= dim) { o -= dim; ++g; }
-    }
-    // ragged tail of a partial tile
-    for (int b = (full_chunks << 4) + lane; b < total; b += 32) {
-      const int gg = b / dim, oo = b - gg * dim;
-      out[b] = (uint8_t)((rows[gg * stride + (oo >> 5)] >> (oo & 31)) & 1u);
-    }
-  } else if ((pitch & 15) == 0 && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) {
+    const uint16_t* half = reinterpret_cast<const uint16_t*>(stream);
+    uint4* dst = reinterpret_cast<uint4*>(out);
+#pragma unroll 4
+    for (int k = lane; k < full_chunks; k += 32) dst[k] = bits16_to_bytes(half[k]);
+    for (int b = (full_chunks << 4) + lane; b < total; b += 32)  // ragged tail of a partial tile
+      out[b] = (uint8_t)((stream[b >> 5] >> (b & 31)) & 1u);
+  } else if ((pitch & 15) == 0 && aligned) {
     const int chunks = (dim + 15) >> 4;
     for (int idx = lane; idx < n_valid * chunks; idx += 32) {
       const int g = idx / chunks, j = idx - g * chunks;
       const int o = j * 16, avail = dim - o;
-      uint32_t bits = row_bits16(rows + g * stride, o, words);
-      uint8_t* dst = out + (int64_t)g * pitch + o;
+      const int pos = g * dim + o;
+      const uint32_t bits =
+          __funnelshift_r(stream[pos >> 5], stream[(pos >> 5) + 1], pos & 31) & 0xffffu;
+      uint8_t* d = out + (int64_t)g * pitch + o;
       if (avail >= 16) {
-        uint4 val;
-        val.x = nibble_to_bytes(bits);
-        val.y = nibble_to_bytes(bits >> 4);
-        val.z = nibble_to_bytes(bits >> 8);
-        val.w = nibble_to_bytes(bits >> 12);
-        *reinterpret_cast<uint4*>(dst) = val;
+        *reinterpret_cast<uint4*>(d) = bits16_to_bytes(bits);
       } else {
-        for (int i = 0; i < avail; ++i) dst[i] = (uint8_t)((bits >> i) & 1u);
+        for (int i = 0; i < avail; ++i) d[i] = (uint8_t)((bits >> i) & 1u);
       }
     }
   } else {
     for (int g = 0; g < n_valid; ++g)
-      for (int o = lane; o < dim; o += 32)
-        out[(int64_t)g * pitch + o] = (uint8_t)((rows[g * stride + (o >> 5)] >> (o & 31)) & 1u);
+      for (int o = lane; o < dim; o += 32) {
+        const int pos = g * dim + o;
+        out[(int64_t)g * pitch + o] = (uint8_t)((stream[pos >> 5] >> (pos & 31)) & 1u);
+      }
   }
 }
 

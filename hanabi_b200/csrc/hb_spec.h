@@ -39,6 +39,10 @@ struct Spec {
   int32_t deck_max, per_color, bits_per_card;
   int32_t obs_size, max_moves;
   int32_t hands_len, board_len, discard_len, last_len, know_len;
+  int32_t fast_reset;  // the unrolled re-deal applies (no random start, >= 2 card types left throughout)
+  // Deck bitmap helpers (one bit per card instance, same layout as the discard
+  // thermometers): first bit of every type block by block width.
+  uint64_t full_deck, type_m23, type_m3, type_m1;
 };
 
 HB_HD int InstancesOfRank(int R, int rank) {  // hanabi_game.cc:126-136
@@ -70,6 +74,17 @@ inline int FinishSpec(Spec* s) {
   s->obs_size = s->hands_len + s->board_len + s->discard_len + s->last_len +
                 (s->obs_type == kMinimal ? 0 : s->know_len);
   s->max_moves = 2 * s->H + (s->P - 1) * s->C + (s->P - 1) * s->R;
+  s->full_deck = s->type_m23 = s->type_m3 = s->type_m1 = 0;
+  for (int c = 0; c < s->C; ++c)
+    for (int r = 0; r < s->R; ++r) {
+      const int n = InstancesOfRank(s->R, r), off = c * s->per_color + DiscardRankOffset(r);
+      s->full_deck |= ((1ull << n) - 1ull) << off;
+      if (n >= 2) s->type_m23 |= 1ull << off;
+      if (n == 3) s->type_m3 |= 1ull << off;
+      if (n == 1) s->type_m1 |= 1ull << off;
+    }
+  // A deck with more cards than the largest multiplicity (3) holds >= 2 types.
+  s->fast_reset = (!s->random_start && s->deck_max - s->P * s->H >= 3) ? 1 : 0;
   return 0;
 }
 
