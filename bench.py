@@ -267,24 +267,23 @@ def main():
     h_cur, h_rew = pin(ne, dt=torch.int32), pin(ne, dt=torch.int32)
     h_done, h_act = pin(ne, dt=torch.uint8), pin(ne, dt=torch.int32)
     hb.reset_host(h_obs, h_mask, h_cur)
-    gen = torch.Generator().manual_seed(7 + rank)
+    t_policy = [0.0]
 
-    def host_policy():
-      # uniform random legal move per game on the host (torch CPU ops)
-      w = torch.rand((ne, A), generator=gen) * h_mask + h_mask
-      h_act.copy_(w.argmax(dim=1).to(torch.int32))
-
-    def host_step():
-      host_policy()
+    def host_step(t):
+      # uniform random legal move per game, chosen on the host from the host mask
+      p0 = time.perf_counter()
+      ph.host_random_legal_actions(h_mask, seed=7, step=t, out=h_act)
+      t_policy[0] += time.perf_counter() - p0
       hb.step_encode_host(h_act, h_rew, h_done, h_obs, h_mask, h_cur)
 
-    for _ in range(3):
-      host_step()
+    for t in range(3):
+      host_step(t)
     if dist:
       dist.barrier()
+    t_policy[0] = 0.0
     t0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-      host_step()
+    for t in range(args.e2e_steps):
+      host_step(3 + t)
     dt = time.perf_counter() - t0
     if dist:
       tm = torch.tensor([dt], dtype=torch.float64, device=dev)
@@ -293,6 +292,8 @@ def main():
     e2e = {"value": world * ne * args.e2e_steps / dt, "unit": "env-steps/s",
            "h2d_bytes_per_step": ne * 4, "d2h_bytes_per_step": ne * (D + A + 4 + 1 + 4),
            "games_per_step": ne, "steps": args.e2e_steps,
+           "ms_per_step": dt / args.e2e_steps * 1e3,
+           "host_policy_ms_per_step": t_policy[0] / args.e2e_steps * 1e3,
            "note": "BatchStepEncodeHost with pinned host buffers; host random-legal policy inside "
                    "the timed region"}
     del hb

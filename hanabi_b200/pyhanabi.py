@@ -37,6 +37,31 @@ def encode_ffi_string(x):
   return str(ffi.string(x), "ascii")
 
 
+def read_cdef(cdef_file):
+  """The declarations between the header's `extern "C" {` and
+  `} /* extern "C" */` marker lines (same rule as the reference's try_cdef,
+  pyhanabi.py:56-69)."""
+  reading_cdef = False
+  cdef_string = ""
+  for line in open(cdef_file).readlines():
+    line = line.rstrip()
+    if re.match("extern *\"C\" *{", line):
+      reading_cdef = True
+      continue
+    elif re.match("} */[*] *extern *\"C\" *[*]/", line):
+      reading_cdef = False
+      continue
+    if reading_cdef:
+      cdef_string = cdef_string + line + "\n"
+  return cdef_string
+
+
+def declared_functions(cdef_file):
+  """Names of all functions the header declares inside its extern "C" block."""
+  text = re.sub(r"/\*.*?\*/", " ", read_cdef(cdef_file), flags=re.S)
+  return sorted(set(re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*\(", text)))
+
+
 def try_cdef(header=PYHANABI_HEADER, prefixes=DEFAULT_CDEF_PREFIXES):
   """Parse the library header; same contract as the reference's try_cdef."""
   global cdef_loaded_flag
@@ -45,20 +70,7 @@ def try_cdef(header=PYHANABI_HEADER, prefixes=DEFAULT_CDEF_PREFIXES):
   for prefix in prefixes:
     try:
       cdef_file = header if prefix is None else prefix + "/" + header
-      lines = open(cdef_file).readlines()
-      reading_cdef = False
-      cdef_string = ""
-      for line in lines:
-        line = line.rstrip()
-        if re.match("extern *\"C\" *{", line):
-          reading_cdef = True
-          continue
-        elif re.match("} */[*] *extern *\"C\" *[*]/", line):
-          reading_cdef = False
-          continue
-        if reading_cdef:
-          cdef_string = cdef_string + line + "\n"
-      ffi.cdef(cdef_string)
+      ffi.cdef(read_cdef(cdef_file))
       cdef_loaded_flag = True
       return True
     except IOError:
@@ -121,6 +133,532 @@ def _params_to_c(params):
     keep.append(ffi.new("char[]", str(value).encode("ascii")))
   arr = ffi.new("char * [" + str(max(len(keep), 1)) + "]", keep if keep else [ffi.NULL])
   return len(keep), arr, keep
+
+
+# ---------------------------------------------------------------------------
+# Per-object API: the same classes and methods as the reference binding
+# (hanabi_learning_environment/pyhanabi.py:117-972), over the same C symbols.
+import enum  # noqa: E402
+
+
+def _take_string(c_str):
+  text = encode_ffi_string(c_str)
+  lib.DeleteString(c_str)
+  return text
+
+
+def color_idx_to_char(color_idx):
+  """Colour index -> one of "RYGWB"; -1 -> None (reference pyhanabi.py:117-133)."""
+  assert isinstance(color_idx, int)
+  return None if color_idx == -1 else COLOR_CHAR[color_idx]
+
+
+def color_char_to_idx(color_char):
+  """One of "RYGWB" -> colour index (reference pyhanabi.py:136-153)."""
+  assert isinstance(color_char, str)
+  if color_char not in COLOR_CHAR:
+    raise ValueError("Invalid color: {}. Should be one of {}.".format(color_char, COLOR_CHAR))
+  return COLOR_CHAR.index(color_char)
+
+
+class HanabiCard(object):
+  """A card: colour index (RYGWB order) and 0-based rank; -1/-1 is "unknown"."""
+
+  def __init__(self, color, rank):
+    self._color, self._rank = color, rank
+
+  def color(self):
+    return self._color
+
+  def rank(self):
+    return self._rank
+
+  def valid(self):
+    return self._color >= 0 and self._rank >= 0
+
+  def __str__(self):
+    return COLOR_CHAR[self._color] + str(self._rank + 1) if self.valid() else "XX"
+
+  __repr__ = __str__
+
+  def __eq__(self, other):
+    return self._color == other.color() and self._rank == other.rank()
+
+  def to_dict(self):
+    return {"color": color_idx_to_char(self.color()), "rank": self.rank()}
+
+
+class HanabiCardKnowledge(object):
+  """Hint knowledge about one card: the directly hinted colour/rank (or None)
+  and which values no hint has excluded yet."""
+
+  def __init__(self, knowledge):
+    self._knowledge = knowledge
+
+  def color(self):
+    return lib.KnownColor(self._knowledge) if lib.ColorWasHinted(self._knowledge) else None
+
+  def color_plausible(self, color_index):
+    return lib.ColorIsPlausible(self._knowledge, color_index)
+
+  def rank(self):
+    return lib.KnownRank(self._knowledge) if lib.RankWasHinted(self._knowledge) else None
+
+  def rank_plausible(self, rank_index):
+    return lib.RankIsPlausible(self._knowledge, rank_index)
+
+  def __str__(self):
+    return _take_string(lib.CardKnowledgeToString(self._knowledge))
+
+  __repr__ = __str__
+
+  def to_dict(self):
+    return {"color": color_idx_to_char(self.color()), "rank": self.rank()}
+
+
+class HanabiMoveType(enum.IntEnum):
+  INVALID = 0
+  PLAY = 1
+  DISCARD = 2
+  REVEAL_COLOR = 3
+  REVEAL_RANK = 4
+  DEAL = 5
+
+
+class HanabiMove(object):
+  """Owns one C move object."""
+
+  def __init__(self, move):
+    assert move is not None
+    self._move = move
+
+  @property
+  def c_move(self):
+    return self._move
+
+  def type(self):
+    return HanabiMoveType(lib.MoveType(self._move))
+
+  def card_index(self):
+    return lib.CardIndex(self._move)
+
+  def target_offset(self):
+    return lib.TargetOffset(self._move)
+
+  def color(self):
+    return lib.MoveColor(self._move)
+
+  def rank(self):
+    return lib.MoveRank(self._move)
+
+  @staticmethod
+  def _make(fn, *args):
+    c_move = ffi.new("pyhanabi_move_t*")
+    assert fn(*(args + (c_move,)))
+    return HanabiMove(c_move)
+
+  @staticmethod
+  def get_discard_move(card_index):
+    return HanabiMove._make(lib.GetDiscardMove, card_index)
+
+  @staticmethod
+  def get_play_move(card_index):
+    return HanabiMove._make(lib.GetPlayMove, card_index)
+
+  @staticmethod
+  def get_reveal_color_move(target_offset, color):
+    return HanabiMove._make(lib.GetRevealColorMove, target_offset, color)
+
+  @staticmethod
+  def get_reveal_rank_move(target_offset, rank):
+    return HanabiMove._make(lib.GetRevealRankMove, target_offset, rank)
+
+  def __str__(self):
+    return _take_string(lib.MoveToString(self._move))
+
+  __repr__ = __str__
+
+  def __del__(self):
+    if self._move is not None and lib is not None:
+      lib.DeleteMove(self._move)
+      self._move = None
+
+  def to_dict(self):
+    kind = self.type()
+    d = {"action_type": kind.name}
+    if kind in (HanabiMoveType.PLAY, HanabiMoveType.DISCARD):
+      d["card_index"] = self.card_index()
+    elif kind == HanabiMoveType.REVEAL_COLOR:
+      d["target_offset"] = self.target_offset()
+      d["color"] = color_idx_to_char(self.color())
+    elif kind == HanabiMoveType.REVEAL_RANK:
+      d["target_offset"] = self.target_offset()
+      d["rank"] = self.rank()
+    elif kind == HanabiMoveType.DEAL:
+      d["color"] = color_idx_to_char(self.color())
+      d["rank"] = self.rank()
+    else:
+      raise ValueError("Unsupported move: {}".format(self))
+    return d
+
+
+def _bits(mask):
+  return [i for i in range(8) if mask & (1 << i)]
+
+
+class HanabiHistoryItem(object):
+  """A move together with what it did (scored, token gained, cards touched)."""
+
+  def __init__(self, item):
+    self._item = item
+
+  def move(self):
+    c_move = ffi.new("pyhanabi_move_t*")
+    lib.HistoryItemMove(self._item, c_move)
+    return HanabiMove(c_move)
+
+  def player(self):
+    return lib.HistoryItemPlayer(self._item)
+
+  def scored(self):
+    return bool(lib.HistoryItemScored(self._item))
+
+  def information_token(self):
+    return bool(lib.HistoryItemInformationToken(self._item))
+
+  def color(self):
+    return lib.HistoryItemColor(self._item)
+
+  def rank(self):
+    return lib.HistoryItemRank(self._item)
+
+  def card_info_revealed(self):
+    return _bits(lib.HistoryItemRevealBitmask(self._item))
+
+  def card_info_newly_revealed(self):
+    return _bits(lib.HistoryItemNewlyRevealedBitmask(self._item))
+
+  def deal_to_player(self):
+    return lib.HistoryItemDealToPlayer(self._item)
+
+  def __str__(self):
+    return _take_string(lib.HistoryItemToString(self._item))
+
+  __repr__ = __str__
+
+  def __del__(self):
+    if self._item is not None and lib is not None:
+      lib.DeleteHistoryItem(self._item)
+      self._item = None
+
+
+class HanabiEndOfGameType(enum.IntEnum):
+  NOT_FINISHED = 0
+  OUT_OF_LIFE_TOKENS = 1
+  OUT_OF_CARDS = 2
+  COMPLETED_FIREWORKS = 3
+
+
+def _card_from(fn, *args):
+  c_card = ffi.new("pyhanabi_card_t*")
+  fn(*(args + (c_card,)))
+  return HanabiCard(c_card.color, c_card.rank)
+
+
+def _moves_from_list(c_list):
+  out = []
+  for i in range(lib.NumMoves(c_list)):
+    c_move = ffi.new("pyhanabi_move_t*")
+    lib.GetMove(c_list, i, c_move)
+    out.append(HanabiMove(c_move))
+  lib.DeleteMoveList(c_list)
+  return out
+
+
+class HanabiState(object):
+  """One game in progress; chance events are explicit (cur_player() == -1)."""
+
+  def __init__(self, game, c_state=None):
+    self._state = ffi.new("pyhanabi_state_t*")
+    if c_state is None:
+      self._game = game.c_game
+      lib.NewState(self._game, self._state)
+    else:
+      # NOTE: like the reference, `game` is ignored and the copied state's game is used
+      self._game = ffi.new("pyhanabi_game_t*")
+      self._game.game = ffi.cast("void*", lib.StateParentGame(c_state))
+      lib.CopyState(c_state, self._state)
+
+  def copy(self):
+    return HanabiState(None, self._state)
+
+  def observation(self, player):
+    return HanabiObservation(self._state, self._game, player)
+
+  def apply_move(self, move):
+    lib.StateApplyMove(self._state, move.c_move)
+
+  def cur_player(self):
+    return lib.StateCurPlayer(self._state)
+
+  def deck_size(self):
+    return lib.StateDeckSize(self._state)
+
+  def discard_pile(self):
+    return [_card_from(lib.StateGetDiscard, self._state, i)
+            for i in range(lib.StateDiscardPileSize(self._state))]
+
+  def fireworks(self):
+    return [lib.StateFireworks(self._state, c) for c in range(lib.NumColors(self._game))]
+
+  def deal_random_card(self):
+    lib.StateDealRandomCard(self._state)
+
+  def player_hands(self):
+    hands = []
+    for pid in range(self.num_players()):
+      hands.append([_card_from(lib.StateGetHandCard, self._state, pid, i)
+                    for i in range(lib.StateGetHandSize(self._state, pid))])
+    return hands
+
+  def information_tokens(self):
+    return lib.StateInformationTokens(self._state)
+
+  def end_of_game_status(self):
+    return HanabiEndOfGameType(lib.StateEndOfGameStatus(self._state))
+
+  def is_terminal(self):
+    return lib.StateEndOfGameStatus(self._state) != HanabiEndOfGameType.NOT_FINISHED
+
+  def legal_moves(self):
+    return _moves_from_list(lib.StateLegalMoves(self._state))
+
+  def move_is_legal(self, move):
+    return lib.MoveIsLegal(self._state, move.c_move)
+
+  def card_playable_on_fireworks(self, color, rank):
+    return lib.CardPlayableOnFireworks(self._state, color, rank)
+
+  def life_tokens(self):
+    return lib.StateLifeTokens(self._state)
+
+  def num_players(self):
+    return lib.StateNumPlayers(self._state)
+
+  def score(self):
+    return lib.StateScore(self._state)
+
+  def move_history(self):
+    out = []
+    for i in range(lib.StateLenMoveHistory(self._state)):
+      c_item = ffi.new("pyhanabi_history_item_t*")
+      lib.StateGetMoveHistory(self._state, i, c_item)
+      out.append(HanabiHistoryItem(c_item))
+    return out
+
+  def __str__(self):
+    return _take_string(lib.StateToString(self._state))
+
+  __repr__ = __str__
+
+  def __del__(self):
+    if self._state is not None and lib is not None:
+      lib.DeleteState(self._state)
+      self._state = None
+      self._game = None
+
+
+class AgentObservationType(enum.IntEnum):
+  """What an agent may see (hanabi_lib/hanabi_game.h:28-39)."""
+  MINIMAL = 0
+  CARD_KNOWLEDGE = 1
+  SEER = 2
+
+
+class HanabiGame(object):
+  """Rule set plus the game's own RNG stream.  `params` keys: players, colors,
+  ranks, hand_size, max_information_tokens, max_life_tokens, seed,
+  random_start_player, observation_type (hanabi_lib/hanabi_game.cc:29-47)."""
+
+  def __init__(self, params=None):
+    _require_lib()
+    self._game = ffi.new("pyhanabi_game_t*")
+    if params is None:
+      lib.NewDefaultGame(self._game)
+    else:
+      keep = []
+      for key, value in params.items():
+        keep.append(ffi.new("char[]", str(key).encode("ascii")))
+        keep.append(ffi.new("char[]", str(value).encode("ascii")))
+      c_array = ffi.new("char * [" + str(max(len(keep), 1)) + "]", keep if keep else [ffi.NULL])
+      lib.NewGame(self._game, len(keep), c_array)
+
+  def new_initial_state(self):
+    return HanabiState(self)
+
+  @property
+  def c_game(self):
+    return self._game
+
+  def __del__(self):
+    if self._game is not None and lib is not None:
+      lib.DeleteGame(self._game)
+      self._game = None
+
+  def parameter_string(self):
+    return _take_string(lib.GameParamString(self._game))
+
+  def num_players(self):
+    return lib.NumPlayers(self._game)
+
+  def num_colors(self):
+    return lib.NumColors(self._game)
+
+  def num_ranks(self):
+    return lib.NumRanks(self._game)
+
+  def hand_size(self):
+    return lib.HandSize(self._game)
+
+  def max_information_tokens(self):
+    return lib.MaxInformationTokens(self._game)
+
+  def max_life_tokens(self):
+    return lib.MaxLifeTokens(self._game)
+
+  def observation_type(self):
+    return AgentObservationType(lib.ObservationType(self._game))
+
+  def max_moves(self):
+    return lib.MaxMoves(self._game)
+
+  def num_cards(self, color, rank):
+    return lib.NumCards(self._game, color, rank)
+
+  def get_move_uid(self, move):
+    return lib.GetMoveUid(self._game, move.c_move)
+
+  def get_move(self, move_uid):
+    c_move = ffi.new("pyhanabi_move_t*")
+    lib.GetMoveByUid(self._game, move_uid, c_move)
+    return HanabiMove(c_move)
+
+
+class HanabiObservation(object):
+  """One player's view: own cards hidden, every player index relative to the
+  observer (who is always index 0)."""
+
+  def __init__(self, state, game, player):
+    self._observation = ffi.new("pyhanabi_observation_t*")
+    self._game = game
+    lib.NewObservation(state, player, self._observation)
+
+  def __str__(self):
+    return _take_string(lib.ObsToString(self._observation))
+
+  __repr__ = __str__
+
+  def __del__(self):
+    if self._observation is not None and lib is not None:
+      lib.DeleteObservation(self._observation)
+      self._observation = None
+      self._game = None
+
+  def observation(self):
+    return self._observation
+
+  def cur_player_offset(self):
+    return lib.ObsCurPlayerOffset(self._observation)
+
+  def num_players(self):
+    return lib.ObsNumPlayers(self._observation)
+
+  def observed_hands(self):
+    return [[_card_from(lib.ObsGetHandCard, self._observation, pid, i)
+             for i in range(lib.ObsGetHandSize(self._observation, pid))]
+            for pid in range(self.num_players())]
+
+  def card_knowledge(self):
+    out = []
+    for pid in range(self.num_players()):
+      player = []
+      for i in range(lib.ObsGetHandSize(self._observation, pid)):
+        c_knowledge = ffi.new("pyhanabi_card_knowledge_t*")
+        lib.ObsGetHandCardKnowledge(self._observation, pid, i, c_knowledge)
+        player.append(HanabiCardKnowledge(c_knowledge))
+      out.append(player)
+    return out
+
+  def discard_pile(self):
+    return [_card_from(lib.ObsGetDiscard, self._observation, i)
+            for i in range(lib.ObsDiscardPileSize(self._observation))]
+
+  def fireworks(self):
+    return [lib.ObsFireworks(self._observation, c) for c in range(lib.NumColors(self._game))]
+
+  def deck_size(self):
+    return lib.ObsDeckSize(self._observation)
+
+  def last_moves(self):
+    out = []
+    for i in range(lib.ObsNumLastMoves(self._observation)):
+      c_item = ffi.new("pyhanabi_history_item_t*")
+      lib.ObsGetLastMove(self._observation, i, c_item)
+      out.append(HanabiHistoryItem(c_item))
+    return out
+
+  def information_tokens(self):
+    return lib.ObsInformationTokens(self._observation)
+
+  def life_tokens(self):
+    return lib.ObsLifeTokens(self._observation)
+
+  def legal_moves(self):
+    out = []
+    for i in range(lib.ObsNumLegalMoves(self._observation)):
+      c_move = ffi.new("pyhanabi_move_t*")
+      lib.ObsGetLegalMove(self._observation, i, c_move)
+      out.append(HanabiMove(c_move))
+    return out
+
+  def card_playable_on_fireworks(self, color, rank):
+    return lib.ObsCardPlayableOnFireworks(self._observation, color, rank)
+
+
+class ObservationEncoderType(enum.IntEnum):
+  CANONICAL = 0
+
+
+class ObservationEncoder(object):
+  """Canonical bit-vector encoder.  encode() returns a list of ints like the
+  reference (pyhanabi.py:963-972) but reads the bits as bytes instead of
+  parsing the comma-separated string."""
+
+  def __init__(self, game, enc_type=ObservationEncoderType.CANONICAL):
+    self._game = game.c_game
+    self._encoder = ffi.new("pyhanabi_observation_encoder_t*")
+    lib.NewObservationEncoder(self._encoder, self._game, enc_type)
+    self._shape = None
+
+  def __del__(self):
+    if self._encoder is not None and lib is not None:
+      lib.DeleteObservationEncoder(self._encoder)
+      self._encoder = None
+      self._game = None
+
+  def shape(self):
+    if self._shape is None:
+      self._shape = [int(x) for x in _take_string(lib.ObservationShape(self._encoder)).split(",")]
+    return list(self._shape)
+
+  def encode(self, observation):
+    if hasattr(lib, "EncodeObservationBytes"):
+      n = self.shape()[0]
+      buf = ffi.new("uint8_t[]", n)
+      lib.EncodeObservationBytes(self._encoder, observation.observation(), buf, n)
+      return list(bytes(ffi.buffer(buf, n)))
+    text = _take_string(lib.EncodeObservation(self._encoder, observation.observation()))
+    return [int(x) for x in text.split(",")]
 
 
 class HanabiBatch(object):
@@ -373,6 +911,23 @@ def select_action(values, mask, epsilon, seed, step, support=None, out=None):
                                  int(seed) & (2**64 - 1), int(step) & (2**64 - 1),
                                  _tp(out, torch.int32, "int32_t*"), _cur_stream(mask)),
            "BatchSelectAction")
+  return out
+
+
+def host_random_legal_actions(mask, seed, step, out=None, threads=0):
+  """Uniform random legal move per game on the HOST (CPU uint8 mask [n, A] ->
+  CPU int32 actions [n]); bit-identical to select_action(None, mask, 1.0, seed, step)."""
+  import torch
+  _require_lib()
+  n, A = int(mask.shape[0]), int(mask.shape[1])
+  if mask.is_cuda or mask.dtype != torch.uint8 or not mask.is_contiguous():
+    raise ValueError("mask must be a contiguous CPU uint8 tensor")
+  if out is None:
+    out = torch.empty(n, dtype=torch.int32)
+  _check(lib.HostRandomLegalActions(ffi.cast("uint8_t*", mask.data_ptr()), n, A,
+                                    int(seed) & (2**64 - 1), int(step) & (2**64 - 1),
+                                    ffi.cast("int32_t*", out.data_ptr()), int(threads)),
+         "HostRandomLegalActions")
   return out
 
 

@@ -13,6 +13,9 @@ from __future__ import absolute_import
 from __future__ import division
 
 from hanabi_b200 import pyhanabi
+from hanabi_b200.pyhanabi import color_char_to_idx
+
+MOVE_TYPES = [_.name for _ in pyhanabi.HanabiMoveType]
 
 PRESETS = {  # rl_env.py:521-582
     "Hanabi-Full": dict(colors=5, ranks=5, max_information_tokens=8, max_life_tokens=3,
@@ -26,6 +29,126 @@ PRESETS = {  # rl_env.py:521-582
     "Hanabi-Very-Small": dict(colors=1, ranks=5, hand_size=2, max_information_tokens=3,
                               max_life_tokens=1, observation_type=1),
 }
+
+
+class Environment(object):
+  """Abstract environment interface (reference rl_env.py:28-64)."""
+
+  def reset(self, config):
+    raise NotImplementedError("Not implemented in Abstract Base class")
+
+  def step(self, action):
+    raise NotImplementedError("Not implemented in Abstract Base class")
+
+
+class HanabiEnv(Environment):
+  """The reference's single-game environment, unchanged in behaviour
+  (rl_env.py:67-498): same config dict, same per-player observation dicts (all 14
+  keys including `legal_moves_as_int`, `vectorized` and the live `pyhanabi`
+  observation handle), same reward (score delta, rl_env.py:363) and done flag.
+  It runs on the host-side per-object API of libpyhanabi.so; use
+  BatchedHanabiEnv for throughput."""
+
+  def __init__(self, config):
+    assert isinstance(config, dict), "Expected config to be of type dict."
+    self.game = pyhanabi.HanabiGame(config)
+    self.observation_encoder = pyhanabi.ObservationEncoder(
+        self.game, pyhanabi.ObservationEncoderType.CANONICAL)
+    self.players = self.game.num_players()
+
+  def _deal(self):
+    while self.state.cur_player() == pyhanabi.CHANCE_PLAYER_ID:
+      self.state.deal_random_card()
+
+  def reset(self):
+    self.state = self.game.new_initial_state()
+    self._deal()
+    obs = self._make_observation_all_players()
+    obs["current_player"] = self.state.cur_player()
+    return obs
+
+  def vectorized_observation_shape(self):
+    return self.observation_encoder.shape()
+
+  def num_moves(self):
+    return self.game.max_moves()
+
+  def step(self, action):
+    if isinstance(action, dict):
+      action = self._build_move(action)
+    elif isinstance(action, int):
+      action = self.game.get_move(action)
+    else:  # numpy integers are rejected, as in the reference (rl_env.py:349-351)
+      raise ValueError("Expected action as dict or int, got: {}".format(action))
+    last_score = self.state.score()
+    self.state.apply_move(action)
+    self._deal()
+    observation = self._make_observation_all_players()
+    done = self.state.is_terminal()
+    reward = self.state.score() - last_score
+    return (observation, reward, done, {})
+
+  def _make_observation_all_players(self):
+    return {
+        "player_observations": [
+            self._extract_dict_from_backend(pid, self.state.observation(pid))
+            for pid in range(self.players)],
+        "current_player": self.state.cur_player(),
+    }
+
+  def _extract_dict_from_backend(self, player_id, observation):
+    d = {}
+    d["current_player"] = self.state.cur_player()
+    d["current_player_offset"] = observation.cur_player_offset()
+    d["life_tokens"] = observation.life_tokens()
+    d["information_tokens"] = observation.information_tokens()
+    d["num_players"] = observation.num_players()
+    d["deck_size"] = observation.deck_size()
+    d["fireworks"] = dict(zip(pyhanabi.COLOR_CHAR, self.state.fireworks()))
+    d["legal_moves"] = []
+    d["legal_moves_as_int"] = []
+    for move in observation.legal_moves():
+      d["legal_moves"].append(move.to_dict())
+      d["legal_moves_as_int"].append(self.game.get_move_uid(move))
+    d["observed_hands"] = [[card.to_dict() for card in hand]
+                           for hand in observation.observed_hands()]
+    d["discard_pile"] = [card.to_dict() for card in observation.discard_pile()]
+    d["card_knowledge"] = []
+    for player_hints in observation.card_knowledge():
+      hints = []
+      for hint in player_hints:
+        color = hint.color()
+        hints.append({"color": pyhanabi.color_idx_to_char(color) if color is not None else None,
+                      "rank": hint.rank()})
+      d["card_knowledge"].append(hints)
+    d["vectorized"] = self.observation_encoder.encode(observation)
+    d["pyhanabi"] = observation
+    return d
+
+  def _build_move(self, action):
+    assert isinstance(action, dict), "Expected dict, got: {}".format(action)
+    assert "action_type" in action, ("Action should contain `action_type`. "
+                                     "action: {}").format(action)
+    action_type = action["action_type"]
+    assert (action_type in MOVE_TYPES), (
+        "action_type: {} should be one of: {}".format(action_type, MOVE_TYPES))
+    if action_type == "PLAY":
+      move = pyhanabi.HanabiMove.get_play_move(card_index=action["card_index"])
+    elif action_type == "DISCARD":
+      move = pyhanabi.HanabiMove.get_discard_move(card_index=action["card_index"])
+    elif action_type == "REVEAL_RANK":
+      move = pyhanabi.HanabiMove.get_reveal_rank_move(
+          target_offset=action["target_offset"], rank=action["rank"])
+    elif action_type == "REVEAL_COLOR":
+      assert isinstance(action["color"], str)
+      move = pyhanabi.HanabiMove.get_reveal_color_move(
+          target_offset=action["target_offset"], color=color_char_to_idx(action["color"]))
+    else:
+      raise ValueError("Unknown action_type: {}".format(action_type))
+    legal_moves = self.state.legal_moves()
+    assert (str(move) in map(str, legal_moves)), (
+        "Illegal action: {}. Move should be one of : {}".format(move, legal_moves))
+    return move
 
 
 class BatchedHanabiEnv(object):
@@ -118,8 +241,32 @@ def _preset(environment_name, num_players):
   return config
 
 
+def make(environment_name="Hanabi-Full", num_players=2, pyhanabi_path=None):
+  """rl_env.make (reference rl_env.py:501-585): the single-game environment for
+  one of the preset names.  Like the reference it passes no seed, so games are
+  seeded from std::random_device."""
+  if pyhanabi_path is not None:
+    prefixes = (pyhanabi_path,)
+    assert pyhanabi.try_cdef(prefixes=prefixes), "cdef failed to load"
+    assert pyhanabi.try_load(prefixes=prefixes), "library failed to load"
+  return HanabiEnv(config=_preset(environment_name, num_players))
+
+
 def make_batched(environment_name="Hanabi-Full", num_players=2, num_games=1024, device=0, seed=1,
                  auto_reset=True):
   config = _preset(environment_name, num_players)
   config["seed"] = seed
   return BatchedHanabiEnv(config, num_games, device=device, auto_reset=auto_reset)
+
+
+class Agent(object):
+  """Agent interface (reference rl_env.py:592-641)."""
+
+  def __init__(self, config, *args, **kwargs):
+    raise NotImplementedError("Not implemented in Abstract Base class")
+
+  def reset(self, config):
+    raise NotImplementedError("Not implemented in Abstract Base class")
+
+  def act(self, observation):
+    raise NotImplementedError("Not implemented in Abstract Base class")

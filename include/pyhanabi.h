@@ -34,9 +34,150 @@
 /* C++ header, like the reference's: everything between the two marker lines
  * below must stay plain C declarations (no preprocessor lines) because the cffi
  * binding feeds that text to ffi.cdef(). */
+#include <stdbool.h>
 #include <stdint.h>
 
 extern "C" {
+
+/* ===== per-object API kept from the reference ============================
+ * Identical names, argument lists and ownership rules as the reference header
+ * (hanabi_learning_environment/pyhanabi.h:26-190): every New* / Get*Move /
+ * *GetMoveHistory / ObsGetLastMove / ObsGetLegalMove call allocates an object the
+ * caller releases with the matching Delete*; strings are released with
+ * DeleteString; a pyhanabi_card_knowledge_t borrows from its observation.
+ * Input errors abort the process (hanabi_lib/util.h:53-61).  Host-side,
+ * implemented in hanabi_b200/csrc/hb_single.cc. */
+
+/* handles: one pointer each (reference pyhanabi.h:26-64) */
+typedef struct PyHanabiCard { int color; int rank; } pyhanabi_card_t;
+typedef struct PyHanabiCardKnowledge { const void* knowledge; } pyhanabi_card_knowledge_t;
+typedef struct PyHanabiMove { void* move; } pyhanabi_move_t;
+typedef struct PyHanabiHistoryItem { void* item; } pyhanabi_history_item_t;
+typedef struct PyHanabiState { void* state; } pyhanabi_state_t;
+typedef struct PyHanabiGame { void* game; } pyhanabi_game_t;
+typedef struct PyHanabiObservation { void* observation; } pyhanabi_observation_t;
+typedef struct PyHanabiObservationEncoder { void* encoder; } pyhanabi_observation_encoder_t;
+
+/* strings and cards (pyhanabi.h:67,70) */
+void DeleteString(char* str);
+int CardValid(pyhanabi_card_t* card);
+
+/* hint knowledge about one card (pyhanabi.h:73-79) */
+char* CardKnowledgeToString(pyhanabi_card_knowledge_t* knowledge);
+int ColorWasHinted(pyhanabi_card_knowledge_t* knowledge);
+int KnownColor(pyhanabi_card_knowledge_t* knowledge);
+int ColorIsPlausible(pyhanabi_card_knowledge_t* knowledge, int color);
+int RankWasHinted(pyhanabi_card_knowledge_t* knowledge);
+int KnownRank(pyhanabi_card_knowledge_t* knowledge);
+int RankIsPlausible(pyhanabi_card_knowledge_t* knowledge, int rank);
+
+/* moves and move lists (pyhanabi.h:82-95) */
+void DeleteMoveList(void* movelist);
+int NumMoves(void* movelist);
+void GetMove(void* movelist, int index, pyhanabi_move_t* move);
+void DeleteMove(pyhanabi_move_t* move);
+char* MoveToString(pyhanabi_move_t* move);
+int MoveType(pyhanabi_move_t* move);
+int CardIndex(pyhanabi_move_t* move);
+int TargetOffset(pyhanabi_move_t* move);
+int MoveColor(pyhanabi_move_t* move);
+int MoveRank(pyhanabi_move_t* move);
+bool GetDiscardMove(int card_index, pyhanabi_move_t* move);
+bool GetPlayMove(int card_index, pyhanabi_move_t* move);
+bool GetRevealColorMove(int target_offset, int color, pyhanabi_move_t* move);
+bool GetRevealRankMove(int target_offset, int rank, pyhanabi_move_t* move);
+
+/* history items: a move plus its side effects (pyhanabi.h:98-108) */
+void DeleteHistoryItem(pyhanabi_history_item_t* item);
+char* HistoryItemToString(pyhanabi_history_item_t* item);
+void HistoryItemMove(pyhanabi_history_item_t* item, pyhanabi_move_t* move);
+int HistoryItemPlayer(pyhanabi_history_item_t* item);
+int HistoryItemScored(pyhanabi_history_item_t* item);
+int HistoryItemInformationToken(pyhanabi_history_item_t* item);
+int HistoryItemColor(pyhanabi_history_item_t* item);
+int HistoryItemRank(pyhanabi_history_item_t* item);
+int HistoryItemRevealBitmask(pyhanabi_history_item_t* item);
+int HistoryItemNewlyRevealedBitmask(pyhanabi_history_item_t* item);
+int HistoryItemDealToPlayer(pyhanabi_history_item_t* item);
+
+/* one game state (pyhanabi.h:111-139) */
+void NewState(pyhanabi_game_t* game, pyhanabi_state_t* state);
+void CopyState(const pyhanabi_state_t* src, pyhanabi_state_t* dest);
+void DeleteState(pyhanabi_state_t* state);
+const void* StateParentGame(pyhanabi_state_t* state);
+void StateApplyMove(pyhanabi_state_t* state, pyhanabi_move_t* move);
+int StateCurPlayer(pyhanabi_state_t* state);
+void StateDealRandomCard(pyhanabi_state_t* state);
+int StateDeckSize(pyhanabi_state_t* state);
+int StateFireworks(pyhanabi_state_t* state, int color);
+int StateDiscardPileSize(pyhanabi_state_t* state);
+void StateGetDiscard(pyhanabi_state_t* state, int index, pyhanabi_card_t* card);
+int StateGetHandSize(pyhanabi_state_t* state, int pid);
+void StateGetHandCard(pyhanabi_state_t* state, int pid, int index, pyhanabi_card_t* card);
+int StateEndOfGameStatus(pyhanabi_state_t* state);
+int StateInformationTokens(pyhanabi_state_t* state);
+void* StateLegalMoves(pyhanabi_state_t* state);
+int StateLifeTokens(pyhanabi_state_t* state);
+int StateNumPlayers(pyhanabi_state_t* state);
+int StateScore(pyhanabi_state_t* state);
+char* StateToString(pyhanabi_state_t* state);
+bool MoveIsLegal(const pyhanabi_state_t* state, const pyhanabi_move_t* move);
+bool CardPlayableOnFireworks(const pyhanabi_state_t* state, int color, int rank);
+int StateLenMoveHistory(pyhanabi_state_t* state);
+void StateGetMoveHistory(pyhanabi_state_t* state, int index, pyhanabi_history_item_t* item);
+
+/* rule set + the game's own RNG stream (pyhanabi.h:142-154) */
+void DeleteGame(pyhanabi_game_t* game);
+void NewDefaultGame(pyhanabi_game_t* game);
+void NewGame(pyhanabi_game_t* game, int list_length, const char** param_list);
+char* GameParamString(pyhanabi_game_t* game);
+int NumPlayers(pyhanabi_game_t* game);
+int NumColors(pyhanabi_game_t* game);
+int NumRanks(pyhanabi_game_t* game);
+int HandSize(pyhanabi_game_t* game);
+int MaxInformationTokens(pyhanabi_game_t* game);
+int MaxLifeTokens(pyhanabi_game_t* game);
+int ObservationType(pyhanabi_game_t* game);
+int NumCards(pyhanabi_game_t* game, int color, int rank);
+int GetMoveUid(pyhanabi_game_t* game, pyhanabi_move_t* move);
+void GetMoveByUid(pyhanabi_game_t* game, int move_uid, pyhanabi_move_t* move);
+int MaxMoves(pyhanabi_game_t* game);
+
+/* one player's view of a state (pyhanabi.h:157-182) */
+void NewObservation(pyhanabi_state_t* state, int player, pyhanabi_observation_t* observation);
+void DeleteObservation(pyhanabi_observation_t* observation);
+char* ObsToString(pyhanabi_observation_t* observation);
+int ObsCurPlayerOffset(pyhanabi_observation_t* observation);
+int ObsNumPlayers(pyhanabi_observation_t* observation);
+int ObsGetHandSize(pyhanabi_observation_t* observation, int pid);
+void ObsGetHandCard(pyhanabi_observation_t* observation, int pid, int index,
+                    pyhanabi_card_t* card);
+void ObsGetHandCardKnowledge(pyhanabi_observation_t* observation, int pid, int index,
+                             pyhanabi_card_knowledge_t* knowledge);
+int ObsDiscardPileSize(pyhanabi_observation_t* observation);
+void ObsGetDiscard(pyhanabi_observation_t* observation, int index, pyhanabi_card_t* card);
+int ObsFireworks(pyhanabi_observation_t* observation, int color);
+int ObsDeckSize(pyhanabi_observation_t* observation);
+int ObsNumLastMoves(pyhanabi_observation_t* observation);
+void ObsGetLastMove(pyhanabi_observation_t* observation, int index,
+                    pyhanabi_history_item_t* item);
+int ObsInformationTokens(pyhanabi_observation_t* observation);
+int ObsLifeTokens(pyhanabi_observation_t* observation);
+int ObsNumLegalMoves(pyhanabi_observation_t* observation);
+void ObsGetLegalMove(pyhanabi_observation_t* observation, int index, pyhanabi_move_t* move);
+bool ObsCardPlayableOnFireworks(const pyhanabi_observation_t* observation, int color, int rank);
+
+/* canonical observation encoder; EncodeObservation returns "0,1,0,..." as the
+ * reference does (pyhanabi.h:185-190, pyhanabi.cc:839-858) */
+void NewObservationEncoder(pyhanabi_observation_encoder_t* encoder, pyhanabi_game_t* game,
+                           int type);
+void DeleteObservationEncoder(pyhanabi_observation_encoder_t* encoder);
+char* ObservationShape(pyhanabi_observation_encoder_t* encoder);
+char* EncodeObservation(pyhanabi_observation_encoder_t* encoder,
+                        pyhanabi_observation_t* observation);
+/* new: the same bits as bytes into a caller buffer, no ASCII round trip */
+int EncodeObservationBytes(pyhanabi_observation_encoder_t* encoder,
+                           pyhanabi_observation_t* observation, uint8_t* out, int capacity);
 
 /* ===== batched engine (new) ============================================== */
 
@@ -139,6 +280,11 @@ int BatchReadStats(pyhanabi_batch_t* batch, int64_t* host_stats, int clear, void
 int BatchSelectAction(const float* q_or_logits, int num_atoms, const float* support,
                       const uint8_t* mask, int n, int num_actions, float epsilon,
                       uint64_t seed, uint64_t step, int32_t* actions, void* stream);
+/* Host-side twin of BatchSelectAction with epsilon >= 1 (the reference's
+ * agents/random_agent.py for a whole batch): HOST mask in, HOST actions out,
+ * identical to the device kernel for equal (seed, step, game). */
+int HostRandomLegalActions(const uint8_t* mask, int n, int num_actions, uint64_t seed,
+                           uint64_t step, int32_t* actions, int threads);
 int BatchC51QValues(const float* logits, const float* support, const uint8_t* mask, int n,
                     int num_actions, int num_atoms, float* q_out, int32_t* greedy_actions,
                     void* stream);
