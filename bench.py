@@ -202,7 +202,8 @@ def main():
 
   params = WORKLOADS[args.workload]
   n = args.games
-  seeds = (np.arange(n, dtype=np.int64) + 1 + rank * n).astype(np.int32)  # seed_i = 1 + global index
+  from hanabi_b200 import sharding
+  seeds = np.asarray(sharding.shard_seeds(1, world * n, rank, world), np.int32)  # 1 + global index
   batch = ph.HanabiBatch(params, n, seeds, device=local_rank)
   D, A = batch.obs_size, batch.max_moves
   obs = torch.empty((n, D), dtype=torch.uint8, device=dev)
@@ -241,8 +242,7 @@ def main():
     k_ev[t][0].record()
     batch.step_encode(act, rew, done, obs, mask, cur)
     k_ev[t][1].record()
-  if dist:
-    dist.all_reduce(stats)  # the only collective: 256 bytes of episode statistics
+  sharding.reduce_episode_statistics(stats)  # the only collective: 256 B over NCCL (no-op at N=1)
   ev1.record()
   torch.cuda.synchronize()
   clocks = sampler.stop()

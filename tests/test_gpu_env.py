@@ -1,0 +1,94 @@
+"""GPU tests of the layers above the kernels: BatchedHanabiEnv, the host-buffer
+entry points and the host twin of the random policy."""
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+from tests import common
+from tests.common import CONFIGS
+
+pytestmark = pytest.mark.gpu
+
+
+def test_batched_env_matches_reference_semantics():
+  import torch
+  from hanabi_b200 import rl_env
+  n = 300
+  env = rl_env.make_batched("Hanabi-Full", num_players=3, num_games=n, seed=41)
+  cpu = O.CpuBatch("ref" if O.have_ref() else "oracle",
+                   dict(players=3, colors=5, ranks=5, max_information_tokens=8, max_life_tokens=3,
+                        observation_type=1), n, common.seeds_for(n, base=41))
+  assert env.vectorized_observation_shape() == [956] and env.num_moves() == 30
+  obs = env.reset()
+  cpu.reset()
+  rng = np.random.default_rng(0)
+  for t in range(60):
+    common.assert_same(cpu.encode(), obs["vectorized"].cpu().numpy(), "vectorized @%d" % t)
+    mask = cpu.legal_mask()
+    common.assert_same(mask, obs["legal_moves_mask"].cpu().numpy(), "mask @%d" % t)
+    common.assert_same(cpu.cur_player(), obs["current_player"].cpu().numpy(), "cur @%d" % t)
+    legal_f = env.legal_moves_as_float().cpu().numpy()
+    assert ((legal_f == 0) == (mask == 1)).all() and np.isneginf(legal_f[mask == 0]).all()
+    a = common.choose_actions(None, mask, rng, False, 5, 5)
+    obs, reward, done, info = env.step(torch.as_tensor(a, device=env.device))
+    r, d, s, _ = cpu.step(a)
+    common.assert_same(r, reward.cpu().numpy(), "reward")
+    common.assert_same(d, done.cpu().numpy(), "done")
+    common.assert_same(s, info["score"].cpu().numpy(), "score")
+  st = env.episode_statistics()
+  assert st["episodes"] > 0
+
+
+def test_host_buffer_entry_points_match_device_path():
+  import torch
+  from hanabi_b200 import pyhanabi as ph
+  n = 70000  # several chunks, ragged last tile
+  params = CONFIGS["full2"]
+  seeds = common.seeds_for(n, base=5)
+  dev = ph.HanabiBatch(params, n, seeds)
+  host = ph.HanabiBatch(params, n, seeds)
+  D, A = dev.obs_size, dev.max_moves
+  cuda = torch.device("cuda:0")
+  d_obs = torch.zeros((n, D), dtype=torch.uint8, device=cuda)
+  d_mask = torch.zeros((n, A), dtype=torch.uint8, device=cuda)
+  d_cur = torch.zeros(n, dtype=torch.int32, device=cuda)
+  d_rew = torch.zeros(n, dtype=torch.int32, device=cuda)
+  d_done = torch.zeros(n, dtype=torch.uint8, device=cuda)
+  d_score = torch.zeros(n, dtype=torch.int32, device=cuda)
+  d_act = torch.zeros(n, dtype=torch.int32, device=cuda)
+  h_obs = torch.zeros((n, D), dtype=torch.uint8).pin_memory()
+  h_mask = torch.zeros((n, A), dtype=torch.uint8).pin_memory()
+  h_cur = torch.zeros(n, dtype=torch.int32).pin_memory()
+  h_rew = torch.zeros(n, dtype=torch.int32).pin_memory()
+  h_done = torch.zeros(n, dtype=torch.uint8).pin_memory()
+  h_score = torch.zeros(n, dtype=torch.int32).pin_memory()
+  h_act = torch.zeros(n, dtype=torch.int32).pin_memory()
+  dev.reset()
+  dev.observe(d_obs, d_mask, d_cur)
+  host.reset_host(h_obs, h_mask, h_cur)
+  for t in range(12):
+    assert torch.equal(d_obs.cpu(), h_obs) and torch.equal(d_mask.cpu(), h_mask)
+    assert torch.equal(d_cur.cpu(), h_cur)
+    # the host policy is the bit-identical twin of the device kernel
+    ph.select_action(None, d_mask, 1.0, seed=7, step=t, out=d_act)
+    ph.host_random_legal_actions(h_mask, seed=7, step=t, out=h_act)
+    assert torch.equal(d_act.cpu(), h_act)
+    dev.step_encode(d_act, d_rew, d_done, d_obs, d_mask, d_cur, scores=d_score)
+    host.step_encode_host(h_act, h_rew, h_done, h_obs, h_mask, h_cur, scores=h_score)
+    assert torch.equal(d_rew.cpu(), h_rew) and torch.equal(d_done.cpu(), h_done)
+    assert torch.equal(d_score.cpu(), h_score)
+  # padded host pitch
+  h_pad = torch.full((n, D + 14), 9, dtype=torch.uint8).pin_memory()
+  host.step_encode_host(h_act, h_rew, h_done, h_pad, h_mask, h_cur)
+  dev.step_encode(d_act, d_rew, d_done, d_obs, d_mask, d_cur)
+  assert torch.equal(h_pad[:, :D], d_obs.cpu()) and (h_pad[:, D:] == 9).all()
+
+
+def test_new_batch_rejects_bad_parameters():
+  from hanabi_b200 import pyhanabi as ph
+  with pytest.raises(RuntimeError, match="hand_size"):
+    ph.HanabiBatch(dict(players=2, hand_size=7), 4, [1, 2, 3, 4])
+  with pytest.raises(RuntimeError, match="players"):
+    ph.HanabiBatch(dict(players=6), 4, [1, 2, 3, 4])
+  with pytest.raises(RuntimeError, match="deck"):
+    ph.HanabiBatch(dict(players=5, colors=1, ranks=5, hand_size=4), 4, [1, 2, 3, 4])
