@@ -19,7 +19,8 @@
 namespace hb {
 
 enum Mode { kModeStep = 0, kModeReset = 1, kModeObserve = 2 };
-constexpr int kBlock = 128;
+constexpr int kBlock = 256;      // games per CTA
+constexpr int kQueueCap = 128;   // finished games a CTA re-deals through the shared-memory queue
 constexpr int kStreamPad = 2;    // readable pad words after each packed bit stream
 constexpr int kNumStats = 32;    // [0] episodes [1] sum score [2] sum length [3..28] score histogram
 constexpr int kDumpLen = 272;    // canonical unpacked state, see oracle/oracle_api.h
@@ -46,86 +47,144 @@ struct KArgs {
   int warp_smem_words;  // shared-memory words per warp: obs stream + mask stream + pads
 };
 
+// One CTA = 256 games = 8 warp tiles.  Phases separated by CTA barriers keep the
+// warps of an SM inside the same stretch of code (the kernel is ~100 KB of SASS,
+// far beyond the instruction caches) and let finished games be re-dealt by
+// compacted threads:
+//   A  load state (+ prefetch two RNG words) -> apply move -> deal -> terminal;
+//      finished games enqueue themselves in shared memory
+//   B  the first n threads of the CTA draw the initial deals of the n queued games
+//   C  install new games, store state, encode observation + legal mask into the
+//      warp's packed bit stream, expand to bytes with 128-bit stores
 template <class V, int MODE>
 __global__ void __launch_bounds__(kBlock) k_main(const __grid_constant__ KArgs a) {
   extern __shared__ uint32_t smem[];
   __shared__ int s_stats[kNumStats];
+  __shared__ int s_nq;
+  __shared__ int s_q_tid[kQueueCap];
+  __shared__ int s_q_mti[kQueueCap];
+  __shared__ ResetResult s_res[kQueueCap];
   const V v(a.spec);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t g = a.g_begin + (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  const int64_t cta0 = a.g_begin + (int64_t)blockIdx.x * kBlock;
+  const int64_t g = cta0 + threadIdx.x;
   const int64_t tile0 = g - lane;  // first game of this warp's tile
   const bool valid = g < a.g_end;
-  if (MODE == kModeStep) {
+  const bool tile_live = tile0 < a.g_end;
+  if (MODE != kModeObserve) {
     if (threadIdx.x < kNumStats) s_stats[threadIdx.x] = 0;
+    if (threadIdx.x == 0) s_nq = 0;
     __syncthreads();
   }
-  if (tile0 >= a.g_end) {
-    if (MODE == kModeStep) __syncthreads();
-    return;
-  }
   Game G;
-  if (valid) load_game(a.state, a.N, g, v, G);
-  else load_game(a.state, a.N, tile0, v, G);  // keep the lane well-defined; never stored
+  Prefetch pre;
+  pre.r0 = pre.r1 = 0;
+  pre.valid_at = -1;
+  bool queued = false;
+  int slot = -1;
+  int reward = 0, done_out = 0, score_out = 0;
 
-  if (MODE == kModeStep) {
-    int reward = 0, done_out = 0, score_out = 0, illegal = 0;
-    bool moved = false, term = false;
-    int ep_len = 0;
-    if (valid) {
-      if (G.done) {
-        done_out = 1;  // finished game, no auto-reset: the step is a no-op
-        score_out = score_of(v, G);
-      } else {
-        const int uid = a.actions[g];
-        const uint64_t legal = legal_bits(v, G);
-        if (uid < 0 || uid >= a.spec.max_moves || !((legal >> uid) & 1ull)) {
-          illegal = 1;
-          G.err = 1;
+  // ---------------------------------------------------------------- phase A
+  if (tile_live) {
+    load_game(a.state, a.N, valid ? g : tile0, v, G);  // idle lanes mirror a live game; never stored
+    bool restart = false;
+    if (MODE == kModeStep) {
+      if (valid && !G.done && G.mti + 2 <= kMtN) {
+        const uint32_t* my = a.mt + g * (int64_t)kMtN + G.mti;
+        pre.r0 = __ldcg(my);
+        pre.r1 = __ldcg(my + 1);
+        pre.valid_at = G.mti;
+      }
+      bool moved = false, term = false;
+      int ep_len = 0;
+      if (valid) {
+        if (G.done) {
+          done_out = 1;  // finished game, no auto-reset: the step is a no-op
           score_out = score_of(v, G);
         } else {
-          const int before = score_of(v, G);
-          apply_move(v, G, uid);
-          score_out = score_of(v, G);
-          reward = score_out - before;  // rl_env.py:363
-          term = is_terminal(v, G);
-          done_out = term ? 1 : 0;
-          ep_len = G.eplen;
-          moved = true;
+          const int uid = a.actions[g];
+          const uint64_t legal = legal_bits(v, G);
+          if (uid < 0 || uid >= a.spec.max_moves || !((legal >> uid) & 1ull)) {
+            G.err = 1;  // illegal action: game unchanged, flagged
+            score_out = score_of(v, G);
+          } else {
+            const int before = score_of(v, G);
+            apply_move(v, G, uid);
+            score_out = score_of(v, G);
+            reward = score_out - before;  // rl_env.py:363
+            term = is_terminal(v, G);
+            done_out = term ? 1 : 0;
+            ep_len = G.eplen;
+            moved = true;
+          }
         }
       }
-    }
-    // the deal that follows a play/discard (also for a game that just ended: the
-    // reference deals before it looks at IsTerminal), then the re-deal of finished games
-    deal_loop(v, a.spec, G, moved, false, g, a.mt, lane, a.sampler_mode);
-    restart_games(v, a.spec, G, term && a.auto_reset, g, a.mt, lane, a.sampler_mode);
-    if (valid) {
+      // the deal that follows a play/discard -- also for a game that just ended:
+      // the reference deals before it looks at IsTerminal (rl_env.py:357-361)
+      deal_loop(v, a.spec, G, moved, false, g, a.mt, lane, a.sampler_mode, &pre);
       if (term && !a.auto_reset) G.done = 1;
+      restart = term && a.auto_reset;
+      // episode statistics: warp aggregate -> CTA shared counters
+      const unsigned tm = __ballot_sync(kFull, term);
+      if (tm) {
+        const int ssum = __reduce_add_sync(kFull, term ? score_out : 0);
+        const int lsum = __reduce_add_sync(kFull, term ? ep_len : 0);
+        if (lane == 0) {
+          atomicAdd(&s_stats[0], __popc(tm));
+          atomicAdd(&s_stats[1], ssum);
+          atomicAdd(&s_stats[2], lsum);
+        }
+        if (term) atomicAdd(&s_stats[3 + (score_out > 25 ? 25 : score_out)], 1);
+      }
+    } else if (MODE == kModeReset) {
+      restart = valid && (a.which == nullptr || a.which[g] != 0);
+      if (restart) { G.done = 0; G.err = 0; }
+    }
+    if (MODE != kModeObserve) {
+      queued = restart && a.spec.fast_reset && (G.mti + 2 * v.P() * v.H() <= kMtN);
+      const unsigned qm = __ballot_sync(kFull, queued);
+      if (qm) {
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&s_nq, __popc(qm));
+        base = __shfl_sync(kFull, base, 0);
+        slot = base + __popc(qm & ((1u << lane) - 1u));
+        if (queued && slot >= kQueueCap) queued = false;  // queue full: general path below
+        if (queued) {
+          s_q_tid[slot] = threadIdx.x;
+          s_q_mti[slot] = G.mti;
+        }
+      }
+      const bool slow = restart && !queued;  // random start player, block boundary, tiny decks
+      if (__any_sync(kFull, slow))
+        deal_loop(v, a.spec, G, slow, slow, g, a.mt, lane, a.sampler_mode);
+    }
+  }
+
+  // ---------------------------------------------------------------- phase B
+  if (MODE != kModeObserve) {
+    __syncthreads();
+    const int nq = s_nq < kQueueCap ? s_nq : kQueueCap;
+    for (int i = threadIdx.x; i < nq; i += kBlock) {
+      const int64_t gq = cta0 + s_q_tid[i];
+      reset_draw(v, a.spec, a.mt + gq * (int64_t)kMtN + s_q_mti[i], a.sampler_mode, s_res[i]);
+    }
+    __syncthreads();
+    if (MODE == kModeStep && a.stats && threadIdx.x < kNumStats && s_stats[threadIdx.x] != 0)
+      atomicAdd(&a.stats[threadIdx.x], (unsigned long long)s_stats[threadIdx.x]);
+  }
+  if (!tile_live) return;
+
+  // ---------------------------------------------------------------- phase C
+  if (queued) reset_apply(v, a.spec, G, s_res[slot]);
+  if (valid) {
+    if (MODE == kModeStep) {
       if (a.rewards) a.rewards[g] = reward;
       if (a.dones) a.dones[g] = (uint8_t)done_out;
       if (a.scores) a.scores[g] = score_out;
     }
-    (void)illegal;
-    // episode statistics: warp aggregate -> CTA shared counters -> one global atomic per CTA
-    const unsigned tm = __ballot_sync(kFull, term);
-    if (tm) {
-      const int ssum = __reduce_add_sync(kFull, term ? score_out : 0);
-      const int lsum = __reduce_add_sync(kFull, term ? ep_len : 0);
-      if (lane == 0) {
-        atomicAdd(&s_stats[0], __popc(tm));
-        atomicAdd(&s_stats[1], ssum);
-        atomicAdd(&s_stats[2], lsum);
-      }
-      if (term) atomicAdd(&s_stats[3 + (score_out > 25 ? 25 : score_out)], 1);
-    }
-  } else if (MODE == kModeReset) {
-    const bool restart = valid && (a.which == nullptr || a.which[g] != 0);
-    if (restart) { G.done = 0; G.err = 0; }
-    restart_games(v, a.spec, G, restart, g, a.mt, lane, a.sampler_mode);
+    if (a.cur_player) a.cur_player[g] = G.cur;
+    if (MODE != kModeObserve) store_game(a.state, a.N, g, v, G);
   }
-
-  if (valid && a.cur_player) a.cur_player[g] = G.cur;
-  if (valid && MODE != kModeObserve) store_game(a.state, a.N, g, v, G);
-
   const int n_valid = (int)((a.g_end - tile0) < 32 ? (a.g_end - tile0) : 32);
   uint32_t* obs_stream = smem + (size_t)warp * a.warp_smem_words;
   uint32_t* mask_stream = obs_stream + a.spec.obs_size + kStreamPad;
@@ -141,12 +200,6 @@ __global__ void __launch_bounds__(kBlock) k_main(const __grid_constant__ KArgs a
   if (a.mask)
     expand_stream(mask_stream, a.spec.max_moves, a.mask + tile0 * a.spec.max_moves,
                   a.spec.max_moves, n_valid, lane);
-
-  if (MODE == kModeStep) {
-    __syncthreads();
-    if (a.stats && threadIdx.x < kNumStats && s_stats[threadIdx.x] != 0)
-      atomicAdd(&a.stats[threadIdx.x], (unsigned long long)s_stats[threadIdx.x]);
-  }
 }
 
 // std::mt19937::seed(value) per game; index = 624 forces a block regeneration on
@@ -392,7 +445,15 @@ hb::KArgs BaseArgs(const Batch* b) {
 template <class V, int MODE>
 cudaError_t LaunchOne(const Batch* b, const hb::KArgs& a, cudaStream_t stream) {
   const unsigned grid = (unsigned)((a.g_end - a.g_begin + hb::kBlock - 1) / hb::kBlock);
-  (void)b;
+  static size_t allowed[16] = {0};  // per device: dynamic shared memory already opted in
+  const int dev = b->device & 15;
+  if (b->smem_bytes > allowed[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(hb::k_main<V, MODE>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)b->smem_bytes);
+    if (e != cudaSuccess) return e;
+    allowed[dev] = b->smem_bytes;
+  }
   hb::k_main<V, MODE><<<grid, hb::kBlock, b->smem_bytes, stream>>>(a);
   return cudaGetLastError();
 }

@@ -189,11 +189,26 @@ HB_DEV void mt_twist_warp(uint32_t* mt, int lane) {
 // Warp-convergent service: every lane asks for need in {0,1,2} consecutive
 // words of ITS game's stream.  Lanes whose block is exhausted get it regenerated
 // by the whole warp.  Must be called by all 32 lanes.
+// Raw (untempered) words mti and mti+1 of a game's block, loaded together with
+// the game state so that the deal that follows most moves does not wait on a
+// second dependent global load.  valid_at = the index they were read at, -1 = none.
+struct Prefetch {
+  uint32_t r0, r1;
+  int valid_at;
+};
+
 HB_DEV void warp_fetch_words(uint32_t* mt_all, int64_t g, int& mti, int need, int lane,
-                             uint32_t& w0, uint32_t& w1) {
+                             uint32_t& w0, uint32_t& w1, Prefetch* pre = nullptr) {
   uint32_t* my = mt_all + g * (int64_t)kMtN;
   int got = 0;
-  if (need >= 1 && mti < kMtN) { w0 = mt_temper(__ldcg(my + mti)); ++mti; got = 1; }
+  if (pre != nullptr && need == 2 && pre->valid_at == mti) {
+    w0 = mt_temper(pre->r0);
+    w1 = mt_temper(pre->r1);
+    mti += 2;
+    got = 2;
+    pre->valid_at = -1;
+  }
+  if (need >= 1 && got == 0 && mti < kMtN) { w0 = mt_temper(__ldcg(my + mti)); ++mti; got = 1; }
   if (need >= 2 && got == 1 && mti < kMtN) { w1 = mt_temper(__ldcg(my + mti)); ++mti; got = 2; }
   unsigned tw = __ballot_sync(kFull, got < need);
   while (tw) {
@@ -509,7 +524,7 @@ HB_DEV void init_fresh(V v, const Spec& spec, Game& G, int start_player) {
 // hanabi_game.h:114) and deal its P*H cards.
 template <class V>
 HB_DEV void deal_loop(V v, const Spec& spec, Game& G, bool active, bool restart, int64_t g,
-                      uint32_t* mt_all, int lane, int sampler_mode) {
+                      uint32_t* mt_all, int lane, int sampler_mode, Prefetch* pre = nullptr) {
   for (;;) {
     bool need = active && needs_deal(v, G);
     int fresh_need_start = 0;
@@ -538,7 +553,7 @@ HB_DEV void deal_loop(V v, const Spec& spec, Game& G, bool active, bool restart,
     if (!__any_sync(kFull, need)) break;
     const bool multi = need && deck_types(spec, G.deck) >= 2;
     uint32_t lo = 0, hi = 0;
-    warp_fetch_words(mt_all, g, G.mti, multi ? 2 : 0, lane, lo, hi);
+    warp_fetch_words(mt_all, g, G.mti, multi ? 2 : 0, lane, lo, hi, pre);
     if (need) {
       int pos;
       if (multi) {
@@ -554,67 +569,85 @@ HB_DEV void deal_loop(V v, const Spec& spec, Game& G, bool active, bool restart,
   }
 }
 
-// New game for the lanes with `restart` set, unrolled: all 2*P*H RNG words of
-// the initial deal are known to lie inside the current mt19937 block and every
-// draw is a >= 2-type draw (spec.fast_reset), so the loads are independent and
-// the P*H dependent select steps are straight-line code.  Player 0's hand is
-// filled first, then player 1's, ... (PlayerToDeal, hanabi_state.cc:157-164).
+// ---- re-deal of finished games, compacted over the CTA ----------------------
+// Finished games that qualify (spec.fast_reset: no random start player and every
+// draw of the initial deal is a >= 2-type draw; all 2*P*H RNG words inside the
+// game's current mt19937 block) are queued in shared memory; after a barrier the
+// first threads of the CTA each draw one queued game's P*H cards, so the draw
+// code runs on densely populated warps instead of the few finished lanes of
+// every warp.  A rolled loop keeps the code small.
+struct ResetResult {
+  uint32_t cards[kMaxPlayers];
+  uint32_t deck_lo, deck_hi;
+};
+
+// Draws the initial deal of one game from RNG words `words[0 .. 2*P*H)`.  Player
+// 0's hand is filled first, then player 1's, ... (PlayerToDeal, hanabi_state.cc:157-164).
 template <class V>
-HB_DEV void reset_fast(V v, const Spec& spec, Game& G, bool restart, int64_t g, uint32_t* mt_all,
-                       int sampler_mode) {
-  if (!restart) return;
-  init_fresh(v, spec, G, 0);
-  const uint32_t* my = mt_all + g * (int64_t)kMtN + G.mti;
-  const int H = v.H();
-  uint64_t deck = G.deck;
+HB_DEV void reset_draw(V v, const Spec& spec, const uint32_t* words, int sampler_mode,
+                       ResetResult& out) {
+  uint64_t deck = spec.full_deck;
   int n = v.deck_max();
+  const int H = v.H(), total = v.P() * H;
+#pragma unroll
+  for (int p = 0; p < kMaxPlayers; ++p) out.cards[p] = 0;
+  int p = 0, i = 0;
+#pragma unroll 1
+  for (int r = 0; r < total; ++r) {
+    const uint32_t lo = mt_temper(__ldcg(words + 2 * r));
+    const uint32_t hi = mt_temper(__ldcg(words + 2 * r + 1));
+    bool amb = false;
+    int pos = pick_fast(deck, n, lo, hi, amb);
+    if (sampler_mode == 1 || (amb && sampler_mode != 2)) pos = pick_exact(v, deck, n, lo, hi);
+    int color, rank;
+    card_of_position(v, pos, color, rank);
+    const uint32_t card = (uint32_t)(color | (rank << 3)) << (6 * i);
+#pragma unroll
+    for (int k = 0; k < V::kP; ++k) out.cards[k] |= (k == p) ? card : 0u;
+    deck &= ~(1ull << pos);
+    --n;
+    if (++i == H) { i = 0; ++p; }
+  }
+  out.deck_lo = (uint32_t)deck;
+  out.deck_hi = (uint32_t)(deck >> 32);
+}
+
+// Installs a drawn initial deal as the lane's new game.
+template <class V>
+HB_DEV void reset_apply(V v, const Spec& spec, Game& G, const ResetResult& res) {
+  init_fresh(v, spec, G, 0);
+  const int H = v.H();
   const bool seer = spec.obs_type == kSeer;
+  uint32_t call = 0, rall = 0;
+#pragma unroll
+  for (int i = 0; i < V::kH; ++i)
+    if (i < H) { call |= ((1u << v.C()) - 1u) << (5 * i); rall |= ((1u << v.R()) - 1u) << (5 * i); }
+  const uint32_t flags = (1u << H) - 1u;
 #pragma unroll
   for (int p = 0; p < V::kP; ++p) {
     if (p < v.P()) {
-      uint32_t cards = 0, cpl = 0, rpl = 0;
+      G.cards[p] = res.cards[p];
+      G.cpl[p] = call;
+      G.rpl[p] = rall;
+      G.hw[p] = (uint32_t)H << 16;
+      if (seer) {  // hanabi_state.cc:233-236: knowledge starts as the card itself
+        uint32_t c1 = 0, r1 = 0;
 #pragma unroll
-      for (int i = 0; i < V::kH; ++i) {
-        if (i < H) {
-          const int r = p * H + i;
-          const uint32_t lo = mt_temper(__ldcg(my + 2 * r));
-          const uint32_t hi = mt_temper(__ldcg(my + 2 * r + 1));
-          bool amb = false;
-          int pos = pick_fast(deck, n, lo, hi, amb);
-          if (sampler_mode == 1 || (amb && sampler_mode != 2)) pos = pick_exact(v, deck, n, lo, hi);
-          int color, rank;
-          card_of_position(v, pos, color, rank);
-          cards |= (uint32_t)(color | (rank << 3)) << (6 * i);
-          cpl |= (seer ? (1u << color) : ((1u << v.C()) - 1u)) << (5 * i);
-          rpl |= (seer ? (1u << rank) : ((1u << v.R()) - 1u)) << (5 * i);
-          deck &= ~(1ull << pos);
-          --n;
-        }
+        for (int i = 0; i < V::kH; ++i)
+          if (i < H) {
+            const uint32_t f = res.cards[p] >> (6 * i);
+            c1 |= (1u << (f & 7)) << (5 * i);
+            r1 |= (1u << ((f >> 3) & 7)) << (5 * i);
+          }
+        G.cpl[p] = c1;
+        G.rpl[p] = r1;
+        G.hw[p] |= flags | (flags << 8);
       }
-      G.cards[p] = cards;
-      G.cpl[p] = cpl;
-      G.rpl[p] = rpl;
-      const uint32_t all = (1u << H) - 1u;
-      G.hw[p] = ((uint32_t)H << 16) | (seer ? (all | (all << 8)) : 0u);
     }
   }
-  G.deck = deck;
-  G.deck_size = n;
+  G.deck = (uint64_t)res.deck_lo | ((uint64_t)res.deck_hi << 32);
+  G.deck_size = v.deck_max() - v.P() * H;
   G.mti += 2 * v.P() * H;
-}
-
-// Warp-convergent restart of the flagged lanes: the unrolled path when every
-// flagged lane qualifies, else the general deal loop.
-template <class V>
-HB_DEV void restart_games(V v, const Spec& spec, Game& G, bool restart, int64_t g,
-                          uint32_t* mt_all, int lane, int sampler_mode) {
-  if (!__any_sync(kFull, restart)) return;
-  const bool lane_ok = !restart || (G.mti + 2 * v.P() * v.H() <= kMtN);
-  if (spec.fast_reset && __all_sync(kFull, lane_ok)) {
-    reset_fast(v, spec, G, restart, g, mt_all, sampler_mode);
-  } else {
-    deal_loop(v, spec, G, restart, restart, g, mt_all, lane, sampler_mode);
-  }
 }
 
 // ------------------------------------------------------------------ encoding
