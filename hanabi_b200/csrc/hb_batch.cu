@@ -20,7 +20,8 @@ namespace hb {
 
 enum Mode { kModeStep = 0, kModeReset = 1, kModeObserve = 2 };
 constexpr int kBlock = 256;      // games per CTA
-constexpr int kQueueCap = 128;   // finished games a CTA re-deals through the shared-memory queue
+constexpr int kWarps = kBlock / 32;
+constexpr int kQueueCap = 64;    // finished games a CTA re-deals through the shared-memory queue
 constexpr int kStreamPad = 2;    // readable pad words after each packed bit stream
 constexpr int kNumStats = 32;    // [0] episodes [1] sum score [2] sum length [3..28] score histogram
 constexpr int kDumpLen = 272;    // canonical unpacked state, see oracle/oracle_api.h
@@ -78,8 +79,7 @@ __global__ void __launch_bounds__(kBlock) k_main(const __grid_constant__ KArgs a
   }
   Game G;
   Prefetch pre;
-  pre.r0 = pre.r1 = 0;
-  pre.valid_at = -1;
+  pre.at = -1;
   bool queued = false;
   int slot = -1;
   int reward = 0, done_out = 0, score_out = 0;
@@ -89,12 +89,10 @@ __global__ void __launch_bounds__(kBlock) k_main(const __grid_constant__ KArgs a
     load_game(a.state, a.N, valid ? g : tile0, v, G);  // idle lanes mirror a live game; never stored
     bool restart = false;
     if (MODE == kModeStep) {
-      if (valid && !G.done && G.mti + 2 <= kMtN) {
-        const uint32_t* my = a.mt + g * (int64_t)kMtN + G.mti;
-        pre.r0 = __ldcg(my);
-        pre.r1 = __ldcg(my + 1);
-        pre.valid_at = G.mti;
-      }
+      const int uid = valid ? a.actions[g] : -1;
+      // a play/discard is followed by a deal: start fetching its RNG words now
+      if (valid && !G.done && uid >= 0 && uid < 2 * v.H() && G.deck_size > 0)
+        mt_load5(a.mt + g * (int64_t)kMtN, G.mti, pre);
       bool moved = false, term = false;
       int ep_len = 0;
       if (valid) {
@@ -102,7 +100,6 @@ __global__ void __launch_bounds__(kBlock) k_main(const __grid_constant__ KArgs a
           done_out = 1;  // finished game, no auto-reset: the step is a no-op
           score_out = score_of(v, G);
         } else {
-          const int uid = a.actions[g];
           const uint64_t legal = legal_bits(v, G);
           if (uid < 0 || uid >= a.spec.max_moves || !((legal >> uid) & 1ull)) {
             G.err = 1;  // illegal action: game unchanged, flagged
@@ -121,7 +118,7 @@ __global__ void __launch_bounds__(kBlock) k_main(const __grid_constant__ KArgs a
       }
       // the deal that follows a play/discard -- also for a game that just ended:
       // the reference deals before it looks at IsTerminal (rl_env.py:357-361)
-      deal_loop(v, a.spec, G, moved, false, g, a.mt, lane, a.sampler_mode, &pre);
+      if (moved) deal_loop(v, a.spec, G, false, g, a.mt, a.sampler_mode, &pre);
       if (term && !a.auto_reset) G.done = 1;
       restart = term && a.auto_reset;
       // episode statistics: warp aggregate -> CTA shared counters
@@ -141,7 +138,7 @@ __global__ void __launch_bounds__(kBlock) k_main(const __grid_constant__ KArgs a
       if (restart) { G.done = 0; G.err = 0; }
     }
     if (MODE != kModeObserve) {
-      queued = restart && a.spec.fast_reset && (G.mti + 2 * v.P() * v.H() <= kMtN);
+      queued = restart && a.spec.fast_reset;
       const unsigned qm = __ballot_sync(kFull, queued);
       if (qm) {
         int base = 0;
@@ -154,9 +151,8 @@ __global__ void __launch_bounds__(kBlock) k_main(const __grid_constant__ KArgs a
           s_q_mti[slot] = G.mti;
         }
       }
-      const bool slow = restart && !queued;  // random start player, block boundary, tiny decks
-      if (__any_sync(kFull, slow))
-        deal_loop(v, a.spec, G, slow, slow, g, a.mt, lane, a.sampler_mode);
+      // random start player / tiny decks / queue overflow: general per-thread path
+      if (restart && !queued) deal_loop(v, a.spec, G, true, g, a.mt, a.sampler_mode);
     }
   }
 
@@ -164,9 +160,37 @@ __global__ void __launch_bounds__(kBlock) k_main(const __grid_constant__ KArgs a
   if (MODE != kModeObserve) {
     __syncthreads();
     const int nq = s_nq < kQueueCap ? s_nq : kQueueCap;
-    for (int i = threadIdx.x; i < nq; i += kBlock) {
-      const int64_t gq = cta0 + s_q_tid[i];
-      reset_draw(v, a.spec, a.mt + gq * (int64_t)kMtN + s_q_mti[i], a.sampler_mode, s_res[i]);
+    if (nq > 0) {  // CTA-uniform
+      // B1: one thread per (queued game, word pair) takes the pair from the game's
+      // stream: all loads first, barrier, then the regenerated slots are stored
+      // (a pair's x[k+2] is the next pair's slot, so stores wait for every load)
+      uint32_t* s_words = smem + (size_t)kWarps * a.warp_smem_words;
+      const int pairs = v.P() * v.H();
+      for (int k0 = 0; k0 < nq * pairs; k0 += kBlock) {  // CTA-uniform trip count
+        const int k = k0 + threadIdx.x;
+        const bool act = k < nq * pairs;
+        Prefetch f;
+        uint32_t* x = a.mt;
+        int at = 0;
+        if (act) {
+          const int e = k / pairs, r = k - e * pairs;
+          x = a.mt + (cta0 + s_q_tid[e]) * (int64_t)kMtN;
+          at = mt_wrap(s_q_mti[e] + 2 * r);
+          mt_load5(x, at, f);
+          s_words[2 * k] = mt_temper(f.a);
+          s_words[2 * k + 1] = mt_temper(f.b);
+        }
+        __syncthreads();
+        if (act) {
+          __stcg(x + at, mt_next_block_word(f.a, f.b, f.p));
+          __stcg(x + mt_wrap(at + 1), mt_next_block_word(f.b, f.c, f.q));
+        }
+      }
+      const int per_game = 2 * pairs;
+      __syncthreads();
+      // B2: one thread per queued game draws its initial deal from shared memory
+      for (int i = threadIdx.x; i < nq; i += kBlock)
+        reset_draw(v, a.spec, s_words + i * per_game, a.sampler_mode, s_res[i]);
     }
     __syncthreads();
     if (MODE == kModeStep && a.stats && threadIdx.x < kNumStats && s_stats[threadIdx.x] != 0)
@@ -202,8 +226,9 @@ __global__ void __launch_bounds__(kBlock) k_main(const __grid_constant__ KArgs a
                   a.spec.max_moves, n_valid, lane);
 }
 
-// std::mt19937::seed(value) per game; index = 624 forces a block regeneration on
-// first use, as libstdc++ does.
+// std::mt19937::seed(value) per game followed by the first block regeneration
+// (libstdc++ does it lazily on the first draw), so that the block holds outputs
+// 0..623 (untempered) and the index starts at 0.
 __global__ void k_seed(uint32_t* mt, const int32_t* seeds, int64_t N) {
   const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= N) return;
@@ -214,14 +239,15 @@ __global__ void k_seed(uint32_t* mt, const int32_t* seeds, int64_t N) {
     x = 1812433253u * (x ^ (x >> 30)) + (uint32_t)i;
     my[i] = x;
   }
+  for (int k = 0; k < kMtN; ++k)
+    my[k] = mt_next_block_word(my[k], my[mt_wrap(k + 1)], my[mt_wrap(k + kMtM)]);
 }
 
 __global__ void k_blank(uint4* state, int64_t N, int ncols) {
   const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= N) return;
   for (int c = 0; c < ncols; ++c) state[(int64_t)c * N + g] = make_uint4(0, 0, 0, 0);
-  // mt index 624: first draw regenerates the block
-  state[(int64_t)(ncols - 1) * N + g] = make_uint4(0, (uint32_t)kMtN << 6, 0, 0);
+  state[(int64_t)(ncols - 1) * N + g] = make_uint4(0, 0, 0, 0);
 }
 
 // Packed state -> canonical unpacked dump (oracle/oracle_api.h layout).
@@ -513,7 +539,8 @@ int NewBatch(pyhanabi_batch_t* out, int list_length, const char** param_list, in
   b->N = num_games;
   b->ncols = b->spec.P + 2;
   b->warp_smem_words = b->spec.obs_size + b->spec.max_moves + 2 * hb::kStreamPad;
-  b->smem_bytes = (size_t)(hb::kBlock / 32) * b->warp_smem_words * sizeof(uint32_t);
+  b->smem_bytes = ((size_t)hb::kWarps * b->warp_smem_words +
+                   (size_t)hb::kQueueCap * 2 * b->spec.P * b->spec.H) * sizeof(uint32_t);
   DeviceGuard guard(device);
   if (!guard.ok) { delete b; return Fail("NewBatch: cudaSetDevice failed"); }
   int32_t* d_seeds = nullptr;

@@ -165,63 +165,60 @@ HB_DEV uint32_t mt_temper(uint32_t z) {
   return z;
 }
 
-// Whole-warp in-place regeneration of one game's 624-word block (the standard
-// genrand block step).  Within a 32-word slice every lane loads before any lane
-// stores; slices run in ascending order so that words k >= 227 see the new
-// values of words k - 227, exactly like the sequential loop.
-HB_DEV void mt_twist_warp(uint32_t* mt, int lane) {
-  for (int base = 0; base < kMtN; base += 32) {
-    const int k = base + lane;
-    uint32_t nv = 0;
-    if (k < kMtN) {
-      const int k1 = (k + 1 == kMtN) ? 0 : k + 1;
-      const int km = (k + kMtM >= kMtN) ? k + kMtM - kMtN : k + kMtM;
-      uint32_t a = __ldcg(mt + k), b = __ldcg(mt + k1), c = __ldcg(mt + km);
-      uint32_t y = (a & 0x80000000u) | (b & 0x7fffffffu);
-      nv = c ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
-    }
-    __syncwarp();
-    if (k < kMtN) __stcg(mt + k, nv);
-    __syncwarp();
-  }
+// mt19937 without the block "twist": every game keeps its 624-word block in HBM
+// and an index k.  Invariant: slots < k already hold the NEXT block's words, slots
+// >= k the current block's.  Taking word k immediately regenerates slot k for the
+// next block, x'[k] = x[k+397] ^ ((x[k] & UPPER | x[k+1] & LOWER) >> 1) ^ mag,
+// which reads exactly the values the sequential block regeneration of
+// std::mt19937 would read at that point (x[k+1] still old; x[k+397] old for
+// k < 227, already new for k >= 227; slot 623 sees the new slot 0).  The output
+// stream is therefore identical, no lane ever stalls on a 624-word regeneration,
+// and a draw costs five word loads and two word stores local to the thread.
+HB_DEV int mt_wrap(int i) { return i >= kMtN ? i - kMtN : i; }
+
+HB_DEV uint32_t mt_next_block_word(uint32_t cur, uint32_t next, uint32_t far) {
+  const uint32_t y = (cur & 0x80000000u) | (next & 0x7fffffffu);
+  return far ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
 }
 
-// Warp-convergent service: every lane asks for need in {0,1,2} consecutive
-// words of ITS game's stream.  Lanes whose block is exhausted get it regenerated
-// by the whole warp.  Must be called by all 32 lanes.
-// Raw (untempered) words mti and mti+1 of a game's block, loaded together with
-// the game state so that the deal that follows most moves does not wait on a
-// second dependent global load.  valid_at = the index they were read at, -1 = none.
+// Raw words needed to take two consecutive outputs at index `at`: x[at], x[at+1],
+// x[at+2], x[at+397], x[at+398] (indices mod 624).  Loaded together with the game
+// state so that the deal that follows most moves does not wait on a second
+// dependent global load.  at < 0 = nothing prefetched.
 struct Prefetch {
-  uint32_t r0, r1;
-  int valid_at;
+  uint32_t a, b, c, p, q;
+  int at;
 };
 
-HB_DEV void warp_fetch_words(uint32_t* mt_all, int64_t g, int& mti, int need, int lane,
-                             uint32_t& w0, uint32_t& w1, Prefetch* pre = nullptr) {
-  uint32_t* my = mt_all + g * (int64_t)kMtN;
-  int got = 0;
-  if (pre != nullptr && need == 2 && pre->valid_at == mti) {
-    w0 = mt_temper(pre->r0);
-    w1 = mt_temper(pre->r1);
-    mti += 2;
-    got = 2;
-    pre->valid_at = -1;
-  }
-  if (need >= 1 && got == 0 && mti < kMtN) { w0 = mt_temper(__ldcg(my + mti)); ++mti; got = 1; }
-  if (need >= 2 && got == 1 && mti < kMtN) { w1 = mt_temper(__ldcg(my + mti)); ++mti; got = 2; }
-  unsigned tw = __ballot_sync(kFull, got < need);
-  while (tw) {
-    const int src = __ffs(tw) - 1;
-    tw &= tw - 1;
-    const long long gs = __shfl_sync(kFull, (long long)g, src);
-    mt_twist_warp(mt_all + gs * (int64_t)kMtN, lane);
-  }
-  if (got < need) {
-    mti = 0;
-    if (got == 0) { w0 = mt_temper(__ldcg(my + mti)); ++mti; got = 1; }
-    if (need >= 2 && got == 1) { w1 = mt_temper(__ldcg(my + mti)); ++mti; }
-  }
+HB_DEV void mt_load5(const uint32_t* x, int k, Prefetch& f) {
+  const int k1 = mt_wrap(k + 1), k2 = mt_wrap(k + 2), m0 = mt_wrap(k + kMtM), m1 = mt_wrap(k + kMtM + 1);
+  f.a = __ldcg(x + k);
+  f.b = __ldcg(x + k1);
+  f.c = __ldcg(x + k2);
+  f.p = __ldcg(x + m0);
+  f.q = __ldcg(x + m1);
+  f.at = k;
+}
+
+// Takes outputs k and k+1 of the game's stream (tempered) and regenerates both slots.
+HB_DEV void mt_take2(uint32_t* x, int& k, uint32_t& w0, uint32_t& w1, Prefetch* pre) {
+  Prefetch f;
+  if (pre != nullptr && pre->at == k) { f = *pre; pre->at = -1; }
+  else mt_load5(x, k, f);
+  w0 = mt_temper(f.a);
+  w1 = mt_temper(f.b);
+  const int k1 = mt_wrap(k + 1);
+  __stcg(x + k, mt_next_block_word(f.a, f.b, f.p));
+  __stcg(x + k1, mt_next_block_word(f.b, f.c, f.q));
+  k = mt_wrap(k + 2);
+}
+
+// Takes one output (random start player draw).
+HB_DEV uint32_t mt_take1(uint32_t* x, int& k) {
+  const uint32_t a = __ldcg(x + k), b = __ldcg(x + mt_wrap(k + 1)), p = __ldcg(x + mt_wrap(k + kMtM));
+  __stcg(x + k, mt_next_block_word(a, b, p));
+  k = mt_wrap(k + 1);
+  return mt_temper(a);
 }
 
 // ------------------------------------------------------------- deal sampling
@@ -517,62 +514,48 @@ HB_DEV void init_fresh(V v, const Spec& spec, Game& G, int start_player) {
   G.last = 0;
 }
 
-// Warp-convergent: deals until no lane's game is waiting for a card.  Lanes
-// with `restart` set first finish the deals of the old game (the reference
-// deals before it looks at IsTerminal, rl_env.py:357-361), then start a new
-// game on the same RNG stream (one std::mt19937 per HanabiGame,
-// hanabi_game.h:114) and deal its P*H cards.
+// Deals until the game is not waiting for a card any more.  With `restart` the
+// deals of the old game are finished first (the reference deals before it looks
+// at IsTerminal, rl_env.py:357-361), then a new game starts on the same RNG
+// stream (one std::mt19937 per HanabiGame, hanabi_game.h:114) and gets its P*H
+// cards.  Purely per-thread.
 template <class V>
-HB_DEV void deal_loop(V v, const Spec& spec, Game& G, bool active, bool restart, int64_t g,
-                      uint32_t* mt_all, int lane, int sampler_mode, Prefetch* pre = nullptr) {
+HB_DEV void deal_loop(V v, const Spec& spec, Game& G, bool restart, int64_t g, uint32_t* mt_all,
+                      int sampler_mode, Prefetch* pre = nullptr) {
+  uint32_t* x = mt_all + g * (int64_t)kMtN;
   for (;;) {
-    bool need = active && needs_deal(v, G);
-    int fresh_need_start = 0;
-    if (active && !need && restart) {
+    bool need = needs_deal(v, G);
+    if (!need && restart) {
       restart = false;
       init_fresh(v, spec, G, 0);
-      fresh_need_start = spec.random_start ? 1 : 0;
-      need = needs_deal(v, G) && !fresh_need_start;
-    }
-    // Random start player: one bounded draw before the first deal
-    // (hanabi_game.cc:138-145), re-drawn on the (2^-30 rare) Lemire rejection.
-    unsigned sp = __ballot_sync(kFull, fresh_need_start != 0);
-    while (sp) {
-      uint32_t w0 = 0, w1 = 0;
-      warp_fetch_words(mt_all, g, G.mti, fresh_need_start, lane, w0, w1);
-      if (fresh_need_start) {
+      if (spec.random_start) {
+        // one bounded draw before the first deal (hanabi_game.cc:138-145),
+        // re-drawn on the (2^-30 rare) Lemire rejection
         uint32_t val;
-        if (lemire_accept(w0, (uint32_t)v.P(), val)) {
-          G.cur = (int)val;
-          fresh_need_start = 0;
-          need = needs_deal(v, G);
-        }
+        while (!lemire_accept(mt_take1(x, G.mti), (uint32_t)v.P(), val)) {}
+        G.cur = (int)val;
       }
-      sp = __ballot_sync(kFull, fresh_need_start != 0);
+      need = needs_deal(v, G);
     }
-    if (!__any_sync(kFull, need)) break;
-    const bool multi = need && deck_types(spec, G.deck) >= 2;
-    uint32_t lo = 0, hi = 0;
-    warp_fetch_words(mt_all, g, G.mti, multi ? 2 : 0, lane, lo, hi, pre);
-    if (need) {
-      int pos;
-      if (multi) {
-        bool amb = false;
-        pos = pick_fast(G.deck, G.deck_size, lo, hi, amb);
-        if (sampler_mode == 1 || (amb && sampler_mode != 2))
-          pos = pick_exact(v, G.deck, G.deck_size, lo, hi);
-      } else {
-        pos = __ffsll((long long)G.deck) - 1;  // one type left: no RNG words are consumed
-      }
-      deal_card(v, G, pos, spec.obs_type);
+    if (!need) break;
+    int pos;
+    if (deck_types(spec, G.deck) >= 2) {
+      uint32_t lo, hi;
+      mt_take2(x, G.mti, lo, hi, pre);
+      bool amb = false;
+      pos = pick_fast(G.deck, G.deck_size, lo, hi, amb);
+      if (sampler_mode == 1 || (amb && sampler_mode != 2))
+        pos = pick_exact(v, G.deck, G.deck_size, lo, hi);
+    } else {
+      pos = __ffsll((long long)G.deck) - 1;  // one type left: no RNG words are consumed
     }
+    deal_card(v, G, pos, spec.obs_type);
   }
 }
 
 // ---- re-deal of finished games, compacted over the CTA ----------------------
 // Finished games that qualify (spec.fast_reset: no random start player and every
-// draw of the initial deal is a >= 2-type draw; all 2*P*H RNG words inside the
-// game's current mt19937 block) are queued in shared memory; after a barrier the
+// draw of the initial deal is a >= 2-type draw) are queued in shared memory; after a barrier the
 // first threads of the CTA each draw one queued game's P*H cards, so the draw
 // code runs on densely populated warps instead of the few finished lanes of
 // every warp.  A rolled loop keeps the code small.
@@ -581,7 +564,8 @@ struct ResetResult {
   uint32_t deck_lo, deck_hi;
 };
 
-// Draws the initial deal of one game from RNG words `words[0 .. 2*P*H)`.  Player
+// Draws the initial deal of one game from TEMPERED RNG words `words[0 .. 2*P*H)`
+// (shared memory, fetched cooperatively by the CTA).  Player
 // 0's hand is filled first, then player 1's, ... (PlayerToDeal, hanabi_state.cc:157-164).
 template <class V>
 HB_DEV void reset_draw(V v, const Spec& spec, const uint32_t* words, int sampler_mode,
@@ -594,8 +578,8 @@ HB_DEV void reset_draw(V v, const Spec& spec, const uint32_t* words, int sampler
   int p = 0, i = 0;
 #pragma unroll 1
   for (int r = 0; r < total; ++r) {
-    const uint32_t lo = mt_temper(__ldcg(words + 2 * r));
-    const uint32_t hi = mt_temper(__ldcg(words + 2 * r + 1));
+    const uint32_t lo = words[2 * r];
+    const uint32_t hi = words[2 * r + 1];
     bool amb = false;
     int pos = pick_fast(deck, n, lo, hi, amb);
     if (sampler_mode == 1 || (amb && sampler_mode != 2)) pos = pick_exact(v, deck, n, lo, hi);
@@ -647,7 +631,7 @@ HB_DEV void reset_apply(V v, const Spec& spec, Game& G, const ResetResult& res) 
   }
   G.deck = (uint64_t)res.deck_lo | ((uint64_t)res.deck_hi << 32);
   G.deck_size = v.deck_max() - v.P() * H;
-  G.mti += 2 * v.P() * H;
+  G.mti = mt_wrap(G.mti + 2 * v.P() * H);
 }
 
 // ------------------------------------------------------------------ encoding

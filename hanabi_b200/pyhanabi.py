@@ -774,6 +774,30 @@ class HanabiBatch(object):
         self._p(cur_player, torch.int32, n, "int32_t*"), int(bool(auto_reset)), self._stream()),
            "BatchStepEncodeScores")
 
+  def bind_step_encode(self, actions, rewards=None, dones=None, obs=None, mask=None,
+                       cur_player=None, scores=None, auto_reset=True, stream=None):
+    """Pre-validated, pre-cast variant of step_encode for tight loops: returns a
+    zero-argument callable that launches the fused kernel on `stream` (default:
+    the stream current at bind time) with the given tensors.  The tensors must
+    stay alive and in place while the callable is used."""
+    torch = self._torch
+    n = self.num_games
+    optr, pitch = self._obs_ptr(obs)
+    args = (self._c, self._p(actions, torch.int32, n, "int32_t*"),
+            self._p(rewards, torch.int32, n, "int32_t*"), self._p(dones, torch.uint8, n, "uint8_t*"),
+            self._p(scores, torch.int32, n, "int32_t*"), optr, pitch,
+            self._p(mask, torch.uint8, n * self.max_moves, "uint8_t*"),
+            self._p(cur_player, torch.int32, n, "int32_t*"), int(bool(auto_reset)),
+            self._stream() if stream is None else ffi.cast("void*", stream.cuda_stream))
+    fn = lib.BatchStepEncodeScores
+    keep = (actions, rewards, dones, obs, mask, cur_player, scores)
+
+    def run(_args=args, _fn=fn, _keep=keep):
+      if _fn(*_args) != 0:
+        raise RuntimeError("BatchStepEncodeScores failed: %s" %
+                           encode_ffi_string(lib.BatchLastError()))
+    return run
+
   # -- host-buffer verbs (CPU tensors, ideally pinned); synchronous
   def _h(self, t, dtype, numel, ctype):
     if t is None:
@@ -912,6 +936,25 @@ def select_action(values, mask, epsilon, seed, step, support=None, out=None):
                                  _tp(out, torch.int32, "int32_t*"), _cur_stream(mask)),
            "BatchSelectAction")
   return out
+
+
+def bind_select_action(values, mask, epsilon, seed, out, support=None, stream=None):
+  """Pre-validated variant of select_action for tight loops: returns run(step)."""
+  import torch
+  _require_lib()
+  n, A = int(mask.shape[0]), int(mask.shape[1])
+  atoms = int(values.shape[2]) if values is not None and values.dim() == 3 else 0
+  s = _cur_stream(mask) if stream is None else ffi.cast("void*", stream.cuda_stream)
+  head = (_tp(values, torch.float32, "float*"), atoms, _tp(support, torch.float32, "float*"),
+          _tp(mask, torch.uint8, "uint8_t*"), n, A, float(epsilon), int(seed) & (2**64 - 1))
+  tail = (_tp(out, torch.int32, "int32_t*"), s)
+  fn = lib.BatchSelectAction
+  keep = (values, mask, out, support)
+
+  def run(step, _head=head, _tail=tail, _fn=fn, _keep=keep):
+    if _fn(*(_head + (step,) + _tail)) != 0:
+      raise RuntimeError("BatchSelectAction failed: %s" % encode_ffi_string(lib.BatchLastError()))
+  return run
 
 
 def host_random_legal_actions(mask, seed, step, out=None, threads=0):
