@@ -19,7 +19,13 @@
 namespace hb {
 
 enum Mode { kModeStep = 0, kModeReset = 1, kModeObserve = 2 };
-constexpr int kBlock = 256;      // games per CTA
+#ifndef HB_BLOCK
+#define HB_BLOCK 128
+#endif
+#ifndef HB_MIN_CTAS
+#define HB_MIN_CTAS 6
+#endif
+constexpr int kBlock = HB_BLOCK;  // games per CTA (measured best: 128 threads, 6 CTAs/SM, 80 registers)
 constexpr int kWarps = kBlock / 32;
 constexpr int kQueueCap = 64;    // finished games a CTA re-deals through the shared-memory queue
 constexpr int kStreamPad = 2;    // readable pad words after each packed bit stream
@@ -48,7 +54,7 @@ struct KArgs {
   int warp_smem_words;  // shared-memory words per warp: obs stream + mask stream + pads
 };
 
-// One CTA = 256 games = 8 warp tiles.  Phases separated by CTA barriers keep the
+// One CTA = kBlock games = kBlock/32 warp tiles.  Phases separated by CTA barriers keep the
 // warps of an SM inside the same stretch of code (the kernel is ~100 KB of SASS,
 // far beyond the instruction caches) and let finished games be re-dealt by
 // compacted threads:
@@ -58,13 +64,14 @@ struct KArgs {
 //   C  install new games, store state, encode observation + legal mask into the
 //      warp's packed bit stream, expand to bytes with 128-bit stores
 template <class V, int MODE>
-__global__ void __launch_bounds__(kBlock) k_main(const __grid_constant__ KArgs a) {
+__global__ void __launch_bounds__(kBlock, HB_MIN_CTAS) k_main(const __grid_constant__ KArgs a) {
   extern __shared__ uint32_t smem[];
   __shared__ int s_stats[kNumStats];
   __shared__ int s_nq;
   __shared__ int s_q_tid[kQueueCap];
   __shared__ int s_q_mti[kQueueCap];
   __shared__ ResetResult s_res[kQueueCap];
+  __shared__ uint32_t s_spread[32];
   const V v(a.spec);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t cta0 = a.g_begin + (int64_t)blockIdx.x * kBlock;
@@ -72,11 +79,12 @@ __global__ void __launch_bounds__(kBlock) k_main(const __grid_constant__ KArgs a
   const int64_t tile0 = g - lane;  // first game of this warp's tile
   const bool valid = g < a.g_end;
   const bool tile_live = tile0 < a.g_end;
+  if (threadIdx.x < 32) s_spread[threadIdx.x] = spread_entry(threadIdx.x, a.spec.C, a.spec.R);
   if (MODE != kModeObserve) {
     if (threadIdx.x < kNumStats) s_stats[threadIdx.x] = 0;
     if (threadIdx.x == 0) s_nq = 0;
-    __syncthreads();
   }
+  __syncthreads();
   Game G;
   Prefetch pre;
   pre.at = -1;
@@ -100,8 +108,7 @@ __global__ void __launch_bounds__(kBlock) k_main(const __grid_constant__ KArgs a
           done_out = 1;  // finished game, no auto-reset: the step is a no-op
           score_out = score_of(v, G);
         } else {
-          const uint64_t legal = legal_bits(v, G);
-          if (uid < 0 || uid >= a.spec.max_moves || !((legal >> uid) & 1ull)) {
+          if (!move_is_legal(v, G, uid, a.spec.max_moves)) {
             G.err = 1;  // illegal action: game unchanged, flagged
             score_out = score_of(v, G);
           } else {
@@ -166,6 +173,7 @@ __global__ void __launch_bounds__(kBlock) k_main(const __grid_constant__ KArgs a
       // (a pair's x[k+2] is the next pair's slot, so stores wait for every load)
       uint32_t* s_words = smem + (size_t)kWarps * a.warp_smem_words;
       const int pairs = v.P() * v.H();
+      const int cap = kQueueCap * pairs;
       for (int k0 = 0; k0 < nq * pairs; k0 += kBlock) {  // CTA-uniform trip count
         const int k = k0 + threadIdx.x;
         const bool act = k < nq * pairs;
@@ -177,8 +185,12 @@ __global__ void __launch_bounds__(kBlock) k_main(const __grid_constant__ KArgs a
           x = a.mt + (cta0 + s_q_tid[e]) * (int64_t)kMtN;
           at = mt_wrap(s_q_mti[e] + 2 * r);
           mt_load5(x, at, f);
-          s_words[2 * k] = mt_temper(f.a);
-          s_words[2 * k + 1] = mt_temper(f.b);
+          const uint32_t lo = mt_temper(f.a), hi = mt_temper(f.b);
+          bool amb = false;
+          const int q = draw_index(v.deck_max() - r, lo, hi, amb);  // deck size of draw r is known
+          s_words[k] = (uint32_t)q | ((uint32_t)amb << 8);
+          s_words[cap + k] = lo;
+          s_words[2 * cap + k] = hi;
         }
         __syncthreads();
         if (act) {
@@ -186,11 +198,11 @@ __global__ void __launch_bounds__(kBlock) k_main(const __grid_constant__ KArgs a
           __stcg(x + mt_wrap(at + 1), mt_next_block_word(f.b, f.c, f.q));
         }
       }
-      const int per_game = 2 * pairs;
       __syncthreads();
-      // B2: one thread per queued game draws its initial deal from shared memory
+      // B2: one thread per queued game runs the select chain on the precomputed indices
       for (int i = threadIdx.x; i < nq; i += kBlock)
-        reset_draw(v, a.spec, s_words + i * per_game, a.sampler_mode, s_res[i]);
+        reset_draw(v, a.spec, s_words + i * pairs, s_words + cap + i * pairs,
+                   s_words + 2 * cap + i * pairs, a.sampler_mode, s_res[i]);
     }
     __syncthreads();
     if (MODE == kModeStep && a.stats && threadIdx.x < kNumStats && s_stats[threadIdx.x] != 0)
@@ -214,7 +226,7 @@ __global__ void __launch_bounds__(kBlock) k_main(const __grid_constant__ KArgs a
   uint32_t* mask_stream = obs_stream + a.spec.obs_size + kStreamPad;
   if (a.obs) {
     const int observer = a.observer < 0 ? G.cur : a.observer;
-    encode_obs(v, a.spec, G, observer, obs_stream, lane);
+    encode_obs(v, a.spec, G, observer, obs_stream, lane, s_spread);
   }
   if (a.mask) pack_mask_stream(mask_stream, a.spec.max_moves, legal_bits(v, G), valid, lane);
   __syncwarp();
@@ -540,7 +552,7 @@ int NewBatch(pyhanabi_batch_t* out, int list_length, const char** param_list, in
   b->ncols = b->spec.P + 2;
   b->warp_smem_words = b->spec.obs_size + b->spec.max_moves + 2 * hb::kStreamPad;
   b->smem_bytes = ((size_t)hb::kWarps * b->warp_smem_words +
-                   (size_t)hb::kQueueCap * 2 * b->spec.P * b->spec.H) * sizeof(uint32_t);
+                   (size_t)hb::kQueueCap * 3 * b->spec.P * b->spec.H) * sizeof(uint32_t);
   DeviceGuard guard(device);
   if (!guard.ok) { delete b; return Fail("NewBatch: cudaSetDevice failed"); }
   int32_t* d_seeds = nullptr;

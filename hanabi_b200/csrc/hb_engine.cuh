@@ -260,13 +260,19 @@ HB_DEV void card_of_position(V v, int pos, int& color, int& rank) {
   rank = o < 3 ? 0 : (o - 1) >> 1;
 }
 
-// Returns the deck bit position of the drawn card.
-HB_DEV int pick_fast(uint64_t deck, int deck_size, uint32_t lo, uint32_t hi, bool& ambiguous) {
+// floor(u * deck_size) for the 64-bit uniform (hi:lo), and whether it is too
+// close to an integer for the integer result to be trusted.
+HB_DEV int draw_index(int deck_size, uint32_t lo, uint32_t hi, bool& ambiguous) {
   const uint64_t U = ((uint64_t)hi << 32) | lo;
   const uint64_t q = __umul64hi(U, (uint64_t)deck_size);
   const uint64_t F = U * (uint64_t)deck_size;
   ambiguous = (F + kGuard) < 2 * kGuard;
-  return select64(deck, (int)q);
+  return (int)q;
+}
+
+// Returns the deck bit position of the drawn card.
+HB_DEV int pick_fast(uint64_t deck, int deck_size, uint32_t lo, uint32_t hi, bool& ambiguous) {
+  return select64(deck, draw_index(deck_size, lo, hi, ambiguous));
 }
 
 template <class V>
@@ -407,6 +413,34 @@ HB_DEV uint64_t legal_bits(V v, const Game& G) {
     }
   }
   return bits;
+}
+
+// HanabiState::MoveIsLegal for one move uid of the player to act
+// (hanabi_state.cc:166-219); cheaper than building the whole mask.
+template <class V>
+HB_DEV bool move_is_legal(V v, const Game& G, int uid, int max_moves) {
+  if (uid < 0 || uid >= max_moves) return false;
+  const int P = v.P(), H = v.H(), C = v.C(), R = v.R();
+  const int n = (int)((sel<V>(G.hw, G.cur) >> 16) & 15);
+  if (uid < H) return G.info < v.IT() && uid < n;
+  if (uid < 2 * H) return uid - H < n;
+  if (G.info <= 0) return false;
+  int u = uid - 2 * H;
+  const bool is_rank = u >= (P - 1) * C;
+  if (is_rank) u -= (P - 1) * C;
+  const int span = is_rank ? R : C;
+  const int offm1 = u / span, val = u - offm1 * span;
+  int t = G.cur + offm1 + 1;
+  t -= t >= P ? P : 0;
+  const uint32_t hand = sel<V>(G.cards, t);
+  const int m = (int)((sel<V>(G.hw, t) >> 16) & 15);
+  bool any = false;
+#pragma unroll
+  for (int i = 0; i < V::kH; ++i) {
+    const uint32_t f = hand >> (6 * i);
+    any |= (i < m) && ((int)(is_rank ? ((f >> 3) & 7) : (f & 7)) == val);
+  }
+  return any;
 }
 
 HB_DEV uint32_t drop_slot(uint32_t w, int idx, int width) {
@@ -564,12 +598,14 @@ struct ResetResult {
   uint32_t deck_lo, deck_hi;
 };
 
-// Draws the initial deal of one game from TEMPERED RNG words `words[0 .. 2*P*H)`
-// (shared memory, fetched cooperatively by the CTA).  Player
-// 0's hand is filled first, then player 1's, ... (PlayerToDeal, hanabi_state.cc:157-164).
+// Draws the initial deal of one game.  Draw r (deck size deck_max - r) comes with
+// its precomputed index qa[r] = floor(u_r * size) | ambiguous << 8 and its tempered
+// RNG words lo[r], hi[r] (only read for the rare exact re-draw), all in shared
+// memory.  The only serial dependency left is deck -> select -> deck.  Player 0's
+// hand is filled first, then player 1's, ... (PlayerToDeal, hanabi_state.cc:157-164).
 template <class V>
-HB_DEV void reset_draw(V v, const Spec& spec, const uint32_t* words, int sampler_mode,
-                       ResetResult& out) {
+HB_DEV void reset_draw(V v, const Spec& spec, const uint32_t* qa, const uint32_t* lo,
+                       const uint32_t* hi, int sampler_mode, ResetResult& out) {
   uint64_t deck = spec.full_deck;
   int n = v.deck_max();
   const int H = v.H(), total = v.P() * H;
@@ -578,11 +614,10 @@ HB_DEV void reset_draw(V v, const Spec& spec, const uint32_t* words, int sampler
   int p = 0, i = 0;
 #pragma unroll 1
   for (int r = 0; r < total; ++r) {
-    const uint32_t lo = words[2 * r];
-    const uint32_t hi = words[2 * r + 1];
-    bool amb = false;
-    int pos = pick_fast(deck, n, lo, hi, amb);
-    if (sampler_mode == 1 || (amb && sampler_mode != 2)) pos = pick_exact(v, deck, n, lo, hi);
+    const uint32_t w = qa[r];
+    int pos = select64(deck, (int)(w & 0xffu));
+    if (sampler_mode == 1 || ((w >> 8) && sampler_mode != 2))
+      pos = pick_exact(v, deck, n, lo[r], hi[r]);
     int color, rank;
     card_of_position(v, pos, color, rank);
     const uint32_t card = (uint32_t)(color | (rank << 3)) << (6 * i);
@@ -693,9 +728,19 @@ struct BitWriter {
 // CanonicalObservationEncoder::Encode for `observer` with the HanabiObservation
 // view folded in.  Writes the lane's obs_size bits into the warp's stream.
 // Warp-convergent (every lane calls it).
+// spread[cm] has bit c*R set for every colour c in the 5-bit mask cm, so that
+// spread[cm] * rank_mask is the colour x rank outer product of the knowledge
+// section in one multiply.  32 words of shared memory, one bank each: any access
+// pattern is conflict-free.
+HB_DEV uint32_t spread_entry(int cm, int C, int R) {
+  uint32_t s = 0;
+  for (int c = 0; c < C; ++c) s |= ((cm >> c) & 1u) << (c * R);
+  return s;
+}
+
 template <class V>
 HB_DEV void encode_obs(V v, const Spec& spec, const Game& G, int observer, uint32_t* stream,
-                       int lane) {
+                       int lane, const uint32_t* spread) {
   const int P = v.P(), H = v.H(), C = v.C(), R = v.R(), bpc = v.bpc();
   BitWriter bw(stream, lane, spec.obs_size);
   // --- hands (canonical_encoders.cc:62-105)
@@ -771,10 +816,7 @@ HB_DEV void encode_obs(V v, const Spec& spec, const Game& G, int observer, uint3
         for (int i = 0; i < V::kH; ++i) {
           if (i < H) {
             const uint32_t cm = (cpl >> (5 * i)) & 31u, rm = (rpl >> (5 * i)) & 31u;
-            uint32_t plaus = 0;
-#pragma unroll
-            for (int c = 0; c < V::kC; ++c)
-              if (c < C) plaus |= ((cm >> c) & 1u) ? (rm << (c * R)) : 0u;
+            const uint32_t plaus = spread[cm] * rm;  // rm < 2^R: the products do not overlap
             const bool have = i < n;
             bw.put(have ? plaus : 0u, bpc);
             bw.put((have && ((hw >> i) & 1u)) ? cm : 0u, C);

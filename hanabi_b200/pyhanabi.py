@@ -83,6 +83,9 @@ def try_load(library=None, prefixes=DEFAULT_LIB_PREFIXES):
   global lib_loaded_flag, lib, lib_path
   if lib_loaded_flag:
     return True
+  if library is None and os.environ.get("HANABI_B200_LIB"):
+    library = os.environ["HANABI_B200_LIB"]  # experiments: an alternative build of the library
+    prefixes = (None,)
   if library is None:
     libnames = PYHANABI_LIB
   elif type(library) in (list, tuple):
