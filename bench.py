@@ -51,6 +51,9 @@ def parse_args():
   ap.add_argument("--e2e-games", type=int, default=1 << 18)
   ap.add_argument("--cpu-seconds", type=float, default=12.0)
   ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--policy", default="random", choices=["random", "rainbow"],
+                  help="random: uniform legal (headline); rainbow: fixed-weight C51 MLP "
+                       "obs->512->A*51 (torch GEMMs) + fused masked argmax, epsilon 0")
   return ap.parse_args()
 
 
@@ -219,8 +222,34 @@ def main():
 
   # pre-bound launches: pointer casts and argument checks happen once, so the
   # Python cost per step stays far below the ~0.25 ms the GPU needs
-  select = ph.bind_select_action(None, mask, 1.0, seed=7, out=act)
   step_encode = batch.bind_step_encode(act, rew, done, obs, mask, cur)
+  launches_per_step = 2
+  if args.policy == "random":
+    select = ph.bind_select_action(None, mask, 1.0, seed=7, out=act)
+  else:
+    # Rainbow actor (agents/rainbow_copy/rainbow_agent.py:36-68,163-172): MLP
+    # obs_dim -> 512 -> A x 51 with fixed random weights; the two GEMMs are library
+    # calls (cuBLAS through torch, TF32), softmax . support, mask and argmax are ours.
+    torch.manual_seed(0)
+    torch.backends.cuda.matmul.allow_tf32 = True
+    atoms = 51
+    w1 = torch.randn(D, 512, device=dev) / D ** 0.5
+    b1 = torch.zeros(512, device=dev)
+    w2 = torch.randn(512, A * atoms, device=dev) / 512 ** 0.5
+    b2 = torch.zeros(A * atoms, device=dev)
+    support = torch.linspace(-25.0, 25.0, atoms, device=dev)
+    x = torch.empty((n, D), dtype=torch.float32, device=dev)
+    h = torch.empty((n, 512), dtype=torch.float32, device=dev)
+    logits = torch.empty((n, A * atoms), dtype=torch.float32, device=dev)
+    greedy = ph.bind_select_action(logits.view(n, A, atoms), mask, 0.0, seed=7, out=act,
+                                   support=support)
+
+    def select(t):
+      x.copy_(obs)
+      torch.addmm(b1, x, w1, out=h)
+      h.relu_()
+      torch.addmm(b2, h, w2, out=logits)
+      greedy(t)
 
   def one_step(t):
     select(t)
@@ -327,7 +356,10 @@ def main():
       "steps": K, "warmup": W, "ms_per_step": elapsed_ms / K, "higher_is_better": True,
       "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
       "config": {"workload": args.workload, "games_per_gpu": n, "obs_dim": D, "num_moves": A,
-                 "policy": "uniform random legal (BatchSelectAction, epsilon=1)",
+                 "policy": ("uniform random legal (BatchSelectAction, epsilon=1)"
+                            if args.policy == "random" else
+                            "Rainbow C51 MLP %d->512->%dx51 (torch TF32 GEMMs) + BatchSelectAction "
+                            "(epsilon=0)" % (D, A)),
                  "auto_reset": True, "seeds": "1 + global game index",
                  "l2": "outputs per step (%.0f MB) exceed the 126 MB L2" % (n * (D + A) / 1e6),
                  "parallelism": "games sharded over %d GPU(s), no step-path collective" % world},
