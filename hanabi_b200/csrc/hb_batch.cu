@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "../../include/pyhanabi.h"
+#include "hb_agents.cuh"
 #include "hb_engine.cuh"
 #include "hb_spec.h"
 
@@ -48,6 +49,7 @@ struct KArgs {
   int64_t obs_pitch;
   uint8_t* mask;
   unsigned long long* stats;
+  uint4* hist;  // optional: the 4 non-deal moves before `last`, newest first (BatchEnableHistory)
   int auto_reset;
   int sampler_mode;
   int observer;
@@ -88,9 +90,10 @@ __global__ void __launch_bounds__(kBlock, HB_MIN_CTAS) k_main(const __grid_const
   Game G;
   Prefetch pre;
   pre.at = -1;
-  bool queued = false;
+  bool queued = false, moved_any = false, restarted = false;
   int slot = -1;
   int reward = 0, done_out = 0, score_out = 0;
+  uint32_t prev_last = 0;
 
   // ---------------------------------------------------------------- phase A
   if (tile_live) {
@@ -104,8 +107,10 @@ __global__ void __launch_bounds__(kBlock, HB_MIN_CTAS) k_main(const __grid_const
       bool moved = false, term = false;
       int ep_len = 0;
       if (valid) {
-        if (G.done) {
-          done_out = 1;  // finished game, no auto-reset: the step is a no-op
+        if (G.done || uid == -1) {
+          // finished game without auto-reset, or action -1 ("no move for this game"):
+          // the step is a no-op for it
+          done_out = G.done;
           score_out = score_of(v, G);
         } else {
           if (!move_is_legal(v, G, uid, a.spec.max_moves)) {
@@ -113,6 +118,7 @@ __global__ void __launch_bounds__(kBlock, HB_MIN_CTAS) k_main(const __grid_const
             score_out = score_of(v, G);
           } else {
             const int before = score_of(v, G);
+            prev_last = G.last;
             apply_move(v, G, uid);
             score_out = score_of(v, G);
             reward = score_out - before;  // rl_env.py:363
@@ -120,6 +126,7 @@ __global__ void __launch_bounds__(kBlock, HB_MIN_CTAS) k_main(const __grid_const
             done_out = term ? 1 : 0;
             ep_len = G.eplen;
             moved = true;
+            moved_any = true;
           }
         }
       }
@@ -145,6 +152,7 @@ __global__ void __launch_bounds__(kBlock, HB_MIN_CTAS) k_main(const __grid_const
       if (restart) { G.done = 0; G.err = 0; }
     }
     if (MODE != kModeObserve) {
+      restarted = restart;
       queued = restart && a.spec.fast_reset;
       const unsigned qm = __ballot_sync(kFull, queued);
       if (qm) {
@@ -220,6 +228,15 @@ __global__ void __launch_bounds__(kBlock, HB_MIN_CTAS) k_main(const __grid_const
     }
     if (a.cur_player) a.cur_player[g] = G.cur;
     if (MODE != kModeObserve) store_game(a.state, a.N, g, v, G);
+    if (MODE != kModeObserve && a.hist != nullptr) {
+      // move history for the rule-based agents: a new game starts with none
+      if (restarted) {
+        a.hist[g] = make_uint4(0, 0, 0, 0);
+      } else if (moved_any) {
+        const uint4 h = a.hist[g];
+        a.hist[g] = make_uint4(prev_last, h.x, h.y, h.z);
+      }
+    }
   }
   const int n_valid = (int)((a.g_end - tile0) < 32 ? (a.g_end - tile0) : 32);
   uint32_t* obs_stream = smem + (size_t)warp * a.warp_smem_words;
@@ -341,6 +358,7 @@ __global__ void k_pack(KArgs a, const int32_t* in, const int32_t* extra) {
   G.done = 0; G.err = 0; G.eplen = 0;
   G.done = is_terminal(v, G) ? 1 : 0;
   store_game(a.state, a.N, g, v, G);
+  if (a.hist) a.hist[g] = make_uint4(0, 0, 0, 0);
 }
 
 // Test hook: the deal sampler alone on caller-provided decks (2-bit counts per
@@ -405,6 +423,7 @@ struct Batch {
   uint32_t* mt = nullptr;
   unsigned long long* stats = nullptr;      // active stats buffer
   unsigned long long* own_stats = nullptr;  // library-owned fallback
+  uint4* hist = nullptr;                    // move history ring, BatchEnableHistory
   int sampler_mode = 0;
   int force_generic = 0;
   int warp_smem_words = 0;
@@ -474,6 +493,7 @@ hb::KArgs BaseArgs(const Batch* b) {
   a.g_begin = 0;
   a.g_end = b->N;
   a.stats = b->stats;
+  a.hist = b->hist;
   a.sampler_mode = b->sampler_mode;
   a.observer = -1;
   a.warp_smem_words = b->warp_smem_words;
@@ -597,6 +617,7 @@ void DeleteBatch(pyhanabi_batch_t* h) {
   cudaFree(b->state);
   cudaFree(b->mt);
   cudaFree(b->own_stats);
+  cudaFree(b->hist);
   delete b;
   h->batch = nullptr;
 }
@@ -843,6 +864,58 @@ int BatchPackState(pyhanabi_batch_t* h, const int32_t* dump, const int32_t* extr
   hb::KArgs a = BaseArgs(b);
   const unsigned grid = (unsigned)((b->N + 127) / 128);
   hb::k_pack<<<grid, 128, 0, (cudaStream_t)stream>>>(a, dump, extra);
+  HB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Keeps the last non-deal moves of every game (16 bytes per game, updated by every
+// step) so that the rule-based policies can see what happened since their previous
+// turn (HanabiObservation::LastMoves, hanabi_lib/hanabi_observation.cc:77-92).
+// Off by default: the hot path does not pay for it unless asked.
+int BatchEnableHistory(pyhanabi_batch_t* h) {
+  HB_BATCH(h);
+  if (b->hist) return 0;
+  HB_CUDA(cudaMalloc(&b->hist, sizeof(uint4) * (size_t)b->N));
+  HB_CUDA(cudaMemset(b->hist, 0, sizeof(uint4) * (size_t)b->N));
+  return 0;
+}
+
+// The reference's hand-written policies for a whole batch (hb_agents.cuh): writes
+// actions[i] for every game whose player to act sits in seat_mask.  agent_kind 0 =
+// RuleBasedAgent (needs BatchEnableHistory before the games are reset, and
+// agent_state: device uint32[num_games][num_slots], zero-initialised by the caller,
+// never reset between episodes -- like the Python object), 1 = SimpleAgent
+// (stateless; agent_state may be NULL).  seat_slot: HOST int[players] mapping a seat
+// to its state slot (NULL = slot 0 for every seat, i.e. one shared agent object).
+int BatchAgentAct(pyhanabi_batch_t* h, int agent_kind, uint32_t seat_mask, const int32_t* seat_slot,
+                  uint32_t* agent_state, int num_slots, int32_t* actions, void* stream) {
+  HB_BATCH(h);
+  if (!actions) return Fail("BatchAgentAct: actions is null");
+  if (agent_kind != 0 && agent_kind != 1) return Fail("BatchAgentAct: agent_kind must be 0 (RuleBasedAgent) or 1 (SimpleAgent)");
+  hb::AgentArgs a;
+  std::memset(&a, 0, sizeof(a));
+  if (agent_kind == 0) {
+    if (!b->hist) return Fail("BatchAgentAct: RuleBasedAgent needs BatchEnableHistory");
+    if (!agent_state || num_slots < 1) return Fail("BatchAgentAct: RuleBasedAgent needs agent_state");
+    if (b->spec.H > (b->spec.P < 4 ? 5 : 4))
+      return Fail("BatchAgentAct: RuleBasedAgent tracks 5 (4 from four players) cards per hand");
+  }
+  for (int p = 0; p < hb::kMaxPlayers; ++p) {
+    a.seat_slot[p] = (seat_slot && p < b->spec.P) ? seat_slot[p] : 0;
+    if (agent_kind == 0 && (a.seat_slot[p] < 0 || a.seat_slot[p] >= num_slots))
+      return Fail("BatchAgentAct: seat_slot out of range");
+  }
+  a.spec = b->spec;
+  a.state = b->state;
+  a.hist = b->hist;
+  a.N = b->N;
+  a.agent_state = agent_state;
+  a.num_slots = num_slots;
+  a.seat_mask = seat_mask;
+  a.kind = agent_kind;
+  a.max_information_tokens = b->spec.IT;
+  a.actions = actions;
+  hb::k_agent_act<<<(unsigned)((b->N + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a);
   HB_CUDA(cudaGetLastError());
   return 0;
 }

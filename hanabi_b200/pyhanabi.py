@@ -868,6 +868,28 @@ class HanabiBatch(object):
                               self._p(extra, torch.int32, self.num_games * 2, "int32_t*"),
                               self._stream()), "BatchPackState")
 
+  # -- the reference's hand-written policies, batched
+  def enable_history(self):
+    """Keep the last non-deal moves per game (needed by agent_act kind 0); call before reset()."""
+    _check(lib.BatchEnableHistory(self._c), "BatchEnableHistory")
+
+  def agent_act(self, kind, seat_mask, actions, agent_state=None, seat_slot=None):
+    """kind 0 = RuleBasedAgent, 1 = SimpleAgent; writes actions[i] where the player
+    to act sits in seat_mask.  agent_state: int32 CUDA tensor [num_games, num_slots]."""
+    torch = self._torch
+    n = self.num_games
+    slots = 0
+    sptr = ffi.NULL
+    if agent_state is not None:
+      if agent_state.dtype != torch.int32 or agent_state.dim() != 2 or agent_state.shape[0] != n:
+        raise ValueError("agent_state must be an int32 [num_games, num_slots] tensor")
+      slots = int(agent_state.shape[1])
+      sptr = self._p(agent_state, torch.int32, n * slots, "uint32_t*")
+    cslot = ffi.NULL if seat_slot is None else ffi.new("int32_t[]", [int(x) for x in seat_slot])
+    _check(lib.BatchAgentAct(self._c, int(kind), int(seat_mask), cslot, sptr, slots,
+                             self._p(actions, torch.int32, n, "int32_t*"), self._stream()),
+           "BatchAgentAct")
+
   # -- statistics
   def set_stats_buffer(self, stats):
     torch = self._torch

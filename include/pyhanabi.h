@@ -206,7 +206,10 @@ int BatchReset(pyhanabi_batch_t* batch, const uint8_t* which, void* stream);
 
 /* rl_env.HanabiEnv.step (rl_env.py:343-366) for every game: apply move uid
  * actions[i], deal, reward = score delta, done = IsTerminal; with auto_reset a
- * finished game is re-dealt in the same call.  rewards/dones/scores may be NULL. */
+ * finished game is re-dealt in the same call.  actions[i] == -1 means "no move
+ * for game i in this call" (game untouched, reward 0).  A game that is finished
+ * and not reset ignores its action (reward 0, done 1).  rewards/dones/scores may
+ * be NULL. */
 int BatchStep(pyhanabi_batch_t* batch, const int32_t* actions, int32_t* rewards,
               uint8_t* dones, int32_t* scores, int auto_reset, void* stream);
 
@@ -303,6 +306,21 @@ int BatchC51TargetDistribution(const float* rewards, const uint8_t* terminals,
                                const float* support, float cumulative_gamma, float* out,
                                int32_t* next_argmax, int batch, int num_actions,
                                int num_atoms, void* stream);
+
+/* ===== the reference's hand-written policies for a whole batch ============
+ * BatchAgentAct writes actions[i] (device int32[num_games]) for every game whose
+ * player to act sits in seat_mask (bit p = seat p); other games keep their entry.
+ * agent_kind 0 = RuleBasedAgent.act_train (agents/rule_based_agent.py:230-296):
+ *   needs BatchEnableHistory (called before the games are reset) and agent_state,
+ *   a zero-initialised device uint32[num_games][num_slots] holding each agent
+ *   object's rank_hinted_but_no_play table; seat_slot (HOST int[players], NULL = all
+ *   seats share slot 0, as create_adhoc_team makes them share one object,
+ *   training/run_adhoc_experiment.py:251-258) maps seats to slots.
+ * agent_kind 1 = SimpleAgent.act (agents/simple_agent.py:32-69): stateless. */
+int BatchEnableHistory(pyhanabi_batch_t* batch);
+int BatchAgentAct(pyhanabi_batch_t* batch, int agent_kind, uint32_t seat_mask,
+                  const int32_t* seat_slot, uint32_t* agent_state, int num_slots,
+                  int32_t* actions, void* stream);
 
 /* Test hooks. */
 int BatchSetDebug(pyhanabi_batch_t* batch, int sampler_mode, int generic);

@@ -92,3 +92,50 @@ def test_new_batch_rejects_bad_parameters():
     ph.HanabiBatch(dict(players=6), 4, [1, 2, 3, 4])
   with pytest.raises(RuntimeError, match="deck"):
     ph.HanabiBatch(dict(players=5, colors=1, ranks=5, hand_size=4), 4, [1, 2, 3, 4])
+
+
+def test_tf_agents_style_adapter_follows_the_wrapper_protocol():
+  """The batched TimeStep adapter vs the reference wrapper's logic
+  (training/tf_agents_lib/pyhanabi_env_wrapper.py:41-90) replayed game by game on
+  the single-game HanabiEnv."""
+  import torch
+  from hanabi_b200 import rl_env, tf_agents_adapter as T
+  n, steps = 24, 70
+  cfg = dict(players=2, colors=2, ranks=5, hand_size=2, max_information_tokens=3,
+             max_life_tokens=1, observation_type=1)
+  benv = rl_env.BatchedHanabiEnv(dict(cfg, seed=100), n, auto_reset=False)
+  wrapped = T.BatchedPyhanabiEnvWrapper(benv)
+  ts = wrapped.reset()
+  envs = [rl_env.HanabiEnv(dict(cfg, seed=100 + i)) for i in range(n)]
+  fmin = np.finfo(np.float32).min
+
+  def ref_obs(env, observations):
+    o = observations["player_observations"][observations["current_player"]]
+    m = np.full(env.num_moves(), fmin, np.float32)
+    m[o["legal_moves_as_int"]] = 0
+    return np.asarray(o["vectorized"], np.uint8), m, env.state.score()
+
+  ref = [ref_obs(e, e.reset()) for e in envs]
+  ended = [False] * n
+  rng = np.random.default_rng(4)
+  assert (ts.step_type.cpu().numpy() == T.FIRST).all() and float(ts.discount) == pytest.approx(0.999)
+  for t in range(steps):
+    state = ts.observation["state"].cpu().numpy()
+    mask = ts.observation["mask"].cpu().numpy()
+    info = ts.observation["info"].cpu().numpy()
+    for i in range(n):
+      assert (state[i] == ref[i][0]).all() and (mask[i] == ref[i][1]).all() and info[i] == ref[i][2]
+    actions = np.asarray([int(rng.choice(np.flatnonzero(mask[i] == 0))) for i in range(n)])
+    ts = wrapped.step(torch.as_tensor(actions, device=benv.device))
+    st, rw = ts.step_type.cpu().numpy(), ts.reward.cpu().numpy()
+    for i, e in enumerate(envs):
+      if ended[i]:  # wrapper :64-67: ignore the action, start a new episode
+        ref[i] = ref_obs(e, e.reset())
+        ended[i] = False
+        assert st[i] == T.FIRST and rw[i] == 0
+      else:
+        observations, reward, done, _ = e.step(int(actions[i]))
+        ref[i] = ref_obs(e, observations)
+        ended[i] = done
+        assert st[i] == (T.LAST if done else T.MID) and rw[i] == np.float32(reward)
+  assert wrapped.action_spec()["maximum"] == benv.num_moves() - 1
