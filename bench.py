@@ -51,9 +51,11 @@ def parse_args():
   ap.add_argument("--e2e-games", type=int, default=1 << 18)
   ap.add_argument("--cpu-seconds", type=float, default=12.0)
   ap.add_argument("--no-cpu-baseline", action="store_true")
-  ap.add_argument("--policy", default="random", choices=["random", "rainbow"],
+  ap.add_argument("--policy", default="random", choices=["random", "rainbow", "adhoc"],
                   help="random: uniform legal (headline); rainbow: fixed-weight C51 MLP "
-                       "obs->512->A*51 (torch GEMMs) + fused masked argmax, epsilon 0")
+                       "obs->512->A*51 (torch GEMMs) + fused masked argmax, epsilon 0; adhoc: "
+                       "seat 0 Rainbow, other seats the batched RuleBasedAgent sharing one object "
+                       "(training/run_adhoc_experiment.py team 1)")
   return ap.parse_args()
 
 
@@ -244,12 +246,28 @@ def main():
     greedy = ph.bind_select_action(logits.view(n, A, atoms), mask, 0.0, seed=7, out=act,
                                    support=support)
 
-    def select(t):
+    def rainbow(t):
       x.copy_(obs)
       torch.addmm(b1, x, w1, out=h)
       h.relu_()
       torch.addmm(b2, h, w2, out=logits)
       greedy(t)
+
+    select = rainbow
+    if args.policy == "adhoc":
+      # ad-hoc team 1: seat 0 = Rainbow, every other seat = RuleBasedAgent, one shared
+      # object (training/run_adhoc_experiment.py:195-258); the rule-based kernel
+      # overwrites the action of the games whose player to act is one of its seats
+      batch.enable_history()
+      batch.reset()
+      batch.observe(obs, mask, cur)
+      agent_state = torch.zeros((n, 1), dtype=torch.int32, device=dev)
+      seat_mask = sum(1 << s for s in range(1, batch.num_players))
+      launches_per_step = 3
+
+      def select(t):
+        rainbow(t)
+        batch.agent_act(0, seat_mask, act, agent_state=agent_state)
 
   def one_step(t):
     select(t)
@@ -359,7 +377,9 @@ def main():
                  "policy": ("uniform random legal (BatchSelectAction, epsilon=1)"
                             if args.policy == "random" else
                             "Rainbow C51 MLP %d->512->%dx51 (torch TF32 GEMMs) + BatchSelectAction "
-                            "(epsilon=0)" % (D, A)),
+                            "(epsilon=0)" % (D, A) +
+                            ("; seats 1.. = batched RuleBasedAgent (BatchAgentAct)"
+                             if args.policy == "adhoc" else "")),
                  "auto_reset": True, "seeds": "1 + global game index",
                  "l2": "outputs per step (%.0f MB) exceed the 126 MB L2" % (n * (D + A) / 1e6),
                  "parallelism": "games sharded over %d GPU(s), no step-path collective" % world},
@@ -368,7 +388,7 @@ def main():
                    "kernel_ms": kernel_ms, "algorithmic_bytes_per_env_step": algo,
                    "peak_source": peak_src},
       "e2e": e2e,
-      "gpu_launches": 2 * K,
+      "gpu_launches": launches_per_step * K,
       "clocks": clocks,
       "episodes": {"count": st[0], "mean_score": st[1] / max(st[0], 1),
                    "mean_length": st[2] / max(st[0], 1)},

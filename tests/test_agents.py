@@ -99,3 +99,60 @@ def test_gpu_agents_reproduce_reference_agent_traces(traces, name):
     d = done_t.cpu().numpy()
     for i in range(n):
       assert bool(d[i]) == bool(tr[i]["done"][t])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["adhoc4_shared", "rule2_separate", "simple4_mixed"])
+def test_gpu_agents_lockstep_with_restated_agents(name):
+  """More games than the golden traces hold: every seat's kernel action equals the
+  (reference-pinned) Python restatement playing the same seeded games on the host."""
+  import torch
+  from hanabi_b200 import pyhanabi as ph, rl_env
+  players, kinds, slots = TEAMS[name]
+  n, steps = 24, 120
+  seeds = [500 + i for i in range(n)]
+  b = ph.HanabiBatch(dict(FULL, players=players), n, seeds)
+  b.enable_history()
+  b.reset()
+  dev = b.device
+  num_slots = max(slots) + 1
+  state = torch.zeros((n, num_slots), dtype=torch.int32, device=dev)
+  act = torch.zeros(n, dtype=torch.int32, device=dev)
+  done_t = torch.zeros(n, dtype=torch.uint8, device=dev)
+  rew_t = torch.zeros(n, dtype=torch.int32, device=dev)
+  rule_mask = sum(1 << s for s, k in enumerate(kinds) if k == "R")
+  simple_mask = sum(1 << s for s, k in enumerate(kinds) if k == "S")
+  envs, teams, obs = [], [], []
+  for s in seeds:
+    cfg = dict(FULL, players=players, seed=s)
+    e = rl_env.HanabiEnv(cfg)
+    objs = {}
+    team = []
+    for seat, k in enumerate(kinds):
+      team.append(objs.setdefault(slots[seat], A.RuleBasedAgent(players)) if k == "R"
+                  else A.SimpleAgent(cfg) if k == "S" else None)
+    envs.append(e); teams.append(team); obs.append(e.reset())
+  for t in range(steps):
+    want = np.zeros(n, np.int32)
+    for i in range(n):
+      cur = obs[i]["current_player"]
+      po = obs[i]["player_observations"][cur]
+      if teams[i][cur] is None:
+        legal = po["legal_moves_as_int"]
+        want[i] = legal[(t * 5 + i) % len(legal)]
+      else:
+        want[i] = teams[i][cur].act_uid(po)
+    act.copy_(torch.as_tensor(want))  # scripted seats keep this entry
+    if rule_mask:
+      b.agent_act(0, rule_mask, act, agent_state=state, seat_slot=slots)
+    if simple_mask:
+      b.agent_act(1, simple_mask, act)
+    got = act.cpu().numpy()
+    assert (got == want).all(), (name, t, np.flatnonzero(got != want)[:4])
+    b.step(act, rew_t, done_t, auto_reset=True)
+    d = done_t.cpu().numpy()
+    for i in range(n):
+      obs[i], _, done, _ = envs[i].step(int(want[i]))
+      assert bool(d[i]) == done
+      if done:
+        obs[i] = envs[i].reset()
