@@ -51,6 +51,9 @@ def parse_args():
   ap.add_argument("--e2e-games", type=int, default=1 << 18)
   ap.add_argument("--cpu-seconds", type=float, default=12.0)
   ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--python-baselines", action="store_true",
+                  help="also time the Python paths of BASELINE.md section 3 (C1-C3) on the host")
+  ap.add_argument("--cpu-python-worker", default=None, help=argparse.SUPPRESS)
   ap.add_argument("--policy", default="random", choices=["random", "rainbow", "adhoc"],
                   help="random: uniform legal (headline); rainbow: fixed-weight C51 MLP "
                        "obs->512->A*51 (torch GEMMs) + fused masked argmax, epsilon 0; adhoc: "
@@ -144,6 +147,70 @@ def cpu_reference_rate(workload, seconds, threads=None):
           "sample": "%d games x %d steps, random-legal policy, auto-reset, %.1f s" % (n, steps, dt)}
 
 
+def python_worker(mode, seconds, seed, workload):
+  """Child process (HANABI_B200_LIB = the reference's own libpyhanabi.so from
+  oracle/_ref): the Python layers a reference user runs today, on the reference's
+  native engine.  mode "rl_env": HanabiEnv.reset/step with the full per-player
+  dicts (what every trainer calls, rl_env.py:343-366); mode "lean": apply_move +
+  deal + current-player observation + encode + legal uids."""
+  import random
+  from hanabi_b200 import pyhanabi, rl_env
+  cfg = dict(WORKLOADS[workload], seed=seed)
+  rnd = random.Random(seed)
+  steps = 0
+  t0 = time.perf_counter()
+  if mode == "rl_env":
+    env = rl_env.HanabiEnv(cfg)
+    obs = env.reset()
+    while time.perf_counter() - t0 < seconds:
+      legal = obs["player_observations"][obs["current_player"]]["legal_moves_as_int"]
+      obs, _, done, _ = env.step(rnd.choice(legal))
+      steps += 1
+      if done:
+        obs = env.reset()
+  else:
+    game = pyhanabi.HanabiGame(cfg)
+    enc = pyhanabi.ObservationEncoder(game)
+    state = None
+    while time.perf_counter() - t0 < seconds:
+      if state is None or state.is_terminal():
+        state = game.new_initial_state()
+        while state.cur_player() == pyhanabi.CHANCE_PLAYER_ID:
+          state.deal_random_card()
+      moves = state.legal_moves()
+      state.apply_move(rnd.choice(moves))
+      while state.cur_player() == pyhanabi.CHANCE_PLAYER_ID:
+        state.deal_random_card()
+      if not state.is_terminal():
+        enc.encode(state.observation(state.cur_player()))
+        [game.get_move_uid(m) for m in state.legal_moves()]
+      steps += 1
+  print(json.dumps({"steps": steps, "seconds": time.perf_counter() - t0}), flush=True)
+
+
+def python_baselines(workload, seconds=4.0):
+  """BASELINE.md section 3, C1-C3, on this box's host cores."""
+  import subprocess
+  from oracle import oracle as O
+  if not os.path.exists(O.REF_PYHANABI_SO):
+    return None
+  env = dict(os.environ, HANABI_B200_LIB=O.REF_PYHANABI_SO)
+  cores = os.cpu_count() or 1
+
+  def launch(mode, count):
+    procs = [subprocess.Popen([sys.executable, os.path.abspath(__file__), "--cpu-python-worker",
+                               "%s:%g:%d" % (mode, seconds, 1 + i), "--workload", workload],
+                              env=env, stdout=subprocess.PIPE, text=True) for i in range(count)]
+    outs = [json.loads(p.communicate()[0].strip().splitlines()[-1]) for p in procs]
+    return sum(o["steps"] for o in outs) / max(o["seconds"] for o in outs)
+
+  return {"unit": "env-steps/s", "cores": cores, "seconds_each": seconds,
+          "rl_env_loop_1_process": launch("rl_env", 1), "lean_pyhanabi_loop_1_process": launch("lean", 1),
+          "rl_env_loop_1_process_per_core": launch("rl_env", cores),
+          "lean_pyhanabi_loop_1_process_per_core": launch("lean", cores),
+          "note": "reference libpyhanabi.so (oracle/_ref) driven by the Python binding/rl_env layer"}
+
+
 def run_reference_arm(args, rank):
   """--impl reference: the reference's CPU implementation of the path, all host threads."""
   if rank != 0:
@@ -187,6 +254,10 @@ def main():
   rank = int(os.environ.get("RANK", "0"))
   local_rank = int(os.environ.get("LOCAL_RANK", "0"))
   world = int(os.environ.get("WORLD_SIZE", "1"))
+  if args.cpu_python_worker:
+    mode, seconds, seed = args.cpu_python_worker.split(":")
+    python_worker(mode, float(seconds), int(seed), args.workload)
+    return
   if args.impl == "reference":
     run_reference_arm(args, rank)
     return
@@ -395,6 +466,8 @@ def main():
   }
   if not args.no_cpu_baseline:
     line["cpu_baseline"] = cpu_reference_rate(args.workload, args.cpu_seconds)
+    if args.python_baselines:
+      line["cpu_baseline"]["python_paths"] = python_baselines(args.workload)
   print(json.dumps(line), flush=True)
   if dist:
     dist.destroy_process_group()
