@@ -260,3 +260,26 @@ def test_episode_statistics():
   assert st["episodes"] == episodes and st["score_sum"] == score_sum
   assert st["score_hist"] == hist.tolist()
   assert st["length_sum"] > episodes
+
+
+def test_unaligned_output_buffer_takes_the_byte_path():
+  """An observation tensor that is not 16-byte aligned (dense pitch) still gets the
+  right bytes, and nothing outside the rows is touched."""
+  import torch
+  from hanabi_b200 import pyhanabi as ph
+  n = 70
+  p = CONFIGS["full2"]
+  seeds = common.seeds_for(n, base=8)
+  cpu = O.CpuBatch("oracle", p, n, seeds)
+  cpu.reset()
+  b = ph.HanabiBatch(p, n, seeds)
+  b.reset()
+  D = b.obs_size
+  store = torch.full((n * D + 64,), 9, dtype=torch.uint8, device=b.device)
+  for shift in (1, 2, 8):
+    store.fill_(9)
+    view = store[shift:shift + n * D].view(n, D)
+    assert view.data_ptr() % 16 != 0
+    b.encode(view)
+    common.assert_same(cpu.encode(), view.cpu().numpy(), "obs at byte offset %d" % shift)
+    assert bool((store[:shift] == 9).all()) and bool((store[shift + n * D:] == 9).all())
