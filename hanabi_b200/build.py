@@ -12,7 +12,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpyhanabi.so")
-CUDA_SOURCES = ["hb_batch.cu", "hb_policy.cu"]
+CUDA_SOURCES = ["hb_batch.cu", "hb_policy.cu", "hb_replay.cu"]
 HOST_SOURCES = ["hb_single.cc"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -1,0 +1,434 @@
+// hb_replay.cu -- device-resident replay memory for the Rainbow learner
+// (SURVEY.md section 8f, row f3): the reference's numpy ring buffer and sum tree
+//   agents/rainbow_copy/replay_memory.py:67-347            OutOfGraphReplayMemory
+//   agents/rainbow_copy/prioritized_replay_memory.py:41-170 OutOfGraphPrioritizedReplayMemory
+//   agents/rainbow_copy/third_party/dopamine/sum_tree.py:30-205  SumTree
+// with the Hanabi configuration stack_size = 1 (training/configs/hanabi_rainbow.gin:39),
+// kept in HBM so that the batched actor can append and the learner can sample
+// without a host round trip.  Same field formats as the reference: uint8
+// observations, int32 actions, float32 rewards, uint8 terminals, float32 legal
+// action vectors (0 / -inf), float64 priorities.
+//
+// Semantics kept from the reference, including the odd ones:
+//  * transitions are appended in order at the cursor, next_state is "whatever is
+//    stored update_horizon slots later" (replay_memory.py:326-331);
+//  * is_valid_transition (:233-258) with stack_size 1: index in range, not the most
+//    recently written slot, and -- only while the buffer is not full -- at least
+//    update_horizon slots behind the cursor;
+//  * the n-step reward stops at the first terminal in the window (:307-324);
+//  * new elements enter the sum tree with priority 100 (DEFAULT_PRIORITY, :38).
+// Difference on purpose: inner sum-tree nodes are recomputed as left + right after
+// every batch of updates (deterministic, one rounding per node) instead of being
+// nudged by += delta per update; leaves are identical, inner sums agree to ~1e-13.
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include <cmath>
+#include <cstring>
+#include <string>
+
+#include "../../include/pyhanabi.h"
+
+int HbFail(const std::string& msg);  // hb_batch.cu
+
+namespace hbr {
+
+constexpr int kMaxHorizon = 16;
+constexpr int kMaxAttempts = 1000;  // MAX_SAMPLE_ATTEMPTS, replay_memory.py:36
+
+struct Replay {
+  int device = 0;
+  int A = 0, D = 0, horizon = 1, prioritized = 0, depth = 0;
+  int64_t cap = 0, add_count = 0;
+  float gamma = 1.f;
+  float disc[kMaxHorizon];
+  uint8_t* obs = nullptr;
+  int32_t* actions = nullptr;
+  float* rewards = nullptr;
+  uint8_t* terminals = nullptr;
+  float* legal = nullptr;
+  double* tree = nullptr;  // heap layout: level l (2^l nodes) starts at 2^l - 1; leaves at level `depth`
+  double max_recorded_priority = 1.0;
+};
+
+struct View {
+  int A, D, horizon, depth;
+  int64_t cap, add_count;
+  float disc[kMaxHorizon];
+  const uint8_t* obs;
+  const int32_t* actions;
+  const float* rewards;
+  const uint8_t* terminals;
+  const float* legal;
+  const double* tree;
+};
+
+__host__ __device__ inline uint64_t mix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+// is_valid_transition, replay_memory.py:233-258 (stack_size == 1).
+__device__ inline bool valid_transition(const View& v, int64_t index) {
+  if (index < 0 || index >= v.cap) return false;
+  const int64_t cursor = v.add_count % v.cap;
+  if (v.add_count < v.cap) {
+    if (index >= cursor - v.horizon) return false;
+  }
+  const int64_t newest = (cursor - 1 + v.cap) % v.cap;  // invalid_range(cursor, capacity, 1)
+  return index != newest;
+}
+
+// SumTree.sample(query_value), sum_tree.py:99-141.
+__device__ inline int64_t tree_sample(const View& v, double query) {
+  query *= v.tree[0];
+  int64_t node = 0;
+  for (int l = 1; l <= v.depth; ++l) {
+    const int64_t left = node * 2;
+    const double left_sum = v.tree[((int64_t)1 << l) - 1 + left];
+    if (query < left_sum) {
+      node = left;
+    } else {
+      node = left + 1;
+      query -= left_sum;
+    }
+  }
+  return node;
+}
+
+__global__ void k_add(uint8_t* obs, int32_t* actions, float* rewards, uint8_t* terminals, float* legal,
+                      int64_t cap, int64_t cursor, int D, int A, const uint8_t* in_obs,
+                      const int32_t* in_actions, const float* in_rewards, const uint8_t* in_terminals,
+                      const float* in_legal, int count) {
+  // one warp per transition: rows are copied with coalesced accesses
+  const int lane = threadIdx.x & 31;
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (i >= count) return;
+  const int64_t slot = (cursor + i) % cap;
+  for (int k = lane; k < D; k += 32) obs[slot * D + k] = in_obs[i * D + k];
+  for (int k = lane; k < A; k += 32) legal[slot * A + k] = in_legal[i * A + k];
+  if (lane == 0) {
+    actions[slot] = in_actions[i];
+    rewards[slot] = in_rewards[i];
+    terminals[slot] = in_terminals[i];
+  }
+}
+
+__global__ void k_set_leaves_range(double* tree, int depth, int64_t cap, int64_t cursor, int count,
+                                   double value) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  tree[((int64_t)1 << depth) - 1 + (cursor + i) % cap] = value;
+}
+
+// Batch of SumTree.set calls: for duplicate indices the last one in the batch wins,
+// as it would sequentially (writer[] holds the winning position per leaf).
+__global__ void k_claim(int32_t* writer, const int32_t* indices, int count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) atomicMax(&writer[indices[i]], i);
+}
+__global__ void k_set_leaves(double* tree, int depth, int32_t* writer, const int32_t* indices,
+                             const float* values, int count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const int32_t leaf = indices[i];
+  if (writer[leaf] == i) tree[((int64_t)1 << depth) - 1 + leaf] = (double)values[i];
+}
+__global__ void k_unclaim(int32_t* writer, const int32_t* indices, int count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) writer[indices[i]] = -1;
+}
+
+// Recompute level `l` parents of the touched leaves: parent = left + right.
+__global__ void k_rebuild_level_range(double* tree, int depth, int l, int64_t cap, int64_t cursor,
+                                      int count) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const int64_t leaf = (cursor + i) % cap;
+  const int64_t node = leaf >> (depth - l);
+  const double* child = tree + (((int64_t)1 << (l + 1)) - 1);
+  tree[((int64_t)1 << l) - 1 + node] = child[2 * node] + child[2 * node + 1];
+}
+__global__ void k_rebuild_level(double* tree, int depth, int l, const int32_t* indices, int count) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const int64_t node = (int64_t)indices[i] >> (depth - l);
+  const double* child = tree + (((int64_t)1 << (l + 1)) - 1);
+  tree[((int64_t)1 << l) - 1 + node] = child[2 * node] + child[2 * node + 1];
+}
+
+__global__ void k_get_priority(View v, const int32_t* indices, int count, float* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) out[i] = (float)v.tree[((int64_t)1 << v.depth) - 1 + indices[i]];
+}
+
+__global__ void k_is_valid(View v, const int32_t* indices, int count, uint8_t* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) out[i] = valid_transition(v, indices[i]) ? 1 : 0;
+}
+
+__global__ void k_tree_sample(View v, const double* queries, int count, int32_t* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) out[i] = (int32_t)tree_sample(v, queries[i]);
+}
+
+// sample_index_batch: prioritized (prioritized_replay_memory.py:109-132) or
+// uniform (replay_memory.py:265-288), each element retried until valid.
+__global__ void k_sample_indices(View v, int prioritized, int stratified, uint64_t seed, uint64_t step,
+                                 int count, int32_t* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  int64_t pick = -1;
+  for (int attempt = 0; attempt < kMaxAttempts && pick < 0; ++attempt) {
+    const uint64_t bits = mix64(mix64(seed ^ (step * 0xD1B54A32D192ED03ull)) ^
+                                ((uint64_t)i * 0x8CB92BA72F3D8DD7ull) ^ ((uint64_t)attempt << 48));
+    const double u = (double)(bits >> 11) * (1.0 / 9007199254740992.0);  // [0, 1)
+    int64_t index;
+    if (prioritized) {
+      // stratified: element i draws from [i/count, (i+1)/count) (sum_tree.py:143-168)
+      const double q = stratified ? ((double)i + u) / (double)count : u;
+      index = tree_sample(v, q);
+    } else if (v.add_count >= v.cap) {
+      index = (int64_t)(u * (double)v.cap);                      // np.random.randint(0, capacity)
+    } else {
+      const int64_t hi = v.add_count % v.cap - 1;                // randint(stack_size - 1, cursor - 1)
+      index = hi > 0 ? (int64_t)(u * (double)hi) : 0;
+    }
+    if (valid_transition(v, index)) pick = index;
+  }
+  out[i] = (int32_t)pick;  // -1: no valid transition found (the reference raises)
+}
+
+// sample_transition_batch(indices=...), replay_memory.py:290-347.  One warp per element.
+__global__ void k_gather(View v, const int32_t* indices, int count, uint8_t* states, int32_t* actions,
+                         float* rewards, uint8_t* next_states, uint8_t* terminals, float* next_legal) {
+  const int lane = threadIdx.x & 31;
+  const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= count) return;
+  const int64_t idx = indices[b];
+  const int64_t boot = (idx + v.horizon) % v.cap;
+  for (int k = lane; k < v.D; k += 32) {
+    states[b * v.D + k] = v.obs[idx * v.D + k];
+    next_states[b * v.D + k] = v.obs[boot * v.D + k];
+  }
+  for (int k = lane; k < v.A; k += 32) next_legal[b * v.A + k] = v.legal[boot * v.A + k];
+  if (lane == 0) {
+    actions[b] = v.actions[idx];
+    float acc = 0.f;
+    uint8_t term = 0;
+    for (int j = 0; j < v.horizon; ++j) {
+      const int64_t t = (idx + j) % v.cap;
+      acc = __fadd_rn(acc, __fmul_rn(v.disc[j], v.rewards[t]));
+      if (v.terminals[t]) { term = 1; break; }  // truncated at the first terminal (inclusive)
+    }
+    rewards[b] = acc;
+    terminals[b] = term;
+  }
+}
+
+}  // namespace hbr
+
+namespace {
+using hbr::Replay;
+
+struct Guard {
+  int prev = -1;
+  explicit Guard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev);
+  }
+  ~Guard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+hbr::View MakeView(const Replay* r) {
+  hbr::View v;
+  v.A = r->A; v.D = r->D; v.horizon = r->horizon; v.depth = r->depth;
+  v.cap = r->cap; v.add_count = r->add_count;
+  std::memcpy(v.disc, r->disc, sizeof(v.disc));
+  v.obs = r->obs; v.actions = r->actions; v.rewards = r->rewards; v.terminals = r->terminals;
+  v.legal = r->legal; v.tree = r->tree;
+  return v;
+}
+
+int Check(cudaError_t e, const char* what) {
+  return e == cudaSuccess ? 0 : HbFail(std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define HBR_CUDA(expr)                       \
+  do {                                       \
+    if (Check((expr), #expr)) return 1;      \
+  } while (0)
+#define HBR_REPLAY(h)                                             \
+  if (!(h) || !(h)->replay) return HbFail("null replay handle");  \
+  Replay* r = static_cast<Replay*>((h)->replay);                  \
+  Guard guard__(r->device)
+}  // namespace
+
+extern "C" {
+
+int NewReplay(pyhanabi_replay_t* out, int num_actions, int observation_size, int64_t capacity,
+              int update_horizon, float gamma, int prioritized, int device) {
+  if (!out) return HbFail("NewReplay: null handle");
+  out->replay = nullptr;
+  if (num_actions <= 0 || observation_size <= 0 || capacity <= 0)
+    return HbFail("NewReplay: sizes must be positive");
+  if (update_horizon < 1 || update_horizon > hbr::kMaxHorizon)
+    return HbFail("NewReplay: update_horizon must be in [1,16]");
+  if (capacity > (int64_t)1 << 30) return HbFail("NewReplay: capacity above 2^30");
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count)
+    return HbFail("NewReplay: no such CUDA device (the replay memory has no CPU fallback)");
+  Replay* r = new Replay;
+  r->device = device; r->A = num_actions; r->D = observation_size; r->cap = capacity;
+  r->horizon = update_horizon; r->gamma = gamma; r->prioritized = prioritized ? 1 : 0;
+  for (int j = 0; j < hbr::kMaxHorizon; ++j)
+    r->disc[j] = (float)std::pow((double)gamma, (double)j);  // math.pow -> float32, replay_memory.py:106-108
+  r->depth = 0;
+  while (((int64_t)1 << r->depth) < capacity) ++r->depth;  // ceil(log2(capacity)), sum_tree.py:75
+  Guard guard(device);
+  const size_t cap = (size_t)capacity;
+  auto fail = [&](const char* what, cudaError_t e) {
+    cudaFree(r->obs); cudaFree(r->actions); cudaFree(r->rewards); cudaFree(r->terminals);
+    cudaFree(r->legal); cudaFree(r->tree);
+    delete r;
+    return Check(e, what);
+  };
+  cudaError_t e;
+  if ((e = cudaMalloc(&r->obs, cap * (size_t)observation_size)) != cudaSuccess) return fail("cudaMalloc obs", e);
+  if ((e = cudaMalloc(&r->actions, cap * sizeof(int32_t))) != cudaSuccess) return fail("cudaMalloc actions", e);
+  if ((e = cudaMalloc(&r->rewards, cap * sizeof(float))) != cudaSuccess) return fail("cudaMalloc rewards", e);
+  if ((e = cudaMalloc(&r->terminals, cap)) != cudaSuccess) return fail("cudaMalloc terminals", e);
+  if ((e = cudaMalloc(&r->legal, cap * (size_t)num_actions * sizeof(float))) != cudaSuccess) return fail("cudaMalloc legal", e);
+  const size_t nodes = ((size_t)2 << r->depth);  // 2^(depth+1) - 1 nodes, + 1 writer-free pad
+  // the tree buffer also hosts the int32 "last writer" scratch behind the nodes
+  if ((e = cudaMalloc(&r->tree, nodes * sizeof(double) + ((size_t)1 << r->depth) * sizeof(int32_t))) != cudaSuccess)
+    return fail("cudaMalloc tree", e);
+  cudaMemset(r->obs, 0, cap * (size_t)observation_size);
+  cudaMemset(r->actions, 0, cap * sizeof(int32_t));
+  cudaMemset(r->rewards, 0, cap * sizeof(float));
+  cudaMemset(r->terminals, 0, cap);
+  cudaMemset(r->legal, 0, cap * (size_t)num_actions * sizeof(float));
+  cudaMemset(r->tree, 0, nodes * sizeof(double));
+  cudaMemset(reinterpret_cast<char*>(r->tree) + nodes * sizeof(double), 0xff, ((size_t)1 << r->depth) * sizeof(int32_t));
+  if ((e = cudaDeviceSynchronize()) != cudaSuccess) return fail("NewReplay init", e);
+  out->replay = r;
+  return 0;
+}
+
+void DeleteReplay(pyhanabi_replay_t* h) {
+  if (!h || !h->replay) return;
+  Replay* r = static_cast<Replay*>(h->replay);
+  Guard guard(r->device);
+  cudaFree(r->obs); cudaFree(r->actions); cudaFree(r->rewards); cudaFree(r->terminals);
+  cudaFree(r->legal); cudaFree(r->tree);
+  delete r;
+  h->replay = nullptr;
+}
+
+int64_t ReplayAddCount(pyhanabi_replay_t* h) { return (h && h->replay) ? static_cast<Replay*>(h->replay)->add_count : -1; }
+int64_t ReplayCapacity(pyhanabi_replay_t* h) { return (h && h->replay) ? static_cast<Replay*>(h->replay)->cap : -1; }
+double ReplayMaxRecordedPriority(pyhanabi_replay_t* h) {
+  return (h && h->replay) ? static_cast<Replay*>(h->replay)->max_recorded_priority : -1.0;
+}
+
+static int RebuildRange(Replay* r, int64_t cursor, int count, cudaStream_t s) {
+  for (int l = r->depth - 1; l >= 0; --l) {
+    hbr::k_rebuild_level_range<<<(count + 255) / 256, 256, 0, s>>>(r->tree, r->depth, l, r->cap, cursor, count);
+  }
+  return Check(cudaGetLastError(), "sum tree rebuild");
+}
+
+int ReplayAdd(pyhanabi_replay_t* h, const uint8_t* obs, const int32_t* actions, const float* rewards,
+              const uint8_t* terminals, const float* legal_actions, int count, float priority,
+              void* stream) {
+  HBR_REPLAY(h);
+  if (!obs || !actions || !rewards || !terminals || !legal_actions) return HbFail("ReplayAdd: null argument");
+  if (count <= 0) return 0;
+  if (count > r->cap) return HbFail("ReplayAdd: more transitions than the capacity in one call");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t cursor = r->add_count % r->cap;
+  const int64_t threads = (int64_t)count * 32;
+  hbr::k_add<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(
+      r->obs, r->actions, r->rewards, r->terminals, r->legal, r->cap, cursor, r->D, r->A, obs, actions,
+      rewards, terminals, legal_actions, count);
+  HBR_CUDA(cudaGetLastError());
+  r->add_count += count;
+  if (r->prioritized) {
+    const double p = priority < 0.f ? 100.0 : (double)priority;  // DEFAULT_PRIORITY
+    if (p > r->max_recorded_priority) r->max_recorded_priority = p;
+    hbr::k_set_leaves_range<<<(count + 255) / 256, 256, 0, s>>>(r->tree, r->depth, r->cap, cursor, count, p);
+    HBR_CUDA(cudaGetLastError());
+    if (RebuildRange(r, cursor, count, s)) return 1;
+  }
+  return 0;
+}
+
+int ReplaySetPriority(pyhanabi_replay_t* h, const int32_t* indices, const float* priorities, int count,
+                      float host_max_priority, void* stream) {
+  HBR_REPLAY(h);
+  if (!r->prioritized) return HbFail("ReplaySetPriority: the replay memory is not prioritized");
+  if (count <= 0) return 0;
+  cudaStream_t s = (cudaStream_t)stream;
+  int32_t* writer = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(r->tree) + ((size_t)2 << r->depth) * sizeof(double));
+  const int g = (count + 255) / 256;
+  hbr::k_claim<<<g, 256, 0, s>>>(writer, indices, count);
+  hbr::k_set_leaves<<<g, 256, 0, s>>>(r->tree, r->depth, writer, indices, priorities, count);
+  hbr::k_unclaim<<<g, 256, 0, s>>>(writer, indices, count);
+  for (int l = r->depth - 1; l >= 0; --l)
+    hbr::k_rebuild_level<<<g, 256, 0, s>>>(r->tree, r->depth, l, indices, count);
+  HBR_CUDA(cudaGetLastError());
+  if ((double)host_max_priority > r->max_recorded_priority) r->max_recorded_priority = host_max_priority;
+  return 0;
+}
+
+int ReplayGetPriority(pyhanabi_replay_t* h, const int32_t* indices, int count, float* priorities, void* stream) {
+  HBR_REPLAY(h);
+  if (!r->prioritized) return HbFail("ReplayGetPriority: the replay memory is not prioritized");
+  hbr::k_get_priority<<<(count + 255) / 256, 256, 0, (cudaStream_t)stream>>>(MakeView(r), indices, count, priorities);
+  HBR_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int ReplayIsValidTransition(pyhanabi_replay_t* h, const int32_t* indices, int count, uint8_t* valid, void* stream) {
+  HBR_REPLAY(h);
+  hbr::k_is_valid<<<(count + 255) / 256, 256, 0, (cudaStream_t)stream>>>(MakeView(r), indices, count, valid);
+  HBR_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int ReplayTreeSample(pyhanabi_replay_t* h, const double* query_values, int count, int32_t* indices, void* stream) {
+  HBR_REPLAY(h);
+  if (!r->prioritized) return HbFail("ReplayTreeSample: the replay memory is not prioritized");
+  hbr::k_tree_sample<<<(count + 255) / 256, 256, 0, (cudaStream_t)stream>>>(MakeView(r), query_values, count, indices);
+  HBR_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int ReplaySampleIndexBatch(pyhanabi_replay_t* h, int count, int stratified, uint64_t seed, uint64_t step,
+                           int32_t* indices, void* stream) {
+  HBR_REPLAY(h);
+  if (r->add_count == 0) return HbFail("ReplaySampleIndexBatch: the replay memory is empty");
+  hbr::k_sample_indices<<<(count + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      MakeView(r), r->prioritized, stratified, seed, step, count, indices);
+  HBR_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int ReplaySampleTransitionBatch(pyhanabi_replay_t* h, const int32_t* indices, int count, uint8_t* states,
+                                int32_t* actions, float* rewards, uint8_t* next_states,
+                                uint8_t* terminals, float* next_legal_actions, void* stream) {
+  HBR_REPLAY(h);
+  if (!indices || !states || !actions || !rewards || !next_states || !terminals || !next_legal_actions)
+    return HbFail("ReplaySampleTransitionBatch: null argument");
+  const int64_t threads = (int64_t)count * 32;
+  hbr::k_gather<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      MakeView(r), indices, count, states, actions, rewards, next_states, terminals, next_legal_actions);
+  HBR_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

@@ -322,6 +322,49 @@ int BatchAgentAct(pyhanabi_batch_t* batch, int agent_kind, uint32_t seat_mask,
                   const int32_t* seat_slot, uint32_t* agent_state, int num_slots,
                   int32_t* actions, void* stream);
 
+/* ===== device-resident replay memory for the Rainbow learner ==============
+ * The reference's numpy ring buffer + sum tree (agents/rainbow_copy/replay_memory.py,
+ * prioritized_replay_memory.py, third_party/dopamine/sum_tree.py) with stack_size 1,
+ * kept in HBM.  All array arguments are DEVICE pointers.  Formats as in the
+ * reference: uint8 observations, int32 actions, float32 rewards, uint8 terminals,
+ * float32 legal-action vectors (0 / -inf).  New elements get priority 100
+ * (DEFAULT_PRIORITY) when `priority` < 0. */
+typedef struct PyHanabiReplay {
+  /* Points to the device-resident replay memory. */
+  void* replay;
+} pyhanabi_replay_t;
+int NewReplay(pyhanabi_replay_t* replay, int num_actions, int observation_size,
+              int64_t capacity, int update_horizon, float gamma, int prioritized, int device);
+void DeleteReplay(pyhanabi_replay_t* replay);
+int64_t ReplayAddCount(pyhanabi_replay_t* replay);
+int64_t ReplayCapacity(pyhanabi_replay_t* replay);
+double ReplayMaxRecordedPriority(pyhanabi_replay_t* replay);
+/* OutOfGraphReplayMemory.add for `count` transitions, appended in order at the cursor. */
+int ReplayAdd(pyhanabi_replay_t* replay, const uint8_t* obs, const int32_t* actions,
+              const float* rewards, const uint8_t* terminals, const float* legal_actions,
+              int count, float priority, void* stream);
+/* is_valid_transition (replay_memory.py:233-258) per index. */
+int ReplayIsValidTransition(pyhanabi_replay_t* replay, const int32_t* indices, int count,
+                            uint8_t* valid, void* stream);
+/* SumTree.sample(query_value) per query in [0,1) (sum_tree.py:99-141). */
+int ReplayTreeSample(pyhanabi_replay_t* replay, const double* query_values, int count,
+                     int32_t* indices, void* stream);
+/* sample_index_batch: valid indices, prioritized (optionally stratified) or uniform;
+ * -1 where no valid transition was found in 1000 attempts. */
+int ReplaySampleIndexBatch(pyhanabi_replay_t* replay, int count, int stratified, uint64_t seed,
+                           uint64_t step, int32_t* indices, void* stream);
+/* sample_transition_batch(indices=...) (replay_memory.py:290-347): n-step rewards
+ * truncated at the first terminal, next state / next legal actions update_horizon
+ * slots later. */
+int ReplaySampleTransitionBatch(pyhanabi_replay_t* replay, const int32_t* indices, int count,
+                                uint8_t* states, int32_t* actions, float* rewards,
+                                uint8_t* next_states, uint8_t* terminals,
+                                float* next_legal_actions, void* stream);
+int ReplaySetPriority(pyhanabi_replay_t* replay, const int32_t* indices,
+                      const float* priorities, int count, float host_max_priority, void* stream);
+int ReplayGetPriority(pyhanabi_replay_t* replay, const int32_t* indices, int count,
+                      float* priorities, void* stream);
+
 /* Test hooks. */
 int BatchSetDebug(pyhanabi_batch_t* batch, int sampler_mode, int generic);
 int BatchDebugDeal(pyhanabi_batch_t* batch, const uint64_t* decks, const int32_t* sizes,
