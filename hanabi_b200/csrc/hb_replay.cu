@@ -99,24 +99,6 @@ __device__ inline int64_t tree_sample(const View& v, double query) {
   return node;
 }
 
-__global__ void k_add(uint8_t* obs, int32_t* actions, float* rewards, uint8_t* terminals, float* legal,
-                      int64_t cap, int64_t cursor, int D, int A, const uint8_t* in_obs,
-                      const int32_t* in_actions, const float* in_rewards, const uint8_t* in_terminals,
-                      const float* in_legal, int count) {
-  // one warp per transition: rows are copied with coalesced accesses
-  const int lane = threadIdx.x & 31;
-  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (i >= count) return;
-  const int64_t slot = (cursor + i) % cap;
-  for (int k = lane; k < D; k += 32) obs[slot * D + k] = in_obs[i * D + k];
-  for (int k = lane; k < A; k += 32) legal[slot * A + k] = in_legal[i * A + k];
-  if (lane == 0) {
-    actions[slot] = in_actions[i];
-    rewards[slot] = in_rewards[i];
-    terminals[slot] = in_terminals[i];
-  }
-}
-
 __global__ void k_set_leaves_range(double* tree, int depth, int64_t cap, int64_t cursor, int count,
                                    double value) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -347,22 +329,34 @@ int ReplayAdd(pyhanabi_replay_t* h, const uint8_t* obs, const int32_t* actions, 
               void* stream) {
   HBR_REPLAY(h);
   if (!obs || !actions || !rewards || !terminals || !legal_actions) return HbFail("ReplayAdd: null argument");
-  if (count <= 0) return 0;
-  if (count > r->cap) return HbFail("ReplayAdd: more transitions than the capacity in one call");
   cudaStream_t s = (cudaStream_t)stream;
-  const int64_t cursor = r->add_count % r->cap;
-  const int64_t threads = (int64_t)count * 32;
-  hbr::k_add<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(
-      r->obs, r->actions, r->rewards, r->terminals, r->legal, r->cap, cursor, r->D, r->A, obs, actions,
-      rewards, terminals, legal_actions, count);
-  HBR_CUDA(cudaGetLastError());
-  r->add_count += count;
-  if (r->prioritized) {
-    const double p = priority < 0.f ? 100.0 : (double)priority;  // DEFAULT_PRIORITY
-    if (p > r->max_recorded_priority) r->max_recorded_priority = p;
-    hbr::k_set_leaves_range<<<(count + 255) / 256, 256, 0, s>>>(r->tree, r->depth, r->cap, cursor, count, p);
-    HBR_CUDA(cudaGetLastError());
-    if (RebuildRange(r, cursor, count, s)) return 1;
+  // A batch longer than the ring overwrites its own head, like sequential adds would:
+  // feed it in stream-ordered pieces of at most `capacity` transitions.
+  for (int done = 0; done < count;) {
+    const int part = (int)((int64_t)(count - done) < r->cap ? (count - done) : r->cap);
+    const int64_t cursor = r->add_count % r->cap;
+    // consecutive slots are contiguous memory (two pieces when the ring wraps): the
+    // append is a set of device-to-device copies at full copy bandwidth
+    const int64_t first = (cursor + part <= r->cap) ? part : (r->cap - cursor);
+    for (int piece = 0; piece < 2; ++piece) {
+      const int64_t cnt = piece == 0 ? first : part - first;
+      if (cnt <= 0) continue;
+      const int64_t dst = piece == 0 ? cursor : 0, src = done + (piece == 0 ? 0 : first);
+      HBR_CUDA(cudaMemcpyAsync(r->obs + dst * r->D, obs + src * r->D, (size_t)cnt * r->D, cudaMemcpyDeviceToDevice, s));
+      HBR_CUDA(cudaMemcpyAsync(r->legal + dst * r->A, legal_actions + src * r->A, (size_t)cnt * r->A * sizeof(float), cudaMemcpyDeviceToDevice, s));
+      HBR_CUDA(cudaMemcpyAsync(r->actions + dst, actions + src, (size_t)cnt * sizeof(int32_t), cudaMemcpyDeviceToDevice, s));
+      HBR_CUDA(cudaMemcpyAsync(r->rewards + dst, rewards + src, (size_t)cnt * sizeof(float), cudaMemcpyDeviceToDevice, s));
+      HBR_CUDA(cudaMemcpyAsync(r->terminals + dst, terminals + src, (size_t)cnt, cudaMemcpyDeviceToDevice, s));
+    }
+    r->add_count += part;
+    if (r->prioritized) {
+      const double p = priority < 0.f ? 100.0 : (double)priority;  // DEFAULT_PRIORITY
+      if (p > r->max_recorded_priority) r->max_recorded_priority = p;
+      hbr::k_set_leaves_range<<<(part + 255) / 256, 256, 0, s>>>(r->tree, r->depth, r->cap, cursor, part, p);
+      HBR_CUDA(cudaGetLastError());
+      if (RebuildRange(r, cursor, part, s)) return 1;
+    }
+    done += part;
   }
   return 0;
 }

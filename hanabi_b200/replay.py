@@ -30,8 +30,12 @@ class DeviceReplayMemory(object):
 
   def __del__(self):
     c = getattr(self, "_c", None)
-    if c is not None and pyhanabi.lib is not None:
-      pyhanabi.lib.DeleteReplay(c)
+    lib = getattr(self, "_lib", None)
+    if c is not None and lib is not None:
+      try:
+        lib.DeleteReplay(c)
+      except Exception:  # interpreter shutdown: cffi may already be torn down
+        pass
       self._c = None
 
   def _check(self, rc, what):
