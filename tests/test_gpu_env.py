@@ -139,3 +139,60 @@ def test_tf_agents_style_adapter_follows_the_wrapper_protocol():
         ended[i] = done
         assert st[i] == (T.LAST if done else T.MID) and rw[i] == np.float32(reward)
   assert wrapped.action_spec()["maximum"] == benv.num_moves() - 1
+
+
+def test_self_play_recorder_posts_the_reference_trajectories():
+  """hanabi_b200.actor.SelfPlayRecorder vs the per-game restatement of the agent's
+  transition bookkeeping (oracle/actor_oracle.py); posted runs land in the device
+  replay memory as contiguous per-seat episodes."""
+  import torch
+  from hanabi_b200 import actor, replay, rl_env
+  from hanabi_b200 import pyhanabi as ph
+  from oracle import actor_oracle
+  n, steps = 40, 90
+  env = rl_env.make_batched("Hanabi-Small", num_players=3, num_games=n, seed=77)
+  D, A, P = env.batch.obs_size, env.batch.max_moves, env.players
+  mem = replay.DeviceReplayMemory(A, D, 1 << 14, update_horizon=3, gamma=0.99)
+  rec = actor.SelfPlayRecorder(n, P, D, A, env.device, replay=mem)
+  books = [actor_oracle.EpisodeBook(P) for _ in range(n)]
+  obs = env.reset()
+  act = torch.zeros(n, dtype=torch.int32, device=env.device)
+  want_posted, got_posted = [], []
+  for t in range(steps):
+    ph.select_action(None, obs["legal_moves_mask"], 1.0, seed=5, step=t, out=act)
+    cur = obs["current_player"].clone()
+    rec.before_step(cur, obs["vectorized"], obs["legal_moves_mask"], act)
+    o_h, m_h, c_h, a_h = (obs["vectorized"].cpu().numpy(), obs["legal_moves_mask"].cpu().numpy(),
+                          cur.cpu().numpy(), act.cpu().numpy())
+    for i in range(n):
+      books[i].act(int(c_h[i]), o_h[i], m_h[i], int(a_h[i]))
+    obs, reward, done, _ = env.step(act)
+    out = rec.after_step(reward, done)
+    r_h, d_h = reward.cpu().numpy(), done.cpu().numpy()
+    for i in range(n):
+      posted = books[i].env_result(float(r_h[i]), bool(d_h[i]))
+      if posted:
+        want_posted.extend(posted)
+    if out is not None:
+      o, a, r, term, legal = [x.cpu().numpy() for x in out]
+      for k in range(len(a)):
+        mask_bytes = (legal[k] == 0).astype(np.uint8).tobytes()
+        got_posted.append((o[k].tobytes(), int(a[k]), np.float32(r[k]), int(term[k]), mask_bytes))
+  assert len(want_posted) > 200 and rec.dropped == 0
+  # same games finish in the same step on both sides and runs are ordered by game then seat
+  assert got_posted == want_posted
+  assert mem.add_count == len(want_posted)
+  # the replay sees each seat's episode as one contiguous run: a 3-step window that
+  # starts inside a run never mixes rewards of two runs unless it crosses a terminal
+  idx = torch.arange(0, mem.add_count - 4, dtype=torch.int32, device=env.device)
+  state, action, reward3, next_state, terminal, _, _ = mem.sample_transition_batch(indices=idx)
+  flat_r = np.asarray([p[2] for p in want_posted], np.float32)
+  flat_t = np.asarray([p[3] for p in want_posted], np.uint8)
+  for i in range(0, len(idx), 17):
+    acc, term = np.float32(0), 0
+    for j in range(3):
+      acc = np.float32(acc + np.float32(0.99 ** j) * flat_r[i + j])
+      if flat_t[i + j]:
+        term = 1
+        break
+    assert abs(float(reward3[i]) - float(acc)) < 1e-5 and int(terminal[i]) == term
