@@ -85,3 +85,13 @@ class SelfPlayRecorder(object):
     self.count[finished] = 0
     self.since[finished] = 0
     return obs, action, reward_out, terminal, legal
+
+
+def linearly_decaying_epsilon(decay_period, step, warmup_steps, epsilon):
+  """Epsilon schedule of the DQN/Rainbow agents
+  (agents/rainbow_copy/dqn_agent.py:44-59): 1.0 during warm-up, then linear decay to
+  `epsilon` over `decay_period` steps."""
+  steps_left = decay_period + warmup_steps - step
+  bonus = (1.0 - epsilon) * steps_left / decay_period
+  bonus = min(max(bonus, 0.0), 1.0 - epsilon)
+  return epsilon + bonus

@@ -35,3 +35,13 @@ def test_masked_argmax_ties_take_first_index():
   q = np.asarray([[1.0, 3.0, 3.0, 2.0], [5.0, 1.0, 1.0, 1.0]], np.float32)
   mask = np.asarray([[1, 1, 1, 1], [0, 1, 1, 0]], np.uint8)
   assert C.masked_argmax(q, mask).tolist() == [1, 1]
+
+
+def test_linearly_decaying_epsilon_schedule():
+  """agents/rainbow_copy/dqn_agent.py:44-59 (values worked by hand from the formula)."""
+  from hanabi_b200.actor import linearly_decaying_epsilon as eps
+  assert eps(1000, 0, 500, 0.02) == 1.0            # warm-up
+  assert eps(1000, 500, 500, 0.02) == 1.0          # decay starts
+  assert abs(eps(1000, 1000, 500, 0.02) - 0.51) < 1e-12
+  assert abs(eps(1000, 1500, 500, 0.02) - 0.02) < 1e-12
+  assert eps(1000, 10**6, 500, 0.02) == 0.02
