@@ -47,6 +47,8 @@ struct KArgs {
   int32_t* cur_player;
   uint8_t* obs;
   int64_t obs_pitch;
+  uint32_t* obs_bits;  // alternative to obs: bit-packed rows of packed_words 32-bit words
+  int packed_words;
   uint8_t* mask;
   unsigned long long* stats;
   uint4* hist;  // optional: the 4 non-deal moves before `last`, newest first (BatchEnableHistory)
@@ -54,6 +56,7 @@ struct KArgs {
   int sampler_mode;
   int observer;
   int warp_smem_words;  // shared-memory words per warp: obs stream + mask stream + pads
+  int obs_stream_words; // words reserved for the observation stream inside that
 };
 
 // One CTA = kBlock games = kBlock/32 warp tiles.  Phases separated by CTA barriers keep the
@@ -240,16 +243,19 @@ __global__ void __launch_bounds__(kBlock, HB_MIN_CTAS) k_main(const __grid_const
   }
   const int n_valid = (int)((a.g_end - tile0) < 32 ? (a.g_end - tile0) : 32);
   uint32_t* obs_stream = smem + (size_t)warp * a.warp_smem_words;
-  uint32_t* mask_stream = obs_stream + a.spec.obs_size + kStreamPad;
-  if (a.obs) {
+  uint32_t* mask_stream = obs_stream + a.obs_stream_words + kStreamPad;
+  if (a.obs || a.obs_bits) {
     const int observer = a.observer < 0 ? G.cur : a.observer;
-    encode_obs(v, a.spec, G, observer, obs_stream, lane, s_spread);
+    encode_obs(v, a.spec, G, observer, obs_stream, lane, s_spread,
+               a.obs_bits ? a.packed_words * 32 : a.spec.obs_size);
   }
   if (a.mask) pack_mask_stream(mask_stream, a.spec.max_moves, legal_bits(v, G), valid, lane);
   __syncwarp();
   if (a.obs)
     expand_stream(obs_stream, a.spec.obs_size, a.obs + tile0 * a.obs_pitch, a.obs_pitch, n_valid,
                   lane);
+  if (a.obs_bits)
+    store_packed_rows(obs_stream, a.packed_words, a.obs_bits + tile0 * a.packed_words, n_valid, lane);
   if (a.mask)
     expand_stream(mask_stream, a.spec.max_moves, a.mask + tile0 * a.spec.max_moves,
                   a.spec.max_moves, n_valid, lane);
@@ -427,6 +433,7 @@ struct Batch {
   int sampler_mode = 0;
   int force_generic = 0;
   int warp_smem_words = 0;
+  int packed_words = 0, obs_stream_words = 0;
   size_t smem_bytes = 0;
   // pinned/pipelined host path
   cudaStream_t h_streams[3] = {nullptr, nullptr, nullptr};
@@ -497,6 +504,8 @@ hb::KArgs BaseArgs(const Batch* b) {
   a.sampler_mode = b->sampler_mode;
   a.observer = -1;
   a.warp_smem_words = b->warp_smem_words;
+  a.packed_words = b->packed_words;
+  a.obs_stream_words = b->obs_stream_words;
   return a;
 }
 
@@ -570,7 +579,11 @@ int NewBatch(pyhanabi_batch_t* out, int list_length, const char** param_list, in
   b->device = device;
   b->N = num_games;
   b->ncols = b->spec.P + 2;
-  b->warp_smem_words = b->spec.obs_size + b->spec.max_moves + 2 * hb::kStreamPad;
+  b->packed_words = 4 * ((b->spec.obs_size + 127) / 128);
+  b->obs_stream_words = b->spec.obs_size > 32 * b->packed_words ? b->spec.obs_size : 32 * b->packed_words;
+  b->obs_stream_words = (b->obs_stream_words + 3) & ~3;
+  // every warp's region starts 16-byte aligned (the packed rows are read as uint4)
+  b->warp_smem_words = (b->obs_stream_words + b->spec.max_moves + 2 * hb::kStreamPad + 3) & ~3;
   b->smem_bytes = ((size_t)hb::kWarps * b->warp_smem_words +
                    (size_t)hb::kQueueCap * 3 * b->spec.P * b->spec.H) * sizeof(uint32_t);
   DeviceGuard guard(device);
@@ -810,6 +823,39 @@ int BatchResetHost(pyhanabi_batch_t* h, uint8_t* obs, int64_t row_pitch, uint8_t
   if (d_mask) HB_CUDA(cudaFreeAsync(d_mask, s));
   if (d_cur) HB_CUDA(cudaFreeAsync(d_cur, s));
   HB_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+// Bit-packed observations: row i = BatchPackedObservationWords() 32-bit words
+// (a multiple of 4, i.e. 16-byte rows), bit j of the row = observation bit j, padding
+// bits zero.  8x less HBM / PCIe traffic than one byte per bit, for consumers that
+// unpack on the fly; np.unpackbits(rows.view(uint8), bitorder="little")[:, :obs_size]
+// gives back the byte form.
+int BatchPackedObservationWords(pyhanabi_batch_t* h) {
+  return (h && h->batch) ? AsBatch(h->batch)->packed_words : -1;
+}
+
+int BatchStepEncodePacked(pyhanabi_batch_t* h, const int32_t* actions, int32_t* rewards,
+                          uint8_t* dones, int32_t* scores, uint32_t* obs_bits, uint8_t* mask,
+                          int32_t* cur_player, int auto_reset, void* stream) {
+  HB_BATCH(h);
+  if (!actions) return Fail("BatchStepEncodePacked: actions is null");
+  if (obs_bits && (reinterpret_cast<uintptr_t>(obs_bits) & 15)) return Fail("BatchStepEncodePacked: obs_bits must be 16-byte aligned");
+  hb::KArgs a = BaseArgs(b);
+  a.actions = actions; a.rewards = rewards; a.dones = dones; a.scores = scores;
+  a.obs_bits = obs_bits; a.mask = mask; a.cur_player = cur_player; a.auto_reset = auto_reset;
+  HB_CUDA(Launch<hb::kModeStep>(b, a, (cudaStream_t)stream));
+  return 0;
+}
+
+int BatchObservePacked(pyhanabi_batch_t* h, int observer, uint32_t* obs_bits, uint8_t* mask,
+                       int32_t* cur_player, void* stream) {
+  HB_BATCH(h);
+  if (observer >= b->spec.P) return Fail("BatchObservePacked: observer out of range");
+  if (obs_bits && (reinterpret_cast<uintptr_t>(obs_bits) & 15)) return Fail("BatchObservePacked: obs_bits must be 16-byte aligned");
+  hb::KArgs a = BaseArgs(b);
+  a.obs_bits = obs_bits; a.observer = observer; a.mask = mask; a.cur_player = cur_player;
+  HB_CUDA(Launch<hb::kModeObserve>(b, a, (cudaStream_t)stream));
   return 0;
 }
 

@@ -740,9 +740,11 @@ HB_DEV uint32_t spread_entry(int cm, int C, int R) {
 
 template <class V>
 HB_DEV void encode_obs(V v, const Spec& spec, const Game& G, int observer, uint32_t* stream,
-                       int lane, const uint32_t* spread) {
+                       int lane, const uint32_t* spread, int slice_bits) {
   const int P = v.P(), H = v.H(), C = v.C(), R = v.R(), bpc = v.bpc();
-  BitWriter bw(stream, lane, spec.obs_size);
+  // slice_bits = distance between two lanes' slices in the stream: obs_size for
+  // the dense byte expansion, a multiple of 128 for the bit-packed output rows
+  BitWriter bw(stream, lane, slice_bits);
   // --- hands (canonical_encoders.cc:62-105)
   uint32_t short_bits = 0;
 #pragma unroll
@@ -827,6 +829,21 @@ HB_DEV void encode_obs(V v, const Spec& spec, const Game& G, int observer, uint3
     }
   }
   bw.finish(lane, spec.obs_size);
+  if (slice_bits != spec.obs_size) {  // packed rows: zero the padding words of this lane's row
+    uint32_t* row = stream + lane * (slice_bits >> 5);
+    for (int w = (spec.obs_size + 31) >> 5; w < (slice_bits >> 5); ++w) row[w] = 0u;
+  }
+}
+
+// Bit-packed observation rows: copies the tile's stream (n_valid rows of
+// `row_words` 32-bit words, bit j of a row = observation bit j) to global memory
+// with 128-bit stores.
+HB_DEV void store_packed_rows(const uint32_t* stream, int row_words, uint32_t* out, int n_valid,
+                              int lane) {
+  const int quads = (n_valid * row_words) >> 2;  // row_words is a multiple of 4
+  const uint4* src = reinterpret_cast<const uint4*>(stream);
+  uint4* dst = reinterpret_cast<uint4*>(out);
+  for (int k = lane; k < quads; k += 32) dst[k] = src[k];
 }
 
 // Legal-move masks of the tile as a packed stream (A bits per game).  The slices

@@ -777,6 +777,32 @@ class HanabiBatch(object):
         self._p(cur_player, torch.int32, n, "int32_t*"), int(bool(auto_reset)), self._stream()),
            "BatchStepEncodeScores")
 
+  # -- bit-packed observations (int32 tensors [num_games, packed_words])
+  @property
+  def packed_words(self):
+    return int(lib.BatchPackedObservationWords(self._c))
+
+  def step_encode_packed(self, actions, rewards=None, dones=None, obs_bits=None, mask=None,
+                         cur_player=None, scores=None, auto_reset=True):
+    torch = self._torch
+    n = self.num_games
+    _check(lib.BatchStepEncodePacked(
+        self._c, self._p(actions, torch.int32, n, "int32_t*"),
+        self._p(rewards, torch.int32, n, "int32_t*"), self._p(dones, torch.uint8, n, "uint8_t*"),
+        self._p(scores, torch.int32, n, "int32_t*"),
+        self._p(obs_bits, torch.int32, n * self.packed_words, "uint32_t*"),
+        self._p(mask, torch.uint8, n * self.max_moves, "uint8_t*"),
+        self._p(cur_player, torch.int32, n, "int32_t*"), int(bool(auto_reset)), self._stream()),
+           "BatchStepEncodePacked")
+
+  def observe_packed(self, obs_bits, mask=None, cur_player=None, observer=-1):
+    torch = self._torch
+    n = self.num_games
+    _check(lib.BatchObservePacked(
+        self._c, int(observer), self._p(obs_bits, torch.int32, n * self.packed_words, "uint32_t*"),
+        self._p(mask, torch.uint8, n * self.max_moves, "uint8_t*"),
+        self._p(cur_player, torch.int32, n, "int32_t*"), self._stream()), "BatchObservePacked")
+
   def bind_step_encode(self, actions, rewards=None, dones=None, obs=None, mask=None,
                        cur_player=None, scores=None, auto_reset=True, stream=None):
     """Pre-validated, pre-cast variant of step_encode for tight loops: returns a

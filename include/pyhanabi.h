@@ -238,6 +238,16 @@ int BatchStepEncodeScores(pyhanabi_batch_t* batch, const int32_t* actions,
                           int64_t row_pitch, uint8_t* mask, int32_t* cur_player,
                           int auto_reset, void* stream);
 
+/* Bit-packed observations (optional, reported separately from the byte form): row i
+ * = BatchPackedObservationWords() uint32 words (16-byte multiple), bit j of the row
+ * = observation bit j, padding zero.  obs_bits must be 16-byte aligned. */
+int BatchPackedObservationWords(pyhanabi_batch_t* batch);
+int BatchStepEncodePacked(pyhanabi_batch_t* batch, const int32_t* actions, int32_t* rewards,
+                          uint8_t* dones, int32_t* scores, uint32_t* obs_bits, uint8_t* mask,
+                          int32_t* cur_player, int auto_reset, void* stream);
+int BatchObservePacked(pyhanabi_batch_t* batch, int observer, uint32_t* obs_bits,
+                       uint8_t* mask, int32_t* cur_player, void* stream);
+
 /* The same two verbs with HOST buffers (pinned memory recommended), for callers
  * that keep their data on the CPU like the reference's trainers do: uploads the
  * actions, runs the fused kernel and downloads the results, chunked over

@@ -283,3 +283,51 @@ def test_unaligned_output_buffer_takes_the_byte_path():
     b.encode(view)
     common.assert_same(cpu.encode(), view.cpu().numpy(), "obs at byte offset %d" % shift)
     assert bool((store[:shift] == 9).all()) and bool((store[shift + n * D:] == 9).all())
+
+
+@pytest.mark.parametrize("name", ["full2", "full5", "small2", "vsmall2", "odd"])
+def test_packed_observations_match_byte_form(name):
+  """Bit-packed rows (BatchStepEncodePacked / BatchObservePacked) unpack to exactly
+  the byte-per-bit observations, padding bits are zero, for full and ragged tiles."""
+  import torch
+  from hanabi_b200 import pyhanabi as ph
+  n = 333
+  p = CONFIGS[name]
+  seeds = common.seeds_for(n, base=61)
+  a = ph.HanabiBatch(p, n, seeds)
+  b = ph.HanabiBatch(p, n, seeds)
+  dev = a.device
+  W, D, A = a.packed_words, a.obs_size, a.max_moves
+  assert W % 4 == 0 and W * 32 >= D and (W - 4) * 32 < D
+  obs = torch.zeros((n, D), dtype=torch.uint8, device=dev)
+  bits = torch.full((n, W), -1, dtype=torch.int32, device=dev)
+  mask_a = torch.zeros((n, A), dtype=torch.uint8, device=dev)
+  mask_b = torch.zeros((n, A), dtype=torch.uint8, device=dev)
+  cur = torch.zeros(n, dtype=torch.int32, device=dev)
+  rew_a = torch.zeros(n, dtype=torch.int32, device=dev); rew_b = torch.zeros_like(rew_a)
+  done_a = torch.zeros(n, dtype=torch.uint8, device=dev); done_b = torch.zeros_like(done_a)
+  act = torch.zeros(n, dtype=torch.int32, device=dev)
+  a.reset(); b.reset()
+  a.observe(obs, mask_a, cur)
+  b.observe_packed(bits, mask_b, cur)
+
+  def check():
+    raw = bits.cpu().numpy().view(np.uint8).reshape(n, W * 4)
+    unpacked = np.unpackbits(raw, axis=1, bitorder="little")
+    common.assert_same(obs.cpu().numpy(), unpacked[:, :D], "packed vs byte observation")
+    assert not unpacked[:, D:].any()
+    assert torch.equal(mask_a, mask_b)
+
+  check()
+  for t in range(30):
+    ph.select_action(None, mask_a, 1.0, seed=9, step=t, out=act)
+    a.step_encode(act, rew_a, done_a, obs, mask_a, cur)
+    bits.fill_(-1)
+    b.step_encode_packed(act, rew_b, done_b, bits, mask_b, cur)
+    assert torch.equal(rew_a, rew_b) and torch.equal(done_a, done_b)
+    check()
+  for observer in range(a.num_players):
+    a.encode(obs, observer)
+    b.observe_packed(bits, observer=observer)
+    raw = np.unpackbits(bits.cpu().numpy().view(np.uint8).reshape(n, W * 4), axis=1, bitorder="little")
+    common.assert_same(obs.cpu().numpy(), raw[:, :D], "packed observation of player %d" % observer)
