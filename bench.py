@@ -51,6 +51,8 @@ def parse_args():
   ap.add_argument("--e2e-games", type=int, default=1 << 18)
   ap.add_argument("--cpu-seconds", type=float, default=12.0)
   ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--packed", action="store_true",
+                  help="also measure the optional bit-packed observation output (extra key)")
   ap.add_argument("--python-baselines", action="store_true",
                   help="also time the Python paths of BASELINE.md section 3 (C1-C3) on the host")
   ap.add_argument("--cpu-python-worker", default=None, help=argparse.SUPPRESS)
@@ -421,6 +423,48 @@ def main():
                    "the timed region"}
     del hb
 
+  # ---- optional extra, reported separately and never mixed into the headline:
+  # bit-packed observation rows (16-byte multiples, 96 B instead of 658 B for 2p)
+  packed = None
+  if args.packed:
+    Wp = batch.packed_words
+    bits = torch.empty((n, Wp), dtype=torch.int32, device=dev)
+    step_packed = lambda: batch.step_encode_packed(act, rew, done, bits, mask, cur)
+    for t in range(W):
+      select(10**6 + t); step_packed()
+    torch.cuda.synchronize()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    Kp = min(K, 500)
+    p0.record()
+    for t in range(Kp):
+      select(10**6 + W + t); step_packed()
+    p1.record()
+    torch.cuda.synchronize()
+    pms = p0.elapsed_time(p1) / Kp
+    packed = {"value": world * n / (pms * 1e-3), "unit": "env-steps/s", "ms_per_step": pms,
+              "obs_bytes_per_game": 4 * Wp, "note": "device-resident, bit-packed observation rows"}
+    if args.e2e_steps > 0:
+      hb2 = ph.HanabiBatch(params, ne, seeds[:ne], device=local_rank)
+      pinned = lambda *shape, dt: torch.empty(shape, dtype=dt).pin_memory()
+      q_bits, q_mask = pinned(ne, Wp, dt=torch.int32), pinned(ne, A, dt=torch.uint8)
+      q_cur, q_rew = pinned(ne, dt=torch.int32), pinned(ne, dt=torch.int32)
+      q_done, q_act = pinned(ne, dt=torch.uint8), pinned(ne, dt=torch.int32)
+      q_obs = pinned(ne, D, dt=torch.uint8)
+      hb2.reset_host(q_obs, q_mask, q_cur)
+      def packed_host_step(t):
+        ph.host_random_legal_actions(q_mask, seed=7, step=t, out=q_act)
+        hb2.step_encode_host_packed(q_act, q_rew, q_done, q_bits, q_mask, q_cur)
+      for t in range(3):
+        packed_host_step(t)
+      t0 = time.perf_counter()
+      for t in range(args.e2e_steps):
+        packed_host_step(3 + t)
+      dtp = time.perf_counter() - t0
+      packed["e2e"] = {"value": world * ne * args.e2e_steps / dtp, "unit": "env-steps/s",
+                       "d2h_bytes_per_step": ne * (4 * Wp + A + 9), "h2d_bytes_per_step": ne * 4,
+                       "games_per_step": ne}
+      del hb2
+
   if rank != 0:
     if dist:
       dist.destroy_process_group()
@@ -464,6 +508,8 @@ def main():
       "episodes": {"count": st[0], "mean_score": st[1] / max(st[0], 1),
                    "mean_length": st[2] / max(st[0], 1)},
   }
+  if packed is not None:
+    line["packed_obs"] = packed
   if not args.no_cpu_baseline:
     line["cpu_baseline"] = cpu_reference_rate(args.workload, args.cpu_seconds)
     if args.python_baselines:

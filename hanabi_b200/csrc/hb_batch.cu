@@ -742,9 +742,9 @@ int BatchStepEncodeScores(pyhanabi_batch_t* h, const int32_t* actions, int32_t* 
 // action upload, the kernel and the result download of neighbouring chunks
 // overlap.  Synchronous: the host buffers are complete on return.  `stream` is
 // the stream whose earlier work on this batch must finish first (may be NULL).
-int BatchStepEncodeHost(pyhanabi_batch_t* h, const int32_t* actions, int32_t* rewards,
-                        uint8_t* dones, int32_t* scores, uint8_t* obs, int64_t row_pitch,
-                        uint8_t* mask, int32_t* cur_player, int auto_reset, void* stream) {
+static int StepHost(pyhanabi_batch_t* h, const int32_t* actions, int32_t* rewards, uint8_t* dones,
+                    int32_t* scores, uint8_t* obs, int64_t row_pitch, uint32_t* obs_bits,
+                    uint8_t* mask, int32_t* cur_player, int auto_reset, void* stream) {
   HB_BATCH(h);
   if (!actions) return Fail("BatchStepEncodeHost: actions is null");
   if (obs && row_pitch < b->spec.obs_size) return Fail("BatchStepEncodeHost: row_pitch smaller than the observation");
@@ -779,8 +779,14 @@ int BatchStepEncodeHost(pyhanabi_batch_t* h, const int32_t* actions, int32_t* re
     a.g_begin = (int64_t)g0; a.g_end = (int64_t)g1;
     a.actions = b->d_actions; a.rewards = b->d_rewards; a.dones = b->d_dones; a.scores = b->d_scores;
     a.obs = obs ? b->d_obs : nullptr; a.obs_pitch = D; a.mask = mask ? b->d_mask : nullptr;
+    a.obs_bits = (!obs && obs_bits) ? reinterpret_cast<uint32_t*>(b->d_obs) : nullptr;  // staging reused
     a.cur_player = b->d_cur; a.auto_reset = auto_reset;
     HB_CUDA(Launch<hb::kModeStep>(b, a, s));
+    if (a.obs_bits) {
+      const size_t row = (size_t)b->packed_words * sizeof(uint32_t);
+      HB_CUDA(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(obs_bits) + g0 * row, b->d_obs + g0 * row, n * row,
+                              cudaMemcpyDeviceToHost, s));
+    }
     if (obs) {
       if (row_pitch == D)
         HB_CUDA(cudaMemcpyAsync(obs + g0 * (size_t)D, b->d_obs + g0 * (size_t)D, n * (size_t)D, cudaMemcpyDeviceToHost, s));
@@ -796,6 +802,21 @@ int BatchStepEncodeHost(pyhanabi_batch_t* h, const int32_t* actions, int32_t* re
   }
   for (int i = 0; i < 3; ++i) HB_CUDA(cudaStreamSynchronize(b->h_streams[i]));
   return 0;
+}
+
+int BatchStepEncodeHost(pyhanabi_batch_t* h, const int32_t* actions, int32_t* rewards,
+                        uint8_t* dones, int32_t* scores, uint8_t* obs, int64_t row_pitch,
+                        uint8_t* mask, int32_t* cur_player, int auto_reset, void* stream) {
+  return StepHost(h, actions, rewards, dones, scores, obs, row_pitch, nullptr, mask, cur_player,
+                  auto_reset, stream);
+}
+
+// Same with bit-packed observation rows in the HOST buffer (8x fewer PCIe bytes).
+int BatchStepEncodeHostPacked(pyhanabi_batch_t* h, const int32_t* actions, int32_t* rewards,
+                              uint8_t* dones, int32_t* scores, uint32_t* obs_bits, uint8_t* mask,
+                              int32_t* cur_player, int auto_reset, void* stream) {
+  return StepHost(h, actions, rewards, dones, scores, nullptr, 0, obs_bits, mask, cur_player,
+                  auto_reset, stream);
 }
 
 // rl_env.HanabiEnv.reset with HOST result buffers (observation, legal mask and

@@ -858,6 +858,19 @@ class HanabiBatch(object):
         self._h(cur_player, torch.int32, n, "int32_t*"), int(bool(auto_reset)), self._stream()),
            "BatchStepEncodeHost")
 
+  def step_encode_host_packed(self, actions, rewards=None, dones=None, obs_bits=None, mask=None,
+                              cur_player=None, scores=None, auto_reset=True):
+    torch = self._torch
+    n = self.num_games
+    _check(lib.BatchStepEncodeHostPacked(
+        self._c, self._h(actions, torch.int32, n, "int32_t*"),
+        self._h(rewards, torch.int32, n, "int32_t*"), self._h(dones, torch.uint8, n, "uint8_t*"),
+        self._h(scores, torch.int32, n, "int32_t*"),
+        self._h(obs_bits, torch.int32, n * self.packed_words, "uint32_t*"),
+        self._h(mask, torch.uint8, n * self.max_moves, "uint8_t*"),
+        self._h(cur_player, torch.int32, n, "int32_t*"), int(bool(auto_reset)), self._stream()),
+           "BatchStepEncodeHostPacked")
+
   def reset_host(self, obs=None, mask=None, cur_player=None):
     torch = self._torch
     n = self.num_games

@@ -256,6 +256,10 @@ int BatchObservePacked(pyhanabi_batch_t* batch, int observer, uint32_t* obs_bits
 int BatchStepEncodeHost(pyhanabi_batch_t* batch, const int32_t* actions, int32_t* rewards,
                         uint8_t* dones, int32_t* scores, uint8_t* obs, int64_t row_pitch,
                         uint8_t* mask, int32_t* cur_player, int auto_reset, void* stream);
+int BatchStepEncodeHostPacked(pyhanabi_batch_t* batch, const int32_t* actions,
+                              int32_t* rewards, uint8_t* dones, int32_t* scores,
+                              uint32_t* obs_bits, uint8_t* mask, int32_t* cur_player,
+                              int auto_reset, void* stream);
 int BatchResetHost(pyhanabi_batch_t* batch, uint8_t* obs, int64_t row_pitch, uint8_t* mask,
                    int32_t* cur_player, void* stream);
 

@@ -82,6 +82,20 @@ def test_host_buffer_entry_points_match_device_path():
   host.step_encode_host(h_act, h_rew, h_done, h_pad, h_mask, h_cur)
   dev.step_encode(d_act, d_rew, d_done, d_obs, d_mask, d_cur)
   assert torch.equal(h_pad[:, :D], d_obs.cpu()) and (h_pad[:, D:] == 9).all()
+  # bit-packed rows in the host buffer unpack to the byte form
+  W = dev.packed_words
+  h_bits = torch.zeros((n, W), dtype=torch.int32).pin_memory()
+  for t in range(12, 16):
+    ph.host_random_legal_actions(h_mask, seed=7, step=t, out=h_act)
+    d_act.copy_(h_act)
+    host.step_encode_host_packed(h_act, h_rew, h_done, h_bits, h_mask, h_cur, scores=h_score)
+    dev.step_encode(d_act, d_rew, d_done, d_obs, d_mask, d_cur, scores=d_score)
+    raw = np.unpackbits(h_bits.numpy().view(np.uint8), axis=1, bitorder="little")
+    common.assert_same(d_obs.cpu().numpy(), raw[:, :D], "host packed rows @%d" % t)
+    assert not raw[:, D:].any()
+    assert torch.equal(d_mask.cpu(), h_mask) and torch.equal(d_cur.cpu(), h_cur)
+    assert torch.equal(d_rew.cpu(), h_rew) and torch.equal(d_done.cpu(), h_done)
+    assert torch.equal(d_score.cpu(), h_score)
 
 
 def test_new_batch_rejects_bad_parameters():
