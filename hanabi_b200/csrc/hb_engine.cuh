@@ -96,21 +96,53 @@ constexpr int kLaValid = 0, kLaTypeSh = 1, kLaActorSh = 3, kLaOffSh = 6, kLaValS
 
 HB_DEV int hand_size(const Game& G, int p_static) { return (G.hw[p_static] >> 16) & 15; }
 
+// The packed state is the one array the next step reads again: with
+// HB_STATE_EVICT_LAST its loads and stores carry an L2 evict-last policy so that the
+// streaming observation stores do not push it out of the 126 MB L2.
+#ifndef HB_STATE_EVICT_LAST
+#define HB_STATE_EVICT_LAST 0
+#endif
+HB_DEV uint64_t state_policy() {
+  uint64_t pol;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+HB_DEV uint4 ld_state(const uint4* p) {
+#if HB_STATE_EVICT_LAST
+  uint4 v;
+  asm volatile("ld.global.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p), "l"(state_policy()));
+  return v;
+#else
+  return *p;
+#endif
+}
+HB_DEV void st_state(uint4* p, uint4 v) {
+#if HB_STATE_EVICT_LAST
+  asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;"
+               :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(state_policy())
+               : "memory");
+#else
+  *p = v;
+#endif
+}
+
 template <class V>
 HB_DEV void load_game(const uint4* __restrict__ st, int64_t N, int64_t g, V v, Game& G) {
 #pragma unroll
   for (int p = 0; p < V::kP; ++p) {
     if (p < v.P()) {
-      uint4 c = st[(int64_t)p * N + g];
+      uint4 c = ld_state(st + (int64_t)p * N + g);
       G.cards[p] = c.x; G.cpl[p] = c.y; G.rpl[p] = c.z; G.hw[p] = c.w;
     } else {
       G.cards[p] = 0; G.cpl[p] = 0; G.rpl[p] = 0; G.hw[p] = 0;
     }
   }
-  uint4 a = st[(int64_t)v.P() * N + g];
+  uint4 a = ld_state(st + (int64_t)v.P() * N + g);
   G.deck = (uint64_t)a.x | ((uint64_t)a.y << 32);
   G.disc = (uint64_t)a.z | ((uint64_t)a.w << 32);
-  uint4 b = st[(int64_t)(v.P() + 1) * N + g];
+  uint4 b = ld_state(st + (int64_t)(v.P() + 1) * N + g);
   G.fw = b.x & 0x7fffu;
   G.info = (b.x >> 15) & 31;
   G.life = (b.x >> 20) & 15;
@@ -129,16 +161,16 @@ template <class V>
 HB_DEV void store_game(uint4* __restrict__ st, int64_t N, int64_t g, V v, const Game& G) {
 #pragma unroll
   for (int p = 0; p < V::kP; ++p) {
-    if (p < v.P()) st[(int64_t)p * N + g] = make_uint4(G.cards[p], G.cpl[p], G.rpl[p], G.hw[p]);
+    if (p < v.P()) st_state(st + (int64_t)p * N + g, make_uint4(G.cards[p], G.cpl[p], G.rpl[p], G.hw[p]));
   }
-  st[(int64_t)v.P() * N + g] = make_uint4((uint32_t)G.deck, (uint32_t)(G.deck >> 32),
-                                          (uint32_t)G.disc, (uint32_t)(G.disc >> 32));
+  st_state(st + (int64_t)v.P() * N + g, make_uint4((uint32_t)G.deck, (uint32_t)(G.deck >> 32),
+                                                   (uint32_t)G.disc, (uint32_t)(G.disc >> 32)));
   uint32_t x = G.fw | ((uint32_t)G.info << 15) | ((uint32_t)G.life << 20) |
                ((uint32_t)G.cur << 24) | ((uint32_t)G.turns << 27) | ((uint32_t)G.done << 30) |
                ((uint32_t)G.err << 31);
   uint32_t y = (uint32_t)G.deck_size | ((uint32_t)G.mti << 6) |
                ((uint32_t)(G.eplen > 4095 ? 4095 : G.eplen) << 16);
-  st[(int64_t)(v.P() + 1) * N + g] = make_uint4(x, y, G.last, G.spare);
+  st_state(st + (int64_t)(v.P() + 1) * N + g, make_uint4(x, y, G.last, G.spare));
 }
 
 // Register-array access with a runtime player index: a predicated select chain
@@ -211,6 +243,23 @@ HB_DEV void mt_take2(uint32_t* x, int& k, uint32_t& w0, uint32_t& w1, Prefetch* 
   __stcg(x + k, mt_next_block_word(f.a, f.b, f.p));
   __stcg(x + k1, mt_next_block_word(f.b, f.c, f.q));
   k = mt_wrap(k + 2);
+}
+
+// L2 prefetch of the words the initial deal of a new game will take from index k
+// on (2 * pairs outputs): x[k .. k + 2*pairs] and x[k+397 .. k+397 + 2*pairs - 1],
+// indices mod 624.  Issued the moment a game is known to end, so that the re-deal's
+// loads find the lines in L2.
+HB_DEV void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+HB_DEV void mt_prefetch_deal(const uint32_t* x, int k, int pairs) {
+  const int n = 2 * pairs;
+  prefetch_l2(x + k);
+  const int e = k + n;
+  prefetch_l2(x + (e < kMtN ? e : kMtN - 1));
+  if (e >= kMtN) prefetch_l2(x);
+  const int m = mt_wrap(k + kMtM), me = m + n - 1;
+  prefetch_l2(x + m);
+  prefetch_l2(x + (me < kMtN ? me : kMtN - 1));
+  if (me >= kMtN) prefetch_l2(x);
 }
 
 // Takes one output (random start player draw).
@@ -835,6 +884,19 @@ HB_DEV void encode_obs(V v, const Spec& spec, const Game& G, int observer, uint3
   }
 }
 
+// The observation / mask rows are written once and never read back by the engine:
+// streaming (evict-first) stores keep them from displacing the game state in L2.
+#ifndef HB_STREAM_STORES
+#define HB_STREAM_STORES 1
+#endif
+HB_DEV void store_out(uint4* p, uint4 v) {
+#if HB_STREAM_STORES
+  __stcs(p, v);
+#else
+  *p = v;
+#endif
+}
+
 // Bit-packed observation rows: copies the tile's stream (n_valid rows of
 // `row_words` 32-bit words, bit j of a row = observation bit j) to global memory
 // with 128-bit stores.
@@ -843,7 +905,7 @@ HB_DEV void store_packed_rows(const uint32_t* stream, int row_words, uint32_t* o
   const int quads = (n_valid * row_words) >> 2;  // row_words is a multiple of 4
   const uint4* src = reinterpret_cast<const uint4*>(stream);
   uint4* dst = reinterpret_cast<uint4*>(out);
-  for (int k = lane; k < quads; k += 32) dst[k] = src[k];
+  for (int k = lane; k < quads; k += 32) store_out(dst + k, src[k]);
 }
 
 // Legal-move masks of the tile as a packed stream (A bits per game).  The slices
@@ -879,16 +941,27 @@ HB_DEV uint4 bits16_to_bytes(uint32_t bits) {
 // the tile is one contiguous, 16-byte aligned byte range and every 128-bit store
 // is fed by one halfword of the stream, a warp covering 512 contiguous bytes per
 // instruction.  The stream must have one readable pad word after its last word.
+// `lut` (optional): 256 entries, byte value -> its 8 bits as 8 bytes of 0/1, in shared
+// memory; two 64-bit table reads replace the twelve ALU operations per 128-bit store.
 HB_DEV void expand_stream(const uint32_t* stream, int dim, uint8_t* out, int64_t pitch,
-                          int n_valid, int lane) {
+                          int n_valid, int lane, const uint2* lut = nullptr) {
   const bool aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
   if (pitch == dim && aligned) {
     const int total = n_valid * dim;
     const int full_chunks = total >> 4;
     const uint16_t* half = reinterpret_cast<const uint16_t*>(stream);
     uint4* dst = reinterpret_cast<uint4*>(out);
+    if (lut != nullptr) {
 #pragma unroll 4
-    for (int k = lane; k < full_chunks; k += 32) dst[k] = bits16_to_bytes(half[k]);
+      for (int k = lane; k < full_chunks; k += 32) {
+        const uint32_t bits = half[k];
+        const uint2 lo = lut[bits & 255u], hi = lut[bits >> 8];
+        store_out(dst + k, make_uint4(lo.x, lo.y, hi.x, hi.y));
+      }
+    } else {
+#pragma unroll 4
+      for (int k = lane; k < full_chunks; k += 32) store_out(dst + k, bits16_to_bytes(half[k]));
+    }
     for (int b = (full_chunks << 4) + lane; b < total; b += 32)  // ragged tail of a partial tile
       out[b] = (uint8_t)((stream[b >> 5] >> (b & 31)) & 1u);
   } else if ((pitch & 15) == 0 && aligned) {
@@ -901,7 +974,7 @@ HB_DEV void expand_stream(const uint32_t* stream, int dim, uint8_t* out, int64_t
           __funnelshift_r(stream[pos >> 5], stream[(pos >> 5) + 1], pos & 31) & 0xffffu;
       uint8_t* d = out + (int64_t)g * pitch + o;
       if (avail >= 16) {
-        *reinterpret_cast<uint4*>(d) = bits16_to_bytes(bits);
+        store_out(reinterpret_cast<uint4*>(d), bits16_to_bytes(bits));
       } else {
         for (int i = 0; i < avail; ++i) d[i] = (uint8_t)((bits >> i) & 1u);
       }

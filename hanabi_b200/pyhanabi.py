@@ -943,6 +943,13 @@ class HanabiBatch(object):
     return {"episodes": vals[0], "score_sum": vals[1], "length_sum": vals[2],
             "score_hist": vals[3:29]}
 
+  def set_l2_residency(self, max_bytes=0):
+    """Keeps the packed state in L2 between steps (BatchSetL2Residency); returns the
+    number of state bytes covered.  max_bytes < 0 switches it off."""
+    covered = ffi.new("int64_t*")
+    _check(lib.BatchSetL2Residency(self._c, int(max_bytes), covered), "BatchSetL2Residency")
+    return int(covered[0])
+
   # -- test hooks
   def set_debug(self, sampler_mode=0, generic=False):
     _check(lib.BatchSetDebug(self._c, int(sampler_mode), int(bool(generic))), "BatchSetDebug")

@@ -379,6 +379,12 @@ int ReplaySetPriority(pyhanabi_replay_t* replay, const int32_t* indices,
 int ReplayGetPriority(pyhanabi_replay_t* replay, const int32_t* indices, int count,
                       float* priorities, void* stream);
 
+/* Keeps the packed game state resident in the L2 cache between steps (an
+   access-policy window on every launch of this batch; the observation stores
+   stream past it).  max_bytes: 0 = the device's maximum persisting carve-out,
+   negative = off.  *covered (nullable) receives the state bytes held. */
+int BatchSetL2Residency(pyhanabi_batch_t* batch, int64_t max_bytes, int64_t* covered);
+
 /* Test hooks. */
 int BatchSetDebug(pyhanabi_batch_t* batch, int sampler_mode, int generic);
 int BatchDebugDeal(pyhanabi_batch_t* batch, const uint64_t* decks, const int32_t* sizes,
