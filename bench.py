@@ -51,6 +51,9 @@ def parse_args():
   ap.add_argument("--e2e-games", type=int, default=1 << 18)
   ap.add_argument("--cpu-seconds", type=float, default=12.0)
   ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--separate-policy", action="store_true",
+                  help="random policy as its own kernel (BatchSelectAction) instead of the step "
+                       "kernel's fused random-action output (BatchStepEncodeRandom)")
   ap.add_argument("--packed", action="store_true",
                   help="also measure the optional bit-packed observation output (extra key)")
   ap.add_argument("--python-baselines", action="store_true",
@@ -297,9 +300,18 @@ def main():
 
   # pre-bound launches: pointer casts and argument checks happen once, so the
   # Python cost per step stays far below the ~0.25 ms the GPU needs
-  step_encode = batch.bind_step_encode(act, rew, done, obs, mask, cur)
+  bound_step = batch.bind_step_encode(act, rew, done, obs, mask, cur)
+  step_encode = lambda t: bound_step()
   launches_per_step = 2
-  if args.policy == "random":
+  fused_policy = args.policy == "random" and not args.separate_policy
+  if fused_policy:
+    # the uniform-random policy rides in the step kernel: it applies act[i] and leaves
+    # the next random legal move in act[i] (same draw as BatchSelectAction, epsilon >= 1)
+    ph.select_action(None, mask, 1.0, seed=7, step=0, out=act)
+    step_encode = batch.bind_step_encode_random(act, 7, rew, done, obs, mask, cur)
+    select = lambda t: None
+    launches_per_step = 1
+  elif args.policy == "random":
     select = ph.bind_select_action(None, mask, 1.0, seed=7, out=act)
   else:
     # Rainbow actor (agents/rainbow_copy/rainbow_agent.py:36-68,163-172): MLP
@@ -344,7 +356,7 @@ def main():
 
   def one_step(t):
     select(t)
-    step_encode()
+    step_encode(t)
 
   W = max(args.warmup, 3)
   K = args.steps
@@ -365,7 +377,7 @@ def main():
   for t in range(K):
     select(W + t)
     k_ev[t][0].record()
-    step_encode()
+    step_encode(W + t)
     k_ev[t][1].record()
   sharding.reduce_episode_statistics(stats)  # the only collective: 256 B over NCCL (no-op at N=1)
   ev1.record()
@@ -430,6 +442,8 @@ def main():
     Wp = batch.packed_words
     bits = torch.empty((n, Wp), dtype=torch.int32, device=dev)
     step_packed = lambda: batch.step_encode_packed(act, rew, done, bits, mask, cur)
+    if fused_policy:
+      select = ph.bind_select_action(None, mask, 1.0, seed=7, out=act)
     for t in range(W):
       select(10**6 + t); step_packed()
     torch.cuda.synchronize()
@@ -489,7 +503,9 @@ def main():
       "steps": K, "warmup": W, "ms_per_step": elapsed_ms / K, "higher_is_better": True,
       "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
       "config": {"workload": args.workload, "games_per_gpu": n, "obs_dim": D, "num_moves": A,
-                 "policy": ("uniform random legal (BatchSelectAction, epsilon=1)"
+                 "policy": ("uniform random legal, drawn inside the step kernel "
+                            "(BatchStepEncodeRandom)" if fused_policy else
+                            "uniform random legal (BatchSelectAction, epsilon=1)"
                             if args.policy == "random" else
                             "Rainbow C51 MLP %d->512->%dx51 (torch TF32 GEMMs) + BatchSelectAction "
                             "(epsilon=0)" % (D, A) +

@@ -15,6 +15,7 @@
 #include "../../include/pyhanabi.h"
 #include "hb_agents.cuh"
 #include "hb_engine.cuh"
+#include "hb_policy_rng.h"
 #include "hb_spec.h"
 
 namespace hb {
@@ -68,6 +69,11 @@ struct KArgs {
   uint32_t* obs_bits;  // alternative to obs: bit-packed rows of packed_words 32-bit words
   int packed_words;
   uint8_t* mask;
+  // optional fused random policy: after the step, a uniformly random legal move of the
+  // new state (the generator of BatchSelectAction keyed (seed, step, game)); may alias
+  // `actions` (every thread reads its action before it writes the next one)
+  int32_t* random_actions;
+  uint64_t policy_seed, policy_step;
   unsigned long long* stats;
   uint4* hist;  // optional: the 4 non-deal moves before `last`, newest first (BatchEnableHistory)
   int auto_reset;
@@ -357,7 +363,15 @@ __global__ void __launch_bounds__(kBlock, (MODE == kModeStep) ? HB_MIN_CTAS_STEP
     encode_obs(v, a.spec, G, observer, obs_stream, lane, s_spread,
                a.obs_bits ? a.packed_words * 32 : a.spec.obs_size);
   }
-  if (a.mask) pack_mask_stream(mask_stream, a.spec.max_moves, legal_bits(v, G), valid, lane);
+  if (a.mask || a.random_actions) {
+    const uint64_t legal = legal_bits(v, G);
+    if (a.random_actions && valid) {
+      const int n_legal = __popcll(legal);
+      const uint64_t bits = hbp::policy_bits(a.policy_seed, a.policy_step, (uint64_t)g);
+      a.random_actions[g] = n_legal > 0 ? select64(legal, hbp::random_legal_rank(bits, n_legal)) : -1;
+    }
+    if (a.mask) pack_mask_stream(mask_stream, a.spec.max_moves, legal, valid, lane);
+  }
   __syncwarp();
   if (a.obs)
     expand_stream(obs_stream, a.spec.obs_size, a.obs + tile0 * a.obs_pitch, a.obs_pitch, n_valid,
@@ -874,6 +888,29 @@ int BatchStepEncodeScores(pyhanabi_batch_t* h, const int32_t* actions, int32_t* 
   a.actions = actions; a.rewards = rewards; a.dones = dones; a.scores = scores;
   a.obs = obs; a.obs_pitch = row_pitch; a.mask = mask; a.cur_player = cur_player;
   a.auto_reset = auto_reset;
+  HB_CUDA(Launch<hb::kModeStep>(b, a, (cudaStream_t)stream));
+  return 0;
+}
+
+// BatchStepEncodeScores plus a fused uniform-random policy: after the move,
+// actions[i] is overwritten with a uniformly random legal move of game i's new
+// state (-1 when there is none) -- exactly what BatchSelectAction(NULL, ..., epsilon
+// >= 1, seed, step) would choose from the mask this call writes, without the second
+// kernel and without reading the mask back.  `random_actions` may be `actions`
+// itself (in-place rollout loop) or a separate buffer.
+int BatchStepEncodeRandom(pyhanabi_batch_t* h, const int32_t* actions, int32_t* rewards,
+                          uint8_t* dones, int32_t* scores, uint8_t* obs, int64_t row_pitch,
+                          uint8_t* mask, int32_t* cur_player, int auto_reset,
+                          int32_t* random_actions, uint64_t seed, uint64_t step, void* stream) {
+  HB_BATCH(h);
+  if (!actions) return Fail("BatchStepEncodeRandom: actions is null");
+  if (!random_actions) return Fail("BatchStepEncodeRandom: random_actions is null");
+  if (obs && row_pitch < b->spec.obs_size) return Fail("BatchStepEncodeRandom: row_pitch smaller than the observation");
+  hb::KArgs a = BaseArgs(b);
+  a.actions = actions; a.rewards = rewards; a.dones = dones; a.scores = scores;
+  a.obs = obs; a.obs_pitch = row_pitch; a.mask = mask; a.cur_player = cur_player;
+  a.auto_reset = auto_reset;
+  a.random_actions = random_actions; a.policy_seed = seed; a.policy_step = step;
   HB_CUDA(Launch<hb::kModeStep>(b, a, (cudaStream_t)stream));
   return 0;
 }

@@ -16,26 +16,11 @@
 #include <vector>
 
 #include "../../include/pyhanabi.h"
+#include "hb_policy_rng.h"
 
 namespace hbp {
 
 constexpr unsigned kFull = 0xffffffffu;
-
-__host__ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
-  z += 0x9E3779B97F4A7C15ull;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  return z ^ (z >> 31);
-}
-
-// Counter-based policy randomness keyed (seed, step, game): reproducible and
-// independent of launch geometry.  The reference uses Python's `random` and
-// numpy's global RNG (dqn_agent.py:409-412), which cannot be reproduced on a
-// device; only the distribution is matched (uniform over legal moves with
-// probability epsilon).
-__host__ __device__ __forceinline__ uint64_t policy_bits(uint64_t seed, uint64_t step, uint64_t game) {
-  return mix64(mix64(seed ^ (step * 0xD1B54A32D192ED03ull)) ^ (game * 0x8CB92BA72F3D8DD7ull));
-}
 
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
@@ -72,6 +57,73 @@ __global__ void k_select_q(const float* __restrict__ q, const uint8_t* __restric
     for (int a = 0; a < A; ++a) {
       const float val = m[a] != 0 ? row[a] : -CUDART_INF_F;
       if (choice < 0 ? (m[a] != 0) : (val > best)) { best = val; choice = a; }
+    }
+  }
+  actions[g] = choice;
+}
+
+// Position of the k-th (0-based) set bit of x; k < popcount(x).
+__device__ __forceinline__ int kth_set_bit(uint64_t x, int k) {
+  uint32_t w = (uint32_t)x;
+  int pos = 0, c = __popc(w);
+  if (k >= c) { k -= c; w = (uint32_t)(x >> 32); pos = 32; }
+  c = __popc(w & 0xffffu);
+  if (k >= c) { k -= c; w >>= 16; pos += 16; }
+  c = __popc(w & 0xffu);
+  if (k >= c) { k -= c; w >>= 8; pos += 8; }
+  c = __popc(w & 0xfu);
+  if (k >= c) { k -= c; w >>= 4; pos += 4; }
+  c = __popc(w & 0x3u);
+  if (k >= c) { k -= c; w >>= 2; pos += 2; }
+  return pos + ((k >= (int)(w & 1u)) ? 1 : 0);
+}
+
+// Same selection for A <= 64, one warp per tile of 32 games: the tile's 32*A mask
+// bytes are one contiguous range, fetched with coalesced 128-bit loads into shared
+// memory; every lane then folds its row into a 64-bit legal set and picks the k-th
+// member by popcount bisection instead of walking the row.
+__global__ void k_select_q_tile(const float* __restrict__ q, const uint8_t* __restrict__ mask,
+                                int n, int A, float epsilon, uint64_t seed, uint64_t step,
+                                int32_t* __restrict__ actions) {
+  extern __shared__ uint4 s_tile[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t tile0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + warp) * 32;
+  if (tile0 >= n) return;
+  const int n_valid = (n - tile0) < 32 ? (int)(n - tile0) : 32;
+  uint4* mine4 = s_tile + (size_t)warp * 2 * A;  // 32 * A bytes
+  uint8_t* mine = reinterpret_cast<uint8_t*>(mine4);
+  const uint8_t* src = mask + tile0 * A;
+  const int total = n_valid * A;
+  if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    const int quads = total >> 4;
+    const uint4* src4 = reinterpret_cast<const uint4*>(src);
+    for (int k = lane; k < quads; k += 32) mine4[k] = __ldcs(src4 + k);
+    for (int b = (quads << 4) + lane; b < total; b += 32) mine[b] = src[b];
+  } else {
+    for (int b = lane; b < total; b += 32) mine[b] = src[b];
+  }
+  __syncwarp();
+  if (lane >= n_valid) return;
+  const int64_t g = tile0 + lane;
+  const uint8_t* m = mine + lane * A;
+  uint64_t legal = 0;
+  for (int a = 0; a < A; ++a) legal |= (uint64_t)(m[a] != 0) << a;
+  const int n_legal = __popcll(legal);
+  if (n_legal == 0) { actions[g] = -1; return; }
+  const uint64_t bits = policy_bits(seed, step, (uint64_t)g);
+  const float u = (float)(bits >> 40) * (1.0f / 16777216.0f);  // 24-bit uniform in [0,1)
+  int choice = -1;
+  if (u <= epsilon && epsilon > 0.0f) {  // random.random() <= epsilon
+    const int k = (int)(((bits & 0xffffffffull) * (uint64_t)n_legal) >> 32);
+    choice = kth_set_bit(legal, k);
+  } else {
+    // argmax_a(q[a] + legal[a]) with legal in {0, -inf}: first maximal index (tf.argmax)
+    float best = -CUDART_INF_F;
+    const float* row = q + g * A;
+    for (uint64_t rest = legal; rest; rest &= rest - 1) {
+      const int a = __ffsll((long long)rest) - 1;
+      const float val = row[a];
+      if (choice < 0 || val > best) { best = val; choice = a; }
     }
   }
   actions[g] = choice;
@@ -236,8 +288,17 @@ int BatchSelectAction(const float* q_or_logits, int num_atoms, const float* supp
   if (!q_or_logits && epsilon < 1.0f) return PFail("BatchSelectAction: values are required unless epsilon >= 1");
   cudaStream_t s = (cudaStream_t)stream;
   if (num_atoms <= 0 || !q_or_logits) {
-    hbp::k_select_q<<<(n + 255) / 256, 256, 0, s>>>(q_or_logits, mask, n, num_actions,
-                                                   q_or_logits ? epsilon : 2.0f, seed, step, actions);
+    const float eps = q_or_logits ? epsilon : 2.0f;
+    if (num_actions <= 64) {
+      const int warps = 4;
+      const int64_t tiles = ((int64_t)n + 31) / 32;
+      hbp::k_select_q_tile<<<(unsigned)((tiles + warps - 1) / warps), warps * 32,
+                             (size_t)warps * 32 * num_actions, s>>>(q_or_logits, mask, n, num_actions,
+                                                                    eps, seed, step, actions);
+    } else {
+      hbp::k_select_q<<<(n + 255) / 256, 256, 0, s>>>(q_or_logits, mask, n, num_actions, eps, seed,
+                                                     step, actions);
+    }
   } else {
     if (!support) return PFail("BatchSelectAction: support is null");
     const int64_t threads = (int64_t)n * 32;

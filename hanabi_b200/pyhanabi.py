@@ -777,6 +777,46 @@ class HanabiBatch(object):
         self._p(cur_player, torch.int32, n, "int32_t*"), int(bool(auto_reset)), self._stream()),
            "BatchStepEncodeScores")
 
+  def step_encode_random(self, actions, seed, step, rewards=None, dones=None, obs=None, mask=None,
+                         cur_player=None, scores=None, auto_reset=True, random_actions=None):
+    """step_encode with the fused uniform-random policy (BatchStepEncodeRandom): applies
+    `actions`, then writes a uniformly random legal move of every game's new state into
+    `random_actions` (default: in place into `actions`)."""
+    torch = self._torch
+    n = self.num_games
+    optr, pitch = self._obs_ptr(obs)
+    out = actions if random_actions is None else random_actions
+    _check(lib.BatchStepEncodeRandom(
+        self._c, self._p(actions, torch.int32, n, "int32_t*"),
+        self._p(rewards, torch.int32, n, "int32_t*"), self._p(dones, torch.uint8, n, "uint8_t*"),
+        self._p(scores, torch.int32, n, "int32_t*"), optr, pitch,
+        self._p(mask, torch.uint8, n * self.max_moves, "uint8_t*"),
+        self._p(cur_player, torch.int32, n, "int32_t*"), int(bool(auto_reset)),
+        self._p(out, torch.int32, n, "int32_t*"), int(seed) & (2**64 - 1), int(step) & (2**64 - 1),
+        self._stream()), "BatchStepEncodeRandom")
+
+  def bind_step_encode_random(self, actions, seed, rewards=None, dones=None, obs=None, mask=None,
+                              cur_player=None, scores=None, auto_reset=True, stream=None):
+    """Pre-bound in-place variant of step_encode_random for tight loops: run(step)."""
+    torch = self._torch
+    n = self.num_games
+    optr, pitch = self._obs_ptr(obs)
+    act = self._p(actions, torch.int32, n, "int32_t*")
+    head = (self._c, act, self._p(rewards, torch.int32, n, "int32_t*"),
+            self._p(dones, torch.uint8, n, "uint8_t*"), self._p(scores, torch.int32, n, "int32_t*"),
+            optr, pitch, self._p(mask, torch.uint8, n * self.max_moves, "uint8_t*"),
+            self._p(cur_player, torch.int32, n, "int32_t*"), int(bool(auto_reset)), act,
+            int(seed) & (2**64 - 1))
+    tail = (self._stream() if stream is None else ffi.cast("void*", stream.cuda_stream),)
+    fn = lib.BatchStepEncodeRandom
+    keep = (actions, rewards, dones, obs, mask, cur_player, scores)
+
+    def run(step, _head=head, _tail=tail, _fn=fn, _keep=keep):
+      if _fn(*(_head + (step,) + _tail)) != 0:
+        raise RuntimeError("BatchStepEncodeRandom failed: %s" %
+                           encode_ffi_string(lib.BatchLastError()))
+    return run
+
   # -- bit-packed observations (int32 tensors [num_games, packed_words])
   @property
   def packed_words(self):

@@ -241,6 +241,16 @@ int BatchStepEncodeScores(pyhanabi_batch_t* batch, const int32_t* actions,
 /* Bit-packed observations (optional, reported separately from the byte form): row i
  * = BatchPackedObservationWords() uint32 words (16-byte multiple), bit j of the row
  * = observation bit j, padding zero.  obs_bits must be 16-byte aligned. */
+/* BatchStepEncodeScores with a fused uniform-random policy (the reference's
+   agents/random_agent.py for every game at once): after the move, random_actions[i]
+   = a uniformly random legal move of game i's new state, -1 if none; the same draw
+   as BatchSelectAction(NULL, 0, NULL, mask, ..., epsilon >= 1, seed, step).
+   random_actions may alias actions (in-place rollout loop). */
+int BatchStepEncodeRandom(pyhanabi_batch_t* batch, const int32_t* actions, int32_t* rewards,
+                          uint8_t* dones, int32_t* scores, uint8_t* obs, int64_t row_pitch,
+                          uint8_t* mask, int32_t* cur_player, int auto_reset,
+                          int32_t* random_actions, uint64_t seed, uint64_t step, void* stream);
+
 int BatchPackedObservationWords(pyhanabi_batch_t* batch);
 int BatchStepEncodePacked(pyhanabi_batch_t* batch, const int32_t* actions, int32_t* rewards,
                           uint8_t* dones, int32_t* scores, uint32_t* obs_bits, uint8_t* mask,

@@ -108,3 +108,46 @@ def test_c51_target_distribution_fused():
   assert (a_got.cpu().numpy() == a_want).mean() > 0.98
   same = a_got.cpu().numpy() == a_want
   np.testing.assert_allclose(got.cpu().numpy()[same], want[same], rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["full2", "small2", "full4"])
+def test_fused_random_policy_equals_the_select_kernel(name):
+  """BatchStepEncodeRandom leaves in `actions` exactly what BatchSelectAction (epsilon >= 1,
+  same seed/step) picks from the mask of the same call; the rollout it drives is legal."""
+  import torch
+  from hanabi_b200 import pyhanabi as ph
+  from tests import common
+  n = 5000  # ragged last tile
+  params = common.CONFIGS[name]
+  seeds = common.seeds_for(n, base=3)
+  a, b = ph.HanabiBatch(params, n, seeds), ph.HanabiBatch(params, n, seeds)
+  dev = torch.device("cuda:0")
+  D, A = a.obs_size, a.max_moves
+  mk = lambda *shape, dt: torch.zeros(shape, dtype=dt, device=dev)
+  obs_a, obs_b = mk(n, D, dt=torch.uint8), mk(n, D, dt=torch.uint8)
+  mask_a, mask_b = mk(n, A, dt=torch.uint8), mk(n, A, dt=torch.uint8)
+  cur_a, cur_b = mk(n, dt=torch.int32), mk(n, dt=torch.int32)
+  rew_a, rew_b = mk(n, dt=torch.int32), mk(n, dt=torch.int32)
+  done_a, done_b = mk(n, dt=torch.uint8), mk(n, dt=torch.uint8)
+  act_a, act_b = mk(n, dt=torch.int32), mk(n, dt=torch.int32)
+  for x, o, m, c in ((a, obs_a, mask_a, cur_a), (b, obs_b, mask_b, cur_b)):
+    x.reset()
+    x.observe(o, m, c)
+  ph.select_action(None, mask_a, 1.0, seed=11, step=0, out=act_a)
+  act_b.copy_(act_a)
+  run = a.bind_step_encode_random(act_a, 11, rew_a, done_a, obs_a, mask_a, cur_a)
+  for t in range(1, 40):
+    run(t)                                             # fused: step + next action (in place)
+    b.step_encode(act_b, rew_b, done_b, obs_b, mask_b, cur_b)
+    ph.select_action(None, mask_b, 1.0, seed=11, step=t, out=act_b)
+    assert torch.equal(act_a, act_b), "actions differ at step %d" % t
+    assert torch.equal(obs_a, obs_b) and torch.equal(mask_a, mask_b)
+    assert torch.equal(rew_a, rew_b) and torch.equal(done_a, done_b)
+    legal = mask_a.gather(1, act_a.long().clamp(min=0).view(-1, 1)).view(-1)
+    assert bool(((legal == 1) | (act_a < 0)).all())
+  # separate output buffer: `actions` stays untouched
+  nxt = mk(n, dt=torch.int32)
+  before = act_a.clone()
+  a.step_encode_random(act_a, 11, 99, rew_a, done_a, obs_a, mask_a, cur_a, random_actions=nxt)
+  assert torch.equal(act_a, before)
+  assert torch.equal(nxt, ph.select_action(None, mask_a, 1.0, seed=11, step=99))
