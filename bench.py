@@ -54,6 +54,10 @@ def parse_args():
   ap.add_argument("--separate-policy", action="store_true",
                   help="random policy as its own kernel (BatchSelectAction) instead of the step "
                        "kernel's fused random-action output (BatchStepEncodeRandom)")
+  ap.add_argument("--shards", type=int, default=2,
+                  help="random policy only: split each GPU's games into this many independent "
+                       "batches on their own CUDA streams, so that one launch's last, partly "
+                       "filled wave of CTAs overlaps the other's body (1 = one launch per step)")
   ap.add_argument("--packed", action="store_true",
                   help="also measure the optional bit-packed observation output (extra key)")
   ap.add_argument("--python-baselines", action="store_true",
@@ -285,32 +289,55 @@ def main():
   n = args.games
   from hanabi_b200 import sharding
   seeds = np.asarray(sharding.shard_seeds(1, world * n, rank, world), np.int32)  # 1 + global index
-  batch = ph.HanabiBatch(params, n, seeds, device=local_rank)
-  D, A = batch.obs_size, batch.max_moves
-  obs = torch.empty((n, D), dtype=torch.uint8, device=dev)
-  mask = torch.empty((n, A), dtype=torch.uint8, device=dev)
-  cur = torch.empty(n, dtype=torch.int32, device=dev)
-  rew = torch.empty(n, dtype=torch.int32, device=dev)
-  done = torch.empty(n, dtype=torch.uint8, device=dev)
-  act = torch.empty(n, dtype=torch.int32, device=dev)
+  fused_policy = args.policy == "random" and not args.separate_policy
+  S = max(1, args.shards) if fused_policy else 1
+  while n % (S * 32):
+    S -= 1
   stats = torch.zeros(32, dtype=torch.int64, device=dev)
-  batch.set_stats_buffer(stats)
-  batch.reset()
-  batch.observe(obs, mask, cur)
+
+  def make_shard(lo, hi):
+    m = hi - lo
+    b = ph.HanabiBatch(params, m, seeds[lo:hi], device=local_rank)
+    t = dict(obs=torch.empty((m, b.obs_size), dtype=torch.uint8, device=dev),
+             mask=torch.empty((m, b.max_moves), dtype=torch.uint8, device=dev),
+             cur=torch.empty(m, dtype=torch.int32, device=dev),
+             rew=torch.empty(m, dtype=torch.int32, device=dev),
+             done=torch.empty(m, dtype=torch.uint8, device=dev),
+             act=torch.empty(m, dtype=torch.int32, device=dev))
+    b.set_stats_buffer(stats)
+    b.reset()
+    b.observe(t["obs"], t["mask"], t["cur"])
+    return b, t
+
+  batch, T0 = make_shard(0, n // S)
+  obs, mask, cur, rew, done, act = (T0[k] for k in ("obs", "mask", "cur", "rew", "done", "act"))
+  D, A = batch.obs_size, batch.max_moves
 
   # pre-bound launches: pointer casts and argument checks happen once, so the
   # Python cost per step stays far below the ~0.25 ms the GPU needs
   bound_step = batch.bind_step_encode(act, rew, done, obs, mask, cur)
   step_encode = lambda t: bound_step()
   launches_per_step = 2
-  fused_policy = args.policy == "random" and not args.separate_policy
   if fused_policy:
     # the uniform-random policy rides in the step kernel: it applies act[i] and leaves
-    # the next random legal move in act[i] (same draw as BatchSelectAction, epsilon >= 1)
-    ph.select_action(None, mask, 1.0, seed=7, step=0, out=act)
-    step_encode = batch.bind_step_encode_random(act, 7, rew, done, obs, mask, cur)
+    # the next random legal move in act[i] (same draw as BatchSelectAction, epsilon >= 1).
+    # S independent shards, each on its own stream: consecutive steps of one shard are
+    # ordered by its stream, different shards overlap freely.
+    shard_list = [(batch, T0)] + [make_shard(i * (n // S), (i + 1) * (n // S)) for i in range(1, S)]
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(device=dev) for _ in range(S)] if S > 1 else [torch.cuda.current_stream()]
+    runs = []
+    for (b_i, t_i), st in zip(shard_list, streams):
+      ph.select_action(None, t_i["mask"], 1.0, seed=7, step=0, out=t_i["act"])
+      runs.append(b_i.bind_step_encode_random(t_i["act"], 7, t_i["rew"], t_i["done"], t_i["obs"],
+                                              t_i["mask"], t_i["cur"], stream=st))
+    torch.cuda.synchronize()
+
+    def step_encode(t):
+      for r in runs:
+        r(t)
     select = lambda t: None
-    launches_per_step = 1
+    launches_per_step = S
   elif args.policy == "random":
     select = ph.bind_select_action(None, mask, 1.0, seed=7, out=act)
   else:
@@ -373,18 +400,33 @@ def main():
   k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
           for _ in range(K)]
   sampler.start()
+  main_stream = torch.cuda.current_stream()
   ev0.record()
-  for t in range(K):
-    select(W + t)
-    k_ev[t][0].record()
-    step_encode(W + t)
-    k_ev[t][1].record()
+  if fused_policy:
+    # one kind of launch in the timed region: its average duration is elapsed / launches,
+    # no per-launch events needed (they would only put gaps between the kernels)
+    if S > 1:
+      for st in streams:
+        st.wait_event(ev0)
+    for t in range(K):
+      step_encode(W + t)
+    if S > 1:
+      for st in streams:
+        main_stream.wait_stream(st)
+  else:
+    for t in range(K):
+      select(W + t)
+      k_ev[t][0].record()
+      step_encode(W + t)
+      k_ev[t][1].record()
   sharding.reduce_episode_statistics(stats)  # the only collective: 256 B over NCCL (no-op at N=1)
   ev1.record()
   torch.cuda.synchronize()
   clocks = sampler.stop()
   elapsed_ms = ev0.elapsed_time(ev1)
-  kernel_ms = sum(a.elapsed_time(b) for a, b in k_ev) / K
+  # fused policy: S concurrent launches cover one step of all games, so the step time is
+  # the launch time of the kernel over n games
+  kernel_ms = elapsed_ms / K if fused_policy else sum(a.elapsed_time(b) for a, b in k_ev) / K
   if dist:
     tmax = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
     dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -440,7 +482,8 @@ def main():
   packed = None
   if args.packed:
     Wp = batch.packed_words
-    bits = torch.empty((n, Wp), dtype=torch.int32, device=dev)
+    n_p = batch.num_games  # the first shard when the games are split
+    bits = torch.empty((n_p, Wp), dtype=torch.int32, device=dev)
     step_packed = lambda: batch.step_encode_packed(act, rew, done, bits, mask, cur)
     if fused_policy:
       select = ph.bind_select_action(None, mask, 1.0, seed=7, out=act)
@@ -455,7 +498,8 @@ def main():
     p1.record()
     torch.cuda.synchronize()
     pms = p0.elapsed_time(p1) / Kp
-    packed = {"value": world * n / (pms * 1e-3), "unit": "env-steps/s", "ms_per_step": pms,
+    packed = {"value": world * n_p / (pms * 1e-3), "unit": "env-steps/s", "ms_per_step": pms,
+              "games": n_p,
               "obs_bytes_per_game": 4 * Wp, "note": "device-resident, bit-packed observation rows"}
     if args.e2e_steps > 0:
       hb2 = ph.HanabiBatch(params, ne, seeds[:ne], device=local_rank)
@@ -513,10 +557,13 @@ def main():
                              if args.policy == "adhoc" else "")),
                  "auto_reset": True, "seeds": "1 + global game index",
                  "l2": "outputs per step (%.0f MB) exceed the 126 MB L2" % (n * (D + A) / 1e6),
-                 "parallelism": "games sharded over %d GPU(s), no step-path collective" % world},
+                 "parallelism": "games sharded over %d GPU(s), no step-path collective" % world +
+                                ("; per GPU %d independent shards of %d games on their own streams"
+                                 % (S, n // S) if S > 1 else "")},
       "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                    "frac": achieved / peak, "traffic": traffic, "kernel": "k_main<step>",
-                   "kernel_ms": kernel_ms, "algorithmic_bytes_per_env_step": algo,
+                   "kernel_ms": kernel_ms, "launches_per_step": launches_per_step,
+                   "algorithmic_bytes_per_env_step": algo,
                    "peak_source": peak_src},
       "e2e": e2e,
       "gpu_launches": launches_per_step * K,
