@@ -54,6 +54,8 @@ def parse_args():
   ap.add_argument("--separate-policy", action="store_true",
                   help="random policy as its own kernel (BatchSelectAction) instead of the step "
                        "kernel's fused random-action output (BatchStepEncodeRandom)")
+  ap.add_argument("--mlp-dtype", choices=["fp32", "tf32", "bf16", "fp16"], default="tf32",
+                  help="element type of the Rainbow policy's two library GEMMs (accumulation is fp32)")
   ap.add_argument("--shards", type=int, default=2,
                   help="random policy only: split each GPU's games into this many independent "
                        "batches on their own CUDA streams, so that one launch's last, partly "
@@ -342,26 +344,39 @@ def main():
     select = ph.bind_select_action(None, mask, 1.0, seed=7, out=act)
   else:
     # Rainbow actor (agents/rainbow_copy/rainbow_agent.py:36-68,163-172): MLP
-    # obs_dim -> 512 -> A x 51 with fixed random weights; the two GEMMs are library
-    # calls (cuBLAS through torch, TF32), softmax . support, mask and argmax are ours.
+    # obs_dim -> 512 -> A x 51 with fixed random weights.  The step kernel writes
+    # bit-packed observation rows, BatchExpandPacked turns them into the first GEMM's
+    # input (0/1 in the GEMM's element type, K zero-padded to a multiple of 32), the two
+    # GEMMs are library calls (cuBLASLt through torch; bias + ReLU in the first one's
+    # epilogue), and BatchSelectActionC51 reads the N-padded logits in place:
+    # softmax . support, legal mask, argmax.
     torch.manual_seed(0)
-    torch.backends.cuda.matmul.allow_tf32 = True
+    mlp = args.mlp_dtype
+    tdt = {"fp32": torch.float32, "tf32": torch.float32, "bf16": torch.bfloat16,
+           "fp16": torch.float16}[mlp]
+    torch.backends.cuda.matmul.allow_tf32 = mlp == "tf32"
     atoms = 51
-    w1 = torch.randn(D, 512, device=dev) / D ** 0.5
-    b1 = torch.zeros(512, device=dev)
-    w2 = torch.randn(512, A * atoms, device=dev) / 512 ** 0.5
-    b2 = torch.zeros(A * atoms, device=dev)
+    Kp, Np = (D + 31) // 32 * 32, (A * atoms + 63) // 64 * 64
+    w1 = torch.zeros(Kp, 512, device=dev)
+    w1[:D] = torch.randn(D, 512, device=dev) / D ** 0.5
+    w2 = torch.zeros(512, Np, device=dev)
+    w2[:, :A * atoms] = torch.randn(512, A * atoms, device=dev) / 512 ** 0.5
+    w1, w2 = w1.to(tdt), w2.to(tdt)
+    b1 = torch.zeros(512, device=dev, dtype=tdt)
+    b2 = torch.zeros(Np, device=dev, dtype=tdt)
     support = torch.linspace(-25.0, 25.0, atoms, device=dev)
-    x = torch.empty((n, D), dtype=torch.float32, device=dev)
-    h = torch.empty((n, 512), dtype=torch.float32, device=dev)
-    logits = torch.empty((n, A * atoms), dtype=torch.float32, device=dev)
-    greedy = ph.bind_select_action(logits.view(n, A, atoms), mask, 0.0, seed=7, out=act,
-                                   support=support)
+    bits = torch.empty((n, batch.packed_words), dtype=torch.int32, device=dev)
+    x = torch.empty((n, Kp), dtype=tdt, device=dev)
+    logits = torch.empty((n, Np), dtype=tdt, device=dev)
+    batch.observe_packed(bits)
+    expand = ph.bind_expand_packed(bits, D, x)
+    greedy = ph.bind_select_action_c51(logits, atoms, mask, 0.0, seed=7, out=act, support=support)
+    step_encode = lambda t: batch.step_encode_packed(act, rew, done, bits, mask, cur)
+    launches_per_step = 3  # ours: step, expand, select (+ 2 library GEMMs)
 
     def rainbow(t):
-      x.copy_(obs)
-      torch.addmm(b1, x, w1, out=h)
-      h.relu_()
+      expand()
+      h = torch._addmm_activation(b1, x, w1)  # relu(x @ w1 + b1), one cuBLASLt call
       torch.addmm(b2, h, w2, out=logits)
       greedy(t)
 
@@ -373,9 +388,10 @@ def main():
       batch.enable_history()
       batch.reset()
       batch.observe(obs, mask, cur)
+      batch.observe_packed(bits)
       agent_state = torch.zeros((n, 1), dtype=torch.int32, device=dev)
       seat_mask = sum(1 << s for s in range(1, batch.num_players))
-      launches_per_step = 3
+      launches_per_step = 4
 
       def select(t):
         rainbow(t)
@@ -551,8 +567,9 @@ def main():
                             "(BatchStepEncodeRandom)" if fused_policy else
                             "uniform random legal (BatchSelectAction, epsilon=1)"
                             if args.policy == "random" else
-                            "Rainbow C51 MLP %d->512->%dx51 (torch TF32 GEMMs) + BatchSelectAction "
-                            "(epsilon=0)" % (D, A) +
+                            "Rainbow C51 MLP %d->512->%dx51 (cuBLASLt %s GEMMs via torch) on "
+                            "BatchExpandPacked input + BatchSelectActionC51 (epsilon=0)"
+                            % (D, A, args.mlp_dtype) +
                             ("; seats 1.. = batched RuleBasedAgent (BatchAgentAct)"
                              if args.policy == "adhoc" else "")),
                  "auto_reset": True, "seeds": "1 + global game index",

@@ -8,11 +8,14 @@
 //                              (agents/rainbow_copy/rainbow_agent.py:181-213)
 // fp32 throughout; no tensor cores (there is no dense contraction here).
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <math_constants.h>
 #include <stdint.h>
 
 #include <string>
 #include <thread>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/pyhanabi.h"
@@ -129,8 +132,17 @@ __global__ void k_select_q_tile(const float* __restrict__ q, const uint8_t* __re
   actions[g] = choice;
 }
 
+// Logit element types of the C51 head (BatchSelectActionC51 `dtype`).
+template <class T> __device__ __forceinline__ float to_f32(T v);
+template <> __device__ __forceinline__ float to_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float to_f32<__half>(__half v) { return __half2float(v); }
+
 // C51 logits given: one warp per game.  q[a] = sum_i support[i] * softmax(logits[a,:])[i].
-__global__ void k_select_c51(const float* __restrict__ logits, const float* __restrict__ support,
+// Game g's logits start at logits + g * row_pitch (elements), action a at + a * atoms.
+template <class T>
+__global__ void k_select_c51(const T* __restrict__ logits, int64_t row_pitch,
+                             const float* __restrict__ support,
                              const uint8_t* __restrict__ mask, int n, int A, int atoms,
                              float epsilon, uint64_t seed, uint64_t step,
                              int32_t* __restrict__ actions, float* __restrict__ q_out) {
@@ -147,23 +159,37 @@ __global__ void k_select_c51(const float* __restrict__ logits, const float* __re
   const bool explore = (u <= epsilon && epsilon > 0.0f);
   int choice = -1;
   if (explore && q_out == nullptr) {
-    int k = (int)(((bits & 0xffffffffull) * (uint64_t)n_legal) >> 32);
+    int k = random_legal_rank(bits, n_legal);
     for (int a = 0; a < A; ++a)
       if (m[a] != 0 && k-- == 0) { choice = a; break; }
   } else {
     float best = -CUDART_INF_F;
+    const T* base = logits + (int64_t)g * row_pitch;
+    const bool two = atoms <= 64;  // the usual 51 atoms: every logit is read exactly once
+    const float s0 = lane < atoms ? support[lane] : 0.f;
+    const float s1 = two && lane + 32 < atoms ? support[lane + 32] : 0.f;
     for (int a = 0; a < A; ++a) {
       const bool legal = m[a] != 0;
       if (!legal && q_out == nullptr) continue;  // warp-uniform: skip the read entirely
-      const float* row = logits + ((int64_t)g * A + a) * atoms;
-      float mx = -CUDART_INF_F;
-      for (int i = lane; i < atoms; i += 32) mx = fmaxf(mx, row[i]);
-      mx = warp_max(mx);
+      const T* row = base + (int64_t)a * atoms;
       float se = 0.f, sw = 0.f;
-      for (int i = lane; i < atoms; i += 32) {
-        const float e = expf(row[i] - mx);
-        se += e;
-        sw += e * support[i];
+      if (two) {
+        const float v0 = lane < atoms ? to_f32<T>(row[lane]) : -CUDART_INF_F;
+        const float v1 = lane + 32 < atoms ? to_f32<T>(row[lane + 32]) : -CUDART_INF_F;
+        const float mx = warp_max(fmaxf(v0, v1));
+        const float e0 = lane < atoms ? expf(v0 - mx) : 0.f;
+        const float e1 = lane + 32 < atoms ? expf(v1 - mx) : 0.f;
+        se = e0 + e1;
+        sw = e0 * s0 + e1 * s1;
+      } else {
+        float mx = -CUDART_INF_F;
+        for (int i = lane; i < atoms; i += 32) mx = fmaxf(mx, to_f32<T>(row[i]));
+        mx = warp_max(mx);
+        for (int i = lane; i < atoms; i += 32) {
+          const float e = expf(to_f32<T>(row[i]) - mx);
+          se += e;
+          sw += e * support[i];
+        }
       }
       se = warp_sum(se);
       sw = warp_sum(sw);
@@ -172,13 +198,209 @@ __global__ void k_select_c51(const float* __restrict__ logits, const float* __re
       if (legal && (choice < 0 || qa > best)) { best = qa; choice = a; }
     }
     if (explore) {
-      int k = (int)(((bits & 0xffffffffull) * (uint64_t)n_legal) >> 32);
+      int k = random_legal_rank(bits, n_legal);
       choice = -1;
       for (int a = 0; a < A; ++a)
         if (m[a] != 0 && k-- == 0) { choice = a; break; }
     }
   }
   if (lane == 0) actions[g] = choice;
+}
+
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// Two consecutive 16-bit logits from one 32-bit shared-memory word.
+template <class T> __device__ __forceinline__ float2 unpack2(uint32_t w);
+template <> __device__ __forceinline__ float2 unpack2<__nv_bfloat16>(uint32_t w) {
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+template <> __device__ __forceinline__ float2 unpack2<__half>(uint32_t w) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&w));
+}
+
+// sum_i e_i and sum_i e_i * support_i over one action's atoms, e_i = 2^(v_i * log2e + nm),
+// from the staged row.  s_sup[0..63] = support, s_sup[64..127] = support shifted by one.
+template <class T>
+__device__ __forceinline__ void action_sums(const T* row, int start, int atoms, float nm,
+                                            const float* s_sup, float& se, float& sw) {
+  constexpr float kL2e = 1.4426950408889634f;
+  se = 0.f; sw = 0.f;
+  if (sizeof(T) == 4) {
+    const float* r = reinterpret_cast<const float*>(row) + start;
+#pragma unroll 4
+    for (int i = 0; i < atoms; ++i) {
+      const float e = ex2_fast(fmaf(r[i], kL2e, nm));
+      se += e;
+      sw = fmaf(e, s_sup[i], sw);
+    }
+  } else {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(row) + (start >> 1);
+    const int odd = start & 1;
+    if (odd) {  // the action starts in the high half of its first word
+      const float e = ex2_fast(fmaf(unpack2<typename std::conditional<sizeof(T) == 4, __half, T>::type>(w[0]).y, kL2e, nm));
+      se = e;
+      sw = e * s_sup[0];
+    }
+    w += odd;
+    const float2* sp = reinterpret_cast<const float2*>(s_sup + (odd ? 64 : 0));
+    const int pairs = (atoms - odd) >> 1;
+#pragma unroll 5
+    for (int j = 0; j < pairs; ++j) {
+      const float2 v = unpack2<typename std::conditional<sizeof(T) == 4, __half, T>::type>(w[j]);
+      const float2 sv = sp[j];
+      const float e0 = ex2_fast(fmaf(v.x, kL2e, nm)), e1 = ex2_fast(fmaf(v.y, kL2e, nm));
+      se += e0 + e1;
+      sw = fmaf(e0, sv.x, sw);
+      sw = fmaf(e1, sv.y, sw);
+    }
+    if ((atoms - odd) & 1) {  // one more element in the low half of the next word
+      const float e = ex2_fast(fmaf(unpack2<typename std::conditional<sizeof(T) == 4, __half, T>::type>(w[pairs]).x, kL2e, nm));
+      se += e;
+      sw = fmaf(e, s_sup[atoms - 1], sw);  // `atoms` = this call's length
+    }
+  }
+}
+
+// The same selection with the game's whole logits row staged in shared memory: the
+// warp fetches the row with coalesced 128-bit loads (all in flight at once), then lane
+// a owns action a -- softmax . support over its atoms without any shuffle -- and a
+// final warp reduction takes the first maximal legal action.  exp(v - M) uses the row
+// maximum M (>= every action's own maximum: no overflow); an action whose terms all
+// underflow against M is redone against its own maximum.
+// Needs 16-byte aligned rows (base and pitch) and atoms <= 63;
+// smem: 128 floats + warps * row_smem_bytes.
+template <class T>
+__global__ void k_select_c51_rows(const T* __restrict__ logits, int64_t row_pitch,
+                                  const float* __restrict__ support,
+                                  const uint8_t* __restrict__ mask, int n, int A, int atoms,
+                                  float epsilon, uint64_t seed, uint64_t step,
+                                  int32_t* __restrict__ actions, float* __restrict__ q_out,
+                                  int row_smem_bytes) {
+  extern __shared__ uint4 s_rows[];
+  float* s_sup = reinterpret_cast<float*>(s_rows);  // [0,64): support, [64,128): shifted by one
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x < 128) {
+    const int i = threadIdx.x & 63, sh = threadIdx.x >> 6;
+    s_sup[threadIdx.x] = i + sh < atoms ? support[i + sh] : 0.f;
+  }
+  __syncthreads();
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (g >= n) return;
+  T* row = reinterpret_cast<T*>(reinterpret_cast<uint8_t*>(s_rows) + 512 + (size_t)warp * row_smem_bytes);
+  const T* src = logits + (int64_t)g * row_pitch;
+  const int len = A * atoms;
+  constexpr int kPer = 16 / (int)sizeof(T);
+  const int full = len / kPer;
+  float mx = -CUDART_INF_F;
+  for (int k = lane; k < full; k += 32) {
+    const uint4 v = __ldcs(reinterpret_cast<const uint4*>(src) + k);
+    reinterpret_cast<uint4*>(row)[k] = v;
+    if (sizeof(T) == 4) {
+      mx = fmaxf(fmaxf(mx, __uint_as_float(v.x)), fmaxf(__uint_as_float(v.y), fmaxf(__uint_as_float(v.z), __uint_as_float(v.w))));
+    } else {
+      typedef typename std::conditional<sizeof(T) == 4, __half, T>::type T16;
+      const float2 a = unpack2<T16>(v.x), b = unpack2<T16>(v.y), c = unpack2<T16>(v.z), d = unpack2<T16>(v.w);
+      mx = fmaxf(fmaxf(fmaxf(mx, a.x), fmaxf(a.y, b.x)), fmaxf(fmaxf(b.y, c.x), fmaxf(c.y, fmaxf(d.x, d.y))));
+    }
+  }
+  for (int i = full * kPer + lane; i < len; i += 32) {
+    const T v = src[i];
+    row[i] = v;
+    mx = fmaxf(mx, to_f32<T>(v));
+  }
+  mx = warp_max(mx);
+  __syncwarp();
+  const uint8_t* m = mask + (int64_t)g * A;
+  const uint64_t bits = policy_bits(seed, step, (uint64_t)g);
+  const float u = (float)(bits >> 40) * (1.0f / 16777216.0f);
+  const bool explore = (u <= epsilon && epsilon > 0.0f);
+  const float nm = -mx * 1.4426950408889634f;
+  float best = -CUDART_INF_F;
+  int choice = -1, n_legal = 0;
+  // (measured alternative: compacting the legal actions and cutting each into three
+  // atom chunks over 30 lanes is slower, 287 vs 257 us at 2^18 games -- the second,
+  // sparsely filled round costs more than the idle lanes here)
+  for (int a = lane; a < A; a += 32) {
+    const bool legal = m[a] != 0;
+    n_legal += legal;
+    if (!legal && q_out == nullptr) continue;
+    float se, sw;
+    action_sums<T>(row, a * atoms, atoms, nm, s_sup, se, sw);
+    if (!(se > 0.f)) {  // everything underflowed against the row maximum
+      float am = -CUDART_INF_F;
+      for (int i = 0; i < atoms; ++i) am = fmaxf(am, to_f32<T>(row[a * atoms + i]));
+      action_sums<T>(row, a * atoms, atoms, -am * 1.4426950408889634f, s_sup, se, sw);
+    }
+    const float qa = sw / se;
+    if (q_out) q_out[(int64_t)g * A + a] = qa;
+    if (legal && (choice < 0 || qa > best)) { best = qa; choice = a; }
+  }
+  n_legal = __reduce_add_sync(kFull, n_legal);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float oq = __shfl_xor_sync(kFull, best, o);
+    const int oa = __shfl_xor_sync(kFull, choice, o);
+    if (oa >= 0 && (choice < 0 || oq > best || (oq == best && oa < choice))) { best = oq; choice = oa; }
+  }
+  if (n_legal == 0) choice = -1;
+  else if (explore) {
+    // uniform legal move: the k-th legal action in ascending order
+    uint64_t legal_set = 0;
+    for (int a0 = 0; a0 < A; a0 += 32) {
+      const int a = a0 + lane;
+      legal_set |= (uint64_t)__ballot_sync(kFull, a < A && m[a] != 0) << a0;
+    }
+    choice = kth_set_bit(legal_set, random_legal_rank(bits, n_legal));
+  }
+  if (lane == 0) actions[g] = choice;
+}
+
+// Bit-packed observation rows -> rows of 0/1 in a GEMM input type, K padded with
+// zeros up to row_pitch.  One thread expands 8 bits into 8 elements.
+template <class T> struct Vec8;
+template <> struct Vec8<float> {
+  static __device__ __forceinline__ void store(float* p, uint32_t b) {
+    float4 lo, hi;
+    lo.x = (float)(b & 1u); lo.y = (float)((b >> 1) & 1u); lo.z = (float)((b >> 2) & 1u); lo.w = (float)((b >> 3) & 1u);
+    hi.x = (float)((b >> 4) & 1u); hi.y = (float)((b >> 5) & 1u); hi.z = (float)((b >> 6) & 1u); hi.w = (float)((b >> 7) & 1u);
+    reinterpret_cast<float4*>(p)[0] = lo;
+    reinterpret_cast<float4*>(p)[1] = hi;
+  }
+};
+template <uint32_t ONE> __device__ __forceinline__ void store8x16(void* p, uint32_t b) {
+  // two 16-bit elements per word: bit i -> ONE in the low half, bit i+1 -> ONE in the high half
+  uint4 v;
+  v.x = ((b & 1u) * ONE) | (((b >> 1) & 1u) * (ONE << 16));
+  v.y = (((b >> 2) & 1u) * ONE) | (((b >> 3) & 1u) * (ONE << 16));
+  v.z = (((b >> 4) & 1u) * ONE) | (((b >> 5) & 1u) * (ONE << 16));
+  v.w = (((b >> 6) & 1u) * ONE) | (((b >> 7) & 1u) * (ONE << 16));
+  *reinterpret_cast<uint4*>(p) = v;
+}
+template <> struct Vec8<__nv_bfloat16> {
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, uint32_t b) { store8x16<0x3f80u>(p, b); }
+};
+template <> struct Vec8<__half> {
+  static __device__ __forceinline__ void store(__half* p, uint32_t b) { store8x16<0x3c00u>(p, b); }
+};
+
+template <class T>
+__global__ void k_expand_bits(const uint32_t* __restrict__ bits, int packed_words, int obs_size,
+                              int64_t n, T* __restrict__ out, int64_t row_pitch) {
+  const int groups = (int)(row_pitch >> 3);  // row_pitch is a multiple of 8
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * groups) return;
+  const int64_t g = idx / groups;
+  const int j = (int)(idx - g * groups);
+  uint32_t b = 0;
+  if (8 * j < obs_size) {
+    b = (bits[g * packed_words + (j >> 2)] >> (8 * (j & 3))) & 0xffu;
+    const int rem = obs_size - 8 * j;
+    if (rem < 8) b &= (1u << rem) - 1u;
+  }
+  Vec8<T>::store(out + g * row_pitch + 8 * j, b);
 }
 
 // project_distribution, one warp per batch row, op for op in fp32:
@@ -278,6 +500,28 @@ namespace {
 int PFail(const std::string& s) { return HbFail(s); }
 }  // namespace
 
+namespace {
+// Row-staged kernel when the rows are 16-byte aligned and fit the default dynamic
+// shared memory (8 warps per CTA), else the streaming one.
+template <class T>
+cudaError_t LaunchSelectC51(const T* logits, int64_t row_pitch, const float* support, const uint8_t* mask,
+                            int n, int A, int atoms, float epsilon, uint64_t seed, uint64_t step,
+                            int32_t* actions, cudaStream_t s) {
+  const unsigned grid = (unsigned)(((int64_t)n * 32 + 255) / 256);
+  const size_t row_bytes = (((size_t)A * atoms * sizeof(T)) + 15) / 16 * 16;
+  const bool aligned = (reinterpret_cast<uintptr_t>(logits) & 15) == 0 && ((row_pitch * sizeof(T)) & 15) == 0;
+  if (aligned && atoms <= 63 && 512 + 8 * row_bytes <= 48 * 1024) {
+    hbp::k_select_c51_rows<T><<<grid, 256, 512 + 8 * row_bytes, s>>>(logits, row_pitch, support, mask, n, A, atoms,
+                                                               epsilon, seed, step, actions, nullptr,
+                                                               (int)row_bytes);
+  } else {
+    hbp::k_select_c51<T><<<grid, 256, 0, s>>>(logits, row_pitch, support, mask, n, A, atoms, epsilon, seed,
+                                              step, actions, nullptr);
+  }
+  return cudaGetLastError();
+}
+}  // namespace
+
 extern "C" {
 
 int BatchSelectAction(const float* q_or_logits, int num_atoms, const float* support,
@@ -302,11 +546,58 @@ int BatchSelectAction(const float* q_or_logits, int num_atoms, const float* supp
   } else {
     if (!support) return PFail("BatchSelectAction: support is null");
     const int64_t threads = (int64_t)n * 32;
-    hbp::k_select_c51<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(
-        q_or_logits, support, mask, n, num_actions, num_atoms, epsilon, seed, step, actions, nullptr);
+    hbp::k_select_c51<float><<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(
+        q_or_logits, (int64_t)num_actions * num_atoms, support, mask, n, num_actions, num_atoms,
+        epsilon, seed, step, actions, nullptr);
   }
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : PFail(std::string("BatchSelectAction: ") + cudaGetErrorString(e));
+}
+
+// BatchSelectAction for a C51 head whose logits come straight out of a GEMM: element
+// type float32 (dtype 0), bfloat16 (1) or float16 (2), and a row pitch (elements
+// between two games' rows, >= num_actions * num_atoms) so that an N-padded GEMM output
+// can be consumed in place.
+int BatchSelectActionC51(const void* logits, int dtype, int64_t row_pitch, int num_atoms,
+                         const float* support, const uint8_t* mask, int n, int num_actions,
+                         float epsilon, uint64_t seed, uint64_t step, int32_t* actions,
+                         void* stream) {
+  if (!logits || !support || !mask || !actions) return PFail("BatchSelectActionC51: null argument");
+  if (n <= 0 || num_actions <= 0 || num_atoms <= 0) return PFail("BatchSelectActionC51: bad sizes");
+  if (row_pitch < (int64_t)num_actions * num_atoms) return PFail("BatchSelectActionC51: row_pitch too small");
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t e = cudaSuccess;
+  switch (dtype) {
+    case 0: e = LaunchSelectC51(static_cast<const float*>(logits), row_pitch, support, mask, n, num_actions, num_atoms, epsilon, seed, step, actions, s); break;
+    case 1: e = LaunchSelectC51(static_cast<const __nv_bfloat16*>(logits), row_pitch, support, mask, n, num_actions, num_atoms, epsilon, seed, step, actions, s); break;
+    case 2: e = LaunchSelectC51(static_cast<const __half*>(logits), row_pitch, support, mask, n, num_actions, num_atoms, epsilon, seed, step, actions, s); break;
+    default:
+      return PFail("BatchSelectActionC51: dtype must be 0 (float32), 1 (bfloat16) or 2 (float16)");
+  }
+  return e == cudaSuccess ? 0 : PFail(std::string("BatchSelectActionC51: ") + cudaGetErrorString(e));
+}
+
+// Bit-packed observation rows (BatchStepEncodePacked / BatchObservePacked) -> the
+// network's input matrix: out[i][j] = bit j of row i as 0/1 in float32 / bfloat16 /
+// float16 (dtype as above), columns [obs_size, row_pitch) zero, so that K can be padded
+// to the GEMM's alignment.  row_pitch must be a multiple of 8 and `out` 16-byte aligned.
+int BatchExpandPacked(const uint32_t* obs_bits, int packed_words, int obs_size, int n, void* out,
+                      int64_t row_pitch, int dtype, void* stream) {
+  if (!obs_bits || !out) return PFail("BatchExpandPacked: null argument");
+  if (n <= 0 || obs_size <= 0 || packed_words * 32 < obs_size) return PFail("BatchExpandPacked: bad sizes");
+  if (row_pitch < obs_size || (row_pitch & 7)) return PFail("BatchExpandPacked: row_pitch must be >= obs_size and a multiple of 8");
+  if (reinterpret_cast<uintptr_t>(out) & 15) return PFail("BatchExpandPacked: out must be 16-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t threads = (int64_t)n * (row_pitch >> 3);
+  const unsigned grid = (unsigned)((threads + 255) / 256);
+  switch (dtype) {
+    case 0: hbp::k_expand_bits<float><<<grid, 256, 0, s>>>(obs_bits, packed_words, obs_size, n, static_cast<float*>(out), row_pitch); break;
+    case 1: hbp::k_expand_bits<__nv_bfloat16><<<grid, 256, 0, s>>>(obs_bits, packed_words, obs_size, n, static_cast<__nv_bfloat16*>(out), row_pitch); break;
+    case 2: hbp::k_expand_bits<__half><<<grid, 256, 0, s>>>(obs_bits, packed_words, obs_size, n, static_cast<__half*>(out), row_pitch); break;
+    default: return PFail("BatchExpandPacked: dtype must be 0 (float32), 1 (bfloat16) or 2 (float16)");
+  }
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : PFail(std::string("BatchExpandPacked: ") + cudaGetErrorString(e));
 }
 
 // Host-side twin of BatchSelectAction for epsilon >= 1 (uniform random legal
@@ -350,8 +641,9 @@ int BatchC51QValues(const float* logits, const float* support, const uint8_t* ma
                     void* stream) {
   if (!logits || !support || !mask || !q_out || !greedy_actions) return PFail("BatchC51QValues: null argument");
   const int64_t threads = (int64_t)n * 32;
-  hbp::k_select_c51<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      logits, support, mask, n, num_actions, num_atoms, 0.0f, 0, 0, greedy_actions, q_out);
+  hbp::k_select_c51<float><<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      logits, (int64_t)num_actions * num_atoms, support, mask, n, num_actions, num_atoms, 0.0f, 0, 0,
+      greedy_actions, q_out);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : PFail(std::string("BatchC51QValues: ") + cudaGetErrorString(e));
 }

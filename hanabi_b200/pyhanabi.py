@@ -1068,6 +1068,75 @@ def bind_select_action(values, mask, epsilon, seed, out, support=None, stream=No
   return run
 
 
+def _gemm_dtype_code(t):
+  import torch
+  codes = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
+  if t.dtype not in codes:
+    raise ValueError("expected float32, bfloat16 or float16, got %s" % (t.dtype,))
+  return codes[t.dtype]
+
+
+def bind_select_action_c51(logits, num_atoms, mask, epsilon, seed, out, support, stream=None):
+  """Masked epsilon-greedy on the raw output of a C51 head's last GEMM
+  (BatchSelectActionC51): logits is a 2-d CUDA tensor [n, >= A*num_atoms] in float32,
+  bfloat16 or float16 whose rows may be padded (row pitch = logits.stride(0)).
+  Returns run(step)."""
+  import torch
+  _require_lib()
+  n, A = int(mask.shape[0]), int(mask.shape[1])
+  if logits.dim() != 2 or logits.stride(1) != 1 or int(logits.shape[0]) != n:
+    raise ValueError("logits must be [n, pitch] with unit column stride")
+  head = (ffi.cast("void*", logits.data_ptr()), _gemm_dtype_code(logits), int(logits.stride(0)),
+          int(num_atoms), _tp(support, torch.float32, "float*"), _tp(mask, torch.uint8, "uint8_t*"),
+          n, A, float(epsilon), int(seed) & (2**64 - 1))
+  s = _cur_stream(mask) if stream is None else ffi.cast("void*", stream.cuda_stream)
+  tail = (_tp(out, torch.int32, "int32_t*"), s)
+  fn = lib.BatchSelectActionC51
+  keep = (logits, mask, out, support)
+
+  def run(step, _head=head, _tail=tail, _fn=fn, _keep=keep):
+    if _fn(*(_head + (step,) + _tail)) != 0:
+      raise RuntimeError("BatchSelectActionC51 failed: %s" % encode_ffi_string(lib.BatchLastError()))
+  return run
+
+
+def select_action_c51(logits, num_atoms, mask, epsilon, seed, step, support, out=None):
+  import torch
+  if out is None:
+    out = torch.empty(int(mask.shape[0]), dtype=torch.int32, device=mask.device)
+  with torch.cuda.device(mask.device):
+    bind_select_action_c51(logits, num_atoms, mask, epsilon, seed, out, support)(int(step) & (2**64 - 1))
+  return out
+
+
+def bind_expand_packed(obs_bits, obs_size, out, stream=None):
+  """Bit-packed observation rows (int32 [n, packed_words]) -> `out` [n, pitch] of 0/1 in
+  float32 / bfloat16 / float16, columns beyond obs_size zeroed (BatchExpandPacked).
+  Returns run()."""
+  import torch
+  _require_lib()
+  n, words = int(obs_bits.shape[0]), int(obs_bits.shape[1])
+  if out.dim() != 2 or out.stride(1) != 1 or int(out.shape[0]) != n:
+    raise ValueError("out must be [n, pitch] with unit column stride")
+  args = (_tp(obs_bits, torch.int32, "uint32_t*"), words, int(obs_size), n,
+          ffi.cast("void*", out.data_ptr()), int(out.stride(0)), _gemm_dtype_code(out),
+          _cur_stream(out) if stream is None else ffi.cast("void*", stream.cuda_stream))
+  fn = lib.BatchExpandPacked
+  keep = (obs_bits, out)
+
+  def run(_args=args, _fn=fn, _keep=keep):
+    if _fn(*_args) != 0:
+      raise RuntimeError("BatchExpandPacked failed: %s" % encode_ffi_string(lib.BatchLastError()))
+  return run
+
+
+def expand_packed(obs_bits, obs_size, out):
+  import torch
+  with torch.cuda.device(out.device):
+    bind_expand_packed(obs_bits, obs_size, out)()
+  return out
+
+
 def host_random_legal_actions(mask, seed, step, out=None, threads=0):
   """Uniform random legal move per game on the HOST (CPU uint8 mask [n, A] ->
   CPU int32 actions [n]); bit-identical to select_action(None, mask, 1.0, seed, step)."""

@@ -238,9 +238,6 @@ int BatchStepEncodeScores(pyhanabi_batch_t* batch, const int32_t* actions,
                           int64_t row_pitch, uint8_t* mask, int32_t* cur_player,
                           int auto_reset, void* stream);
 
-/* Bit-packed observations (optional, reported separately from the byte form): row i
- * = BatchPackedObservationWords() uint32 words (16-byte multiple), bit j of the row
- * = observation bit j, padding zero.  obs_bits must be 16-byte aligned. */
 /* BatchStepEncodeScores with a fused uniform-random policy (the reference's
    agents/random_agent.py for every game at once): after the move, random_actions[i]
    = a uniformly random legal move of game i's new state, -1 if none; the same draw
@@ -251,6 +248,9 @@ int BatchStepEncodeRandom(pyhanabi_batch_t* batch, const int32_t* actions, int32
                           uint8_t* mask, int32_t* cur_player, int auto_reset,
                           int32_t* random_actions, uint64_t seed, uint64_t step, void* stream);
 
+/* Bit-packed observations (optional, reported separately from the byte form): row i
+ * = BatchPackedObservationWords() uint32 words (16-byte multiple), bit j of the row
+ * = observation bit j, padding zero.  obs_bits must be 16-byte aligned. */
 int BatchPackedObservationWords(pyhanabi_batch_t* batch);
 int BatchStepEncodePacked(pyhanabi_batch_t* batch, const int32_t* actions, int32_t* rewards,
                           uint8_t* dones, int32_t* scores, uint32_t* obs_bits, uint8_t* mask,
@@ -307,6 +307,20 @@ int BatchReadStats(pyhanabi_batch_t* batch, int64_t* host_stats, int clear, void
 int BatchSelectAction(const float* q_or_logits, int num_atoms, const float* support,
                       const uint8_t* mask, int n, int num_actions, float epsilon,
                       uint64_t seed, uint64_t step, int32_t* actions, void* stream);
+/* BatchSelectAction for a C51 head whose logits come straight out of a GEMM:
+ * dtype 0 = float32, 1 = bfloat16, 2 = float16; row_pitch = elements between two
+ * games' rows (>= num_actions * num_atoms), so an N-padded GEMM output is used in
+ * place. */
+int BatchSelectActionC51(const void* logits, int dtype, int64_t row_pitch, int num_atoms,
+                         const float* support, const uint8_t* mask, int n, int num_actions,
+                         float epsilon, uint64_t seed, uint64_t step, int32_t* actions,
+                         void* stream);
+/* Bit-packed observation rows -> the network's input matrix: out[i][j] = bit j of
+ * row i as 0/1 in float32 / bfloat16 / float16 (dtype as above), columns
+ * [obs_size, row_pitch) zero (K padded to the GEMM's alignment).  row_pitch % 8 == 0,
+ * out 16-byte aligned. */
+int BatchExpandPacked(const uint32_t* obs_bits, int packed_words, int obs_size, int n,
+                      void* out, int64_t row_pitch, int dtype, void* stream);
 /* Host-side twin of BatchSelectAction with epsilon >= 1 (the reference's
  * agents/random_agent.py for a whole batch): HOST mask in, HOST actions out,
  * identical to the device kernel for equal (seed, step, game). */

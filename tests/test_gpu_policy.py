@@ -151,3 +151,49 @@ def test_fused_random_policy_equals_the_select_kernel(name):
   a.step_encode_random(act_a, 11, 99, rew_a, done_a, obs_a, mask_a, cur_a, random_actions=nxt)
   assert torch.equal(act_a, before)
   assert torch.equal(nxt, ph.select_action(None, mask_a, 1.0, seed=11, step=99))
+
+
+@pytest.mark.parametrize("dtype_name", ["float32", "bfloat16", "float16"])
+def test_expand_packed_and_c51_select_on_gemm_outputs(dtype_name):
+  """BatchExpandPacked gives the byte observation as 0/1 in the GEMM's input type with a
+  zero-padded K; BatchSelectActionC51 on a padded, typed logits matrix picks what
+  BatchSelectAction picks on the same values in float32."""
+  import torch
+  from hanabi_b200 import pyhanabi as ph
+  from tests import common
+  dt = getattr(torch, dtype_name)
+  n = 3001
+  b = ph.HanabiBatch(common.CONFIGS["full2"], n, common.seeds_for(n, base=9))
+  dev = torch.device("cuda:0")
+  D, A, W = b.obs_size, b.max_moves, b.packed_words
+  obs = torch.zeros((n, D), dtype=torch.uint8, device=dev)
+  bits = torch.zeros((n, W), dtype=torch.int32, device=dev)
+  mask = torch.zeros((n, A), dtype=torch.uint8, device=dev)
+  b.reset()
+  b.observe(obs, mask)
+  b.observe_packed(bits)
+  K = 672
+  x = torch.full((n, K), 7, dtype=dt, device=dev)
+  ph.expand_packed(bits, D, x)
+  assert torch.equal(x[:, :D].float(), obs.float()) and not x[:, D:].any()
+  # a wider pitch: every column from obs_size up to the pitch is zeroed
+  wide = torch.full((n, K + 32), 7, dtype=dt, device=dev)
+  ph.expand_packed(bits, D, wide)
+  assert torch.equal(wide[:, :D].float(), obs.float()) and not wide[:, D:].any()
+  atoms = 51
+  torch.manual_seed(1)
+  full = (torch.randn((n, 1024), device=dev) * 2).to(dt)
+  support = torch.linspace(-25.0, 25.0, atoms, device=dev)
+  got = ph.select_action_c51(full, atoms, mask, 0.0, seed=5, step=3, support=support)
+  ref_logits = full[:, :A * atoms].float().contiguous().view(n, A, atoms)
+  want = ph.select_action(ref_logits, mask, 0.0, seed=5, step=3, support=support)
+  # the two kernels subtract different maxima inside the softmax: near-ties may flip
+  assert float((got == want).float().mean()) > 0.999
+  legal_pick = mask.gather(1, got.long().view(-1, 1)).view(-1)
+  assert bool((legal_pick == 1).all())
+  # and against a torch restatement of q = sum softmax * support with the legal mask
+  q = (torch.softmax(ref_logits, dim=2) * support).sum(dim=2)
+  q = torch.where(mask.bool(), q, torch.full_like(q, float("-inf")))
+  top = q.max(dim=1).values
+  picked = q.gather(1, got.long().view(-1, 1)).view(-1)
+  assert bool(((top - picked).abs() <= 1e-4 * top.abs().clamp(min=1)).all())
