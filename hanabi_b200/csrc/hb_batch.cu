@@ -50,7 +50,6 @@ constexpr int kWarps = kBlock / 32;
 constexpr int kQueueCap = 64;    // finished games a CTA re-deals through the shared-memory queue
 constexpr int kStreamPad = 2;    // readable pad words after each packed bit stream
 constexpr int kNumStats = 32;    // [0] episodes [1] sum score [2] sum length [3..28] score histogram
-constexpr int kDumpLen = 272;    // canonical unpacked state, see oracle/oracle_api.h
 
 struct KArgs {
   Spec spec;
@@ -408,13 +407,9 @@ __global__ void k_blank(uint4* state, int64_t N, int ncols) {
 }
 
 // Packed state -> canonical unpacked dump (oracle/oracle_api.h layout).
-__global__ void k_unpack(KArgs a, int32_t* out) {
-  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= a.N) return;
+__device__ void unpack_one(const KArgs& a, int64_t g, int32_t* d, Game& G) {
   const DView v(a.spec);
-  Game G;
   load_game(a.state, a.N, g, v, G);
-  int32_t* d = out + g * (int64_t)kDumpLen;
   for (int i = 0; i < kDumpLen; ++i) d[i] = 0;
   const int C = a.spec.C, R = a.spec.R;
   d[0] = G.cur; d[1] = G.info; d[2] = G.life; d[3] = G.deck_size;
@@ -443,6 +438,27 @@ __global__ void k_unpack(KArgs a, int32_t* out) {
       d[216 + k] = __popcll((G.deck >> off) & bm);
       d[241 + k] = __popcll((G.disc >> off) & bm);
     }
+}
+
+__global__ void k_unpack(KArgs a, int32_t* out) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= a.N) return;
+  Game G;
+  unpack_one(a, g, out + g * (int64_t)kDumpLen, G);
+}
+
+// One game's dump plus what the dump does not carry (BatchExportGame).
+__global__ void k_export(KArgs a, int64_t g, int32_t* out) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  Game G;
+  unpack_one(a, g, out, G);
+  out[kDumpLen + 0] = G.turns;
+  out[kDumpLen + 1] = (int32_t)G.last;
+  const uint4 h = a.hist ? a.hist[g] : make_uint4(0, 0, 0, 0);
+  out[kDumpLen + 2] = (int32_t)h.x; out[kDumpLen + 3] = (int32_t)h.y;
+  out[kDumpLen + 4] = (int32_t)h.z; out[kDumpLen + 5] = (int32_t)h.w;
+  out[kDumpLen + 6] = G.done;
+  out[kDumpLen + 7] = G.eplen;
 }
 
 // Canonical dump -> packed state (keeps each game's RNG position).  The dump does
@@ -1100,6 +1116,28 @@ int BatchUnpackState(pyhanabi_batch_t* h, int32_t* dump, void* stream) {
   const unsigned grid = (unsigned)((b->N + 127) / 128);
   hb::k_unpack<<<grid, 128, 0, (cudaStream_t)stream>>>(a, dump);
   HB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// One game of the batch as a host-side record (hb::kExportLen int32 values: the
+// canonical dump, turns_to_play, the last non-deal move and the moves before it when
+// the history ring is on).  StateFromBatchGame (hb_single.cc) turns it into a
+// single-game HanabiState for the reference's per-object API.  Synchronous.
+int BatchExportGame(pyhanabi_batch_t* h, int64_t game, int32_t* host_record, void* stream) {
+  HB_BATCH(h);
+  if (!host_record) return Fail("BatchExportGame: host_record is null");
+  if (game < 0 || game >= b->N) return Fail("BatchExportGame: game index out of range");
+  cudaStream_t s = (cudaStream_t)stream;
+  int32_t* d = nullptr;
+  HB_CUDA(cudaMallocAsync(&d, sizeof(int32_t) * hb::kExportLen, s));
+  hb::KArgs a = BaseArgs(b);
+  hb::k_export<<<1, 32, 0, s>>>(a, game, d);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(host_record, d, sizeof(int32_t) * hb::kExportLen, cudaMemcpyDeviceToHost, s);
+  cudaFreeAsync(d, s);
+  if (e != cudaSuccess) return CudaFail("BatchExportGame", e);
+  HB_CUDA(cudaStreamSynchronize(s));
   return 0;
 }
 

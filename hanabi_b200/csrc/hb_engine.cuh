@@ -89,10 +89,7 @@ struct Game {
   uint32_t spare;
 };
 
-// last-action record fields
-constexpr int kLaValid = 0, kLaTypeSh = 1, kLaActorSh = 3, kLaOffSh = 6, kLaValSh = 9,
-              kLaIdxSh = 12, kLaColSh = 15, kLaRankSh = 18, kLaRevealSh = 21, kLaScoredSh = 26,
-              kLaInfoSh = 27;
+// last-action record fields: kLa* in hb_spec.h
 
 HB_DEV int hand_size(const Game& G, int p_static) { return (G.hw[p_static] >> 16) & 15; }
 

@@ -27,6 +27,7 @@
 #include <vector>
 
 #include "../../include/pyhanabi.h"
+#include "hb_spec.h"
 
 namespace hbs {
 
@@ -728,6 +729,79 @@ void DeleteState(pyhanabi_state_t* state) {
   delete AS(State, state->state);
   state->state = nullptr;
 }
+// Rebuilds `state` (an existing state of `game`) from one game of a batch as
+// BatchExportGame returns it, so that the reference's per-object API -- observations,
+// encoders, the rule-based agents, the GUI layer -- can look at a batched game.
+// The batch keeps neither the order of the discard pile (the pile comes back sorted
+// by card type) nor deal moves nor more than the last 1 (5 with BatchEnableHistory)
+// player moves; newly_revealed_bitmask is not recorded and returns as the reveal
+// bitmask.  Everything the canonical encoder and LegalMoves look at is exact.
+void StateFromBatchGame(pyhanabi_game_t* game, const int32_t* rec, pyhanabi_state_t* state) {
+  HBS_REQUIRE(game != nullptr && game->game != nullptr && rec != nullptr && state != nullptr);
+  const Game* g = CAS(Game, game->game);
+  State* st = new State(g);
+  const int C = g->colors, R = g->ranks, P = g->players;
+  st->cur_player = rec[0];
+  st->next_player = (rec[0] + 1) % P;
+  st->info = rec[1];
+  st->life = rec[2];
+  st->deck_total = rec[3];
+  for (int c = 0; c < C; ++c) st->fireworks[c] = rec[6 + c];
+  for (int p = 0; p < P; ++p) {
+    Hand& h = st->hands[p];
+    h.cards.clear();
+    h.knowledge.clear();
+    for (int i = 0; i < rec[11 + p]; ++i) {
+      const int id = rec[16 + p * 8 + i];
+      Card card;
+      card.color = id / R;
+      card.rank = id % R;
+      Knowledge k(C, R);
+      k.color_ok = (uint32_t)rec[56 + p * 8 + i];
+      k.rank_ok = (uint32_t)rec[96 + p * 8 + i];
+      k.color = rec[136 + p * 8 + i];
+      k.rank = rec[176 + p * 8 + i];
+      h.cards.push_back(card);
+      h.knowledge.push_back(k);
+    }
+  }
+  st->discard_pile.clear();
+  for (int k = 0; k < C * R; ++k) {
+    st->deck[k] = rec[216 + k];
+    for (int j = 0; j < rec[241 + k]; ++j) {
+      Card card;
+      card.color = k / R;
+      card.rank = k % R;
+      st->discard_pile.push_back(card);
+    }
+  }
+  st->turns_to_play = rec[hb::kDumpLen];
+  st->history.clear();
+  for (int j = 4; j >= 0; --j) {  // oldest first; [1] is the newest
+    const uint32_t la = (uint32_t)rec[hb::kDumpLen + 1 + j];
+    if (!(la & 1u)) continue;
+    HistoryItem h;
+    const int type = (la >> hb::kLaTypeSh) & 3;
+    h.player = (int8_t)((la >> hb::kLaActorSh) & 7);
+    if (type == hb::kLaPlay || type == hb::kLaDiscard) {
+      h.move = Move(type == hb::kLaPlay ? kPlay : kDiscard, (la >> hb::kLaIdxSh) & 7, -1, -1, -1);
+      h.color = (int8_t)((la >> hb::kLaColSh) & 7);
+      h.rank = (int8_t)((la >> hb::kLaRankSh) & 7);
+      h.scored = (la >> hb::kLaScoredSh) & 1;
+      h.information_token = (la >> hb::kLaInfoSh) & 1;
+    } else {
+      const int off = (la >> hb::kLaOffSh) & 7, val = (la >> hb::kLaValSh) & 7;
+      h.move = type == hb::kLaRevealColor ? Move(kRevealColor, -1, off, val, -1)
+                                          : Move(kRevealRank, -1, off, -1, val);
+      h.reveal_bitmask = (uint8_t)((la >> hb::kLaRevealSh) & 31);
+      h.newly_revealed_bitmask = h.reveal_bitmask;
+    }
+    st->history.push_back(h);
+  }
+  delete AS(State, state->state);
+  state->state = st;
+}
+
 const void* StateParentGame(pyhanabi_state_t* state) {
   HBS_REQUIRE(state != nullptr && state->state != nullptr);
   return CAS(State, state->state)->game;

@@ -33,6 +33,19 @@ enum ObsType { kMinimal = 0, kCardKnowledge = 1, kSeer = 2 };
 // (hanabi_lib/canonical_encoders.cc:258-269), not the HanabiMove::Type enum order.
 enum LaType { kLaPlay = 0, kLaDiscard = 1, kLaRevealColor = 2, kLaRevealRank = 3 };
 
+// Packed record of a non-deal move (state column P+1 .z and the optional history ring):
+// bit 0 valid, then type (LaType), acting player (absolute), target offset, hinted value,
+// card index, colour and rank of the played/discarded card, reveal bitmask, scored,
+// information token gained.
+constexpr int kLaValid = 0, kLaTypeSh = 1, kLaActorSh = 3, kLaOffSh = 6, kLaValSh = 9,
+              kLaIdxSh = 12, kLaColSh = 15, kLaRankSh = 18, kLaRevealSh = 21, kLaScoredSh = 26,
+              kLaInfoSh = 27;
+// BatchExportGame: canonical dump (272 ints, oracle/oracle_api.h layout) followed by
+// [272] turns_to_play [273] last-move record [274..277] the four records before it, newest
+// first (0 unless BatchEnableHistory) [278] done flag [279] episode length
+constexpr int kDumpLen = 272;
+constexpr int kExportLen = 280;
+
 struct Spec {
   int32_t P, C, R, H, IT, LT;
   int32_t obs_type, random_start;

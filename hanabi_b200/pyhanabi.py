@@ -681,6 +681,8 @@ class HanabiBatch(object):
     if len(seeds) != self.num_games:
       raise ValueError("need one seed per game")
     c_seeds = ffi.new("int32_t[]", [((s + 2**31) % 2**32) - 2**31 for s in seeds])
+    self._params = {k: v for k, v in dict(params).items() if k != "seed"}
+    self._host_game = None
     n, arr, keep = _params_to_c(params)
     self._c = ffi.new("pyhanabi_batch_t*")
     _check(lib.NewBatch(self._c, n, arr, self.num_games, int(device), c_seeds), "NewBatch")
@@ -982,6 +984,26 @@ class HanabiBatch(object):
     vals = [int(out[i]) for i in range(32)]
     return {"episodes": vals[0], "score_sum": vals[1], "length_sum": vals[2],
             "score_hist": vals[3:29]}
+
+  def export_state(self, game_index):
+    """Game `game_index` as a single-game HanabiState (BatchExportGame +
+    StateFromBatchGame): observations, encoders, rule-based agents and the GUI layer
+    of the per-object API work on it.  The discard pile comes back sorted by card type
+    and the move history holds the last player move only (five with enable_history())."""
+    if getattr(self, "_host_game", None) is None:
+      self._host_game = HanabiGame(dict(self._params))
+    rec = ffi.new("int32_t[280]")
+    _check(lib.BatchExportGame(self._c, int(game_index), rec, self._stream()), "BatchExportGame")
+    state = HanabiState(self._host_game)
+    lib.StateFromBatchGame(self._host_game.c_game, rec, state._state)
+    return state
+
+  @property
+  def host_game(self):
+    """A single-game HanabiGame with this batch's parameters (move uids, encoders)."""
+    if getattr(self, "_host_game", None) is None:
+      self._host_game = HanabiGame(dict(self._params))
+    return self._host_game
 
   def set_l2_residency(self, max_bytes=0):
     """Keeps the packed state in L2 between steps (BatchSetL2Residency); returns the

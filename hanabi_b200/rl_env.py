@@ -41,6 +41,38 @@ class Environment(object):
     raise NotImplementedError("Not implemented in Abstract Base class")
 
 
+def observation_dict(state, game, encoder, observation):
+  """One player's observation as the reference's dict (rl_env.py:382-438): 14 keys
+  including `legal_moves_as_int`, `vectorized` and the live `pyhanabi` handle."""
+  d = {}
+  d["current_player"] = state.cur_player()
+  d["current_player_offset"] = observation.cur_player_offset()
+  d["life_tokens"] = observation.life_tokens()
+  d["information_tokens"] = observation.information_tokens()
+  d["num_players"] = observation.num_players()
+  d["deck_size"] = observation.deck_size()
+  d["fireworks"] = dict(zip(pyhanabi.COLOR_CHAR, state.fireworks()))
+  d["legal_moves"] = []
+  d["legal_moves_as_int"] = []
+  for move in observation.legal_moves():
+    d["legal_moves"].append(move.to_dict())
+    d["legal_moves_as_int"].append(game.get_move_uid(move))
+  d["observed_hands"] = [[card.to_dict() for card in hand]
+                         for hand in observation.observed_hands()]
+  d["discard_pile"] = [card.to_dict() for card in observation.discard_pile()]
+  d["card_knowledge"] = []
+  for player_hints in observation.card_knowledge():
+    hints = []
+    for hint in player_hints:
+      color = hint.color()
+      hints.append({"color": pyhanabi.color_idx_to_char(color) if color is not None else None,
+                    "rank": hint.rank()})
+    d["card_knowledge"].append(hints)
+  d["vectorized"] = encoder.encode(observation)
+  d["pyhanabi"] = observation
+  return d
+
+
 class HanabiEnv(Environment):
   """The reference's single-game environment, unchanged in behaviour
   (rl_env.py:67-498): same config dict, same per-player observation dicts (all 14
@@ -97,33 +129,7 @@ class HanabiEnv(Environment):
     }
 
   def _extract_dict_from_backend(self, player_id, observation):
-    d = {}
-    d["current_player"] = self.state.cur_player()
-    d["current_player_offset"] = observation.cur_player_offset()
-    d["life_tokens"] = observation.life_tokens()
-    d["information_tokens"] = observation.information_tokens()
-    d["num_players"] = observation.num_players()
-    d["deck_size"] = observation.deck_size()
-    d["fireworks"] = dict(zip(pyhanabi.COLOR_CHAR, self.state.fireworks()))
-    d["legal_moves"] = []
-    d["legal_moves_as_int"] = []
-    for move in observation.legal_moves():
-      d["legal_moves"].append(move.to_dict())
-      d["legal_moves_as_int"].append(self.game.get_move_uid(move))
-    d["observed_hands"] = [[card.to_dict() for card in hand]
-                           for hand in observation.observed_hands()]
-    d["discard_pile"] = [card.to_dict() for card in observation.discard_pile()]
-    d["card_knowledge"] = []
-    for player_hints in observation.card_knowledge():
-      hints = []
-      for hint in player_hints:
-        color = hint.color()
-        hints.append({"color": pyhanabi.color_idx_to_char(color) if color is not None else None,
-                      "rank": hint.rank()})
-      d["card_knowledge"].append(hints)
-    d["vectorized"] = self.observation_encoder.encode(observation)
-    d["pyhanabi"] = observation
-    return d
+    return observation_dict(self.state, self.game, self.observation_encoder, observation)
 
   def _build_move(self, action):
     assert isinstance(action, dict), "Expected dict, got: {}".format(action)
@@ -231,6 +237,27 @@ class BatchedHanabiEnv(object):
 
   def episode_statistics(self, clear=False):
     return self.batch.read_stats(clear=clear)
+
+  def game_state(self, game_index):
+    """Game `game_index` as a single-game pyhanabi.HanabiState (host side, on demand)."""
+    return self.batch.export_state(game_index)
+
+  def game_observations(self, game_index):
+    """What the reference's HanabiEnv returns for one game -- {'player_observations':
+    [14-key dict per player], 'current_player'} (rl_env.py:368-438) -- built on demand
+    from game `game_index` of the batch, for debugging, logging and the GUI layer.  The
+    discard pile is sorted by card type and `pyhanabi.last_moves()` holds the last player
+    move only (five with batch.enable_history()); everything else is exact."""
+    state = self.batch.export_state(game_index)
+    game = self.batch.host_game
+    if getattr(self, "_host_encoder", None) is None:
+      self._host_encoder = pyhanabi.ObservationEncoder(game, pyhanabi.ObservationEncoderType.CANONICAL)
+    return {
+        "player_observations": [
+            observation_dict(state, game, self._host_encoder, state.observation(pid))
+            for pid in range(self.players)],
+        "current_player": state.cur_player(),
+    }
 
 
 def _preset(environment_name, num_players):

@@ -403,6 +403,18 @@ int ReplaySetPriority(pyhanabi_replay_t* replay, const int32_t* indices,
 int ReplayGetPriority(pyhanabi_replay_t* replay, const int32_t* indices, int count,
                       float* priorities, void* stream);
 
+/* One game of a batch for the per-object API above (debugging, the GUI layer, the
+   rule-based agents): BatchExportGame copies game `game` into host_record (280
+   int32: the canonical state dump, turns_to_play, the last player move and -- with
+   BatchEnableHistory -- the four before it); StateFromBatchGame rebuilds `state`
+   (any existing state of a HanabiGame with the batch's parameters) from it.  Exact
+   for everything LegalMoves, Score, the observations' hands/knowledge/tokens and the
+   canonical encoding read; the discard pile comes back sorted by card type and deal
+   moves are not part of the history. */
+int BatchExportGame(pyhanabi_batch_t* batch, int64_t game, int32_t* host_record, void* stream);
+void StateFromBatchGame(pyhanabi_game_t* game, const int32_t* host_record,
+                        pyhanabi_state_t* state);
+
 /* Keeps the packed game state resident in the L2 cache between steps (an
    access-policy window on every launch of this batch; the observation stores
    stream past it).  max_bytes: 0 = the device's maximum persisting carve-out,

@@ -210,3 +210,57 @@ def test_self_play_recorder_posts_the_reference_trajectories():
         term = 1
         break
     assert abs(float(reward3[i]) - float(acc)) < 1e-5 and int(terminal[i]) == term
+
+
+@pytest.mark.parametrize("players", [2, 4])
+def test_exported_game_gives_the_reference_observation_dict(players):
+  """BatchedHanabiEnv.game_observations(i) against the single-game HanabiEnv (same seed,
+  same moves): every key of every player's dict, the discard pile as a multiset."""
+  import torch
+  from hanabi_b200 import rl_env
+  n, probe = 97, [0, 31, 32, 96]
+  env = rl_env.make_batched("Hanabi-Full", num_players=players, num_games=n, seed=200)
+  singles = {}
+  for i in probe:
+    cfg = dict(colors=5, ranks=5, players=players, max_information_tokens=8, max_life_tokens=3,
+               observation_type=1, seed=200 + i)
+    singles[i] = rl_env.HanabiEnv(cfg)
+    singles[i].reset()
+  obs = env.reset()
+  rng = np.random.default_rng(5)
+  alive = set(probe)
+  for t in range(45):
+    mask = obs["legal_moves_mask"].cpu().numpy()
+    for i in sorted(alive):
+      got = env.game_observations(i)
+      want = singles[i]._make_observation_all_players()
+      assert got["current_player"] == want["current_player"]
+      for pg, pw in zip(got["player_observations"], want["player_observations"]):
+        for key in pw:
+          if key == "pyhanabi":
+            continue
+          if key == "discard_pile":
+            order = lambda cards: sorted((c["color"], c["rank"]) for c in cards)
+            assert order(pg[key]) == order(pw[key])
+          else:
+            assert pg[key] == pw[key], (i, t, key)
+      cur = got["current_player"]
+      assert got["player_observations"][cur]["vectorized"] == obs["vectorized"][i].cpu().tolist()
+      # the newest entry of last_moves is the last player move (deals are not kept)
+      moves = [m for m in want["player_observations"][cur]["pyhanabi"].last_moves()
+               if m.move().type() != 5]
+      mine = got["player_observations"][cur]["pyhanabi"].last_moves()
+      if moves:
+        assert str(mine[0].move()) == str(moves[0].move()) and mine[0].player() == moves[0].player()
+        assert mine[0].scored() == moves[0].scored()
+        assert mine[0].information_token() == moves[0].information_token()
+        assert mine[0].card_info_revealed() == moves[0].card_info_revealed()
+    a = common.choose_actions(None, mask, rng, False, 5, 5)
+    obs, reward, done, _ = env.step(torch.as_tensor(a, device=env.device))
+    for i in sorted(alive):
+      _, r, d, _ = singles[i].step(int(a[i]))
+      assert r == int(reward[i]) and d == bool(done[i])
+      if d:
+        alive.discard(i)  # the batch re-deals on the same RNG stream; the single env would re-seed
+    if not alive:
+      break
