@@ -580,6 +580,11 @@ struct Batch {
   // pinned/pipelined host path
   cudaStream_t h_streams[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t h_events[3] = {nullptr, nullptr, nullptr};
+  // BatchStepEncodeHostRange: completion events of the most recent ranges
+  static constexpr int kRangeSlots = 64;
+  cudaEvent_t range_events[kRangeSlots] = {};
+  int64_t range_first[kRangeSlots] = {};
+  int range_next = 0;
   // device staging for the host-buffer entry point, allocated on first use
   int32_t* d_actions = nullptr;
   int32_t* d_rewards = nullptr;
@@ -796,6 +801,8 @@ void DeleteBatch(pyhanabi_batch_t* h) {
     if (b->h_streams[i]) cudaStreamDestroy(b->h_streams[i]);
     if (b->h_events[i]) cudaEventDestroy(b->h_events[i]);
   }
+  for (int i = 0; i < Batch::kRangeSlots; ++i)
+    if (b->range_events[i]) cudaEventDestroy(b->range_events[i]);
   cudaFree(b->d_actions); cudaFree(b->d_rewards); cudaFree(b->d_scores); cudaFree(b->d_cur);
   cudaFree(b->d_dones); cudaFree(b->d_obs); cudaFree(b->d_mask);
   cudaFree(b->state);
@@ -936,6 +943,65 @@ int BatchStepEncodeRandom(pyhanabi_batch_t* h, const int32_t* actions, int32_t* 
 // action upload, the kernel and the result download of neighbouring chunks
 // overlap.  Synchronous: the host buffers are complete on return.  `stream` is
 // the stream whose earlier work on this batch must finish first (may be NULL).
+// Staging buffers and internal streams of the host-buffer entry points (first use).
+static int HostSetup(Batch* b) {
+  if (b->h_streams[0]) return 0;
+  const size_t N = (size_t)b->N;
+  const int D = b->spec.obs_size, A = b->spec.max_moves;
+  for (int i = 0; i < 3; ++i) {
+    HB_CUDA(cudaStreamCreateWithFlags(&b->h_streams[i], cudaStreamNonBlocking));
+    HB_CUDA(cudaEventCreateWithFlags(&b->h_events[i], cudaEventDisableTiming));
+  }
+  for (int i = 0; i < Batch::kRangeSlots; ++i) {
+    HB_CUDA(cudaEventCreateWithFlags(&b->range_events[i], cudaEventDisableTiming));
+    b->range_first[i] = -1;
+  }
+  HB_CUDA(cudaMalloc(&b->d_actions, N * sizeof(int32_t)));
+  HB_CUDA(cudaMalloc(&b->d_rewards, N * sizeof(int32_t)));
+  HB_CUDA(cudaMalloc(&b->d_scores, N * sizeof(int32_t)));
+  HB_CUDA(cudaMalloc(&b->d_cur, N * sizeof(int32_t)));
+  HB_CUDA(cudaMalloc(&b->d_dones, N));
+  HB_CUDA(cudaMalloc(&b->d_obs, N * (size_t)D));
+  HB_CUDA(cudaMalloc(&b->d_mask, N * (size_t)A));
+  return 0;
+}
+
+// Enqueues games [g0, g1) on stream s: action upload, the fused kernel, result download.
+// The host pointers are the bases of the whole arrays (indexed by game).
+static int EnqueueHostRange(Batch* b, size_t g0, size_t g1, const int32_t* actions, int32_t* rewards,
+                            uint8_t* dones, int32_t* scores, uint8_t* obs, int64_t row_pitch,
+                            uint32_t* obs_bits, uint8_t* mask, int32_t* cur_player, int auto_reset,
+                            cudaStream_t s) {
+  const int D = b->spec.obs_size, A = b->spec.max_moves;
+  const size_t n = g1 - g0;
+  HB_CUDA(cudaMemcpyAsync(b->d_actions + g0, actions + g0, n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+  hb::KArgs a = BaseArgs(b);
+  a.g_begin = (int64_t)g0; a.g_end = (int64_t)g1;
+  a.actions = b->d_actions; a.rewards = b->d_rewards; a.dones = b->d_dones; a.scores = b->d_scores;
+  a.obs = obs ? b->d_obs : nullptr; a.obs_pitch = D; a.mask = mask ? b->d_mask : nullptr;
+  a.obs_bits = (!obs && obs_bits) ? reinterpret_cast<uint32_t*>(b->d_obs) : nullptr;  // staging reused
+  a.cur_player = b->d_cur; a.auto_reset = auto_reset;
+  HB_CUDA(Launch<hb::kModeStep>(b, a, s));
+  if (a.obs_bits) {
+    const size_t row = (size_t)b->packed_words * sizeof(uint32_t);
+    HB_CUDA(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(obs_bits) + g0 * row, b->d_obs + g0 * row, n * row,
+                            cudaMemcpyDeviceToHost, s));
+  }
+  if (obs) {
+    if (row_pitch == D)
+      HB_CUDA(cudaMemcpyAsync(obs + g0 * (size_t)D, b->d_obs + g0 * (size_t)D, n * (size_t)D, cudaMemcpyDeviceToHost, s));
+    else
+      HB_CUDA(cudaMemcpy2DAsync(obs + g0 * (size_t)row_pitch, (size_t)row_pitch, b->d_obs + g0 * (size_t)D,
+                                (size_t)D, (size_t)D, n, cudaMemcpyDeviceToHost, s));
+  }
+  if (mask) HB_CUDA(cudaMemcpyAsync(mask + g0 * (size_t)A, b->d_mask + g0 * (size_t)A, n * (size_t)A, cudaMemcpyDeviceToHost, s));
+  if (rewards) HB_CUDA(cudaMemcpyAsync(rewards + g0, b->d_rewards + g0, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  if (dones) HB_CUDA(cudaMemcpyAsync(dones + g0, b->d_dones + g0, n, cudaMemcpyDeviceToHost, s));
+  if (scores) HB_CUDA(cudaMemcpyAsync(scores + g0, b->d_scores + g0, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  if (cur_player) HB_CUDA(cudaMemcpyAsync(cur_player + g0, b->d_cur + g0, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  return 0;
+}
+
 static int StepHost(pyhanabi_batch_t* h, const int32_t* actions, int32_t* rewards, uint8_t* dones,
                     int32_t* scores, uint8_t* obs, int64_t row_pitch, uint32_t* obs_bits,
                     uint8_t* mask, int32_t* cur_player, int auto_reset, void* stream) {
@@ -943,20 +1009,7 @@ static int StepHost(pyhanabi_batch_t* h, const int32_t* actions, int32_t* reward
   if (!actions) return Fail("BatchStepEncodeHost: actions is null");
   if (obs && row_pitch < b->spec.obs_size) return Fail("BatchStepEncodeHost: row_pitch smaller than the observation");
   const size_t N = (size_t)b->N;
-  const int D = b->spec.obs_size, A = b->spec.max_moves;
-  if (!b->h_streams[0]) {
-    for (int i = 0; i < 3; ++i) {
-      HB_CUDA(cudaStreamCreateWithFlags(&b->h_streams[i], cudaStreamNonBlocking));
-      HB_CUDA(cudaEventCreateWithFlags(&b->h_events[i], cudaEventDisableTiming));
-    }
-    HB_CUDA(cudaMalloc(&b->d_actions, N * sizeof(int32_t)));
-    HB_CUDA(cudaMalloc(&b->d_rewards, N * sizeof(int32_t)));
-    HB_CUDA(cudaMalloc(&b->d_scores, N * sizeof(int32_t)));
-    HB_CUDA(cudaMalloc(&b->d_cur, N * sizeof(int32_t)));
-    HB_CUDA(cudaMalloc(&b->d_dones, N));
-    HB_CUDA(cudaMalloc(&b->d_obs, N * (size_t)D));
-    HB_CUDA(cudaMalloc(&b->d_mask, N * (size_t)A));
-  }
+  if (HostSetup(b)) return 1;
   HB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
   int nchunks = (int)((N + 32767) / 32768);
   if (nchunks > 12) nchunks = 12;
@@ -966,36 +1019,58 @@ static int StepHost(pyhanabi_batch_t* h, const int32_t* actions, int32_t* reward
   int c = 0;
   for (size_t g0 = 0; g0 < N; g0 += cs, ++c) {
     const size_t g1 = g0 + cs < N ? g0 + cs : N;
-    const size_t n = g1 - g0;
-    cudaStream_t s = b->h_streams[c % 3];
-    HB_CUDA(cudaMemcpyAsync(b->d_actions + g0, actions + g0, n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-    hb::KArgs a = BaseArgs(b);
-    a.g_begin = (int64_t)g0; a.g_end = (int64_t)g1;
-    a.actions = b->d_actions; a.rewards = b->d_rewards; a.dones = b->d_dones; a.scores = b->d_scores;
-    a.obs = obs ? b->d_obs : nullptr; a.obs_pitch = D; a.mask = mask ? b->d_mask : nullptr;
-    a.obs_bits = (!obs && obs_bits) ? reinterpret_cast<uint32_t*>(b->d_obs) : nullptr;  // staging reused
-    a.cur_player = b->d_cur; a.auto_reset = auto_reset;
-    HB_CUDA(Launch<hb::kModeStep>(b, a, s));
-    if (a.obs_bits) {
-      const size_t row = (size_t)b->packed_words * sizeof(uint32_t);
-      HB_CUDA(cudaMemcpyAsync(reinterpret_cast<uint8_t*>(obs_bits) + g0 * row, b->d_obs + g0 * row, n * row,
-                              cudaMemcpyDeviceToHost, s));
-    }
-    if (obs) {
-      if (row_pitch == D)
-        HB_CUDA(cudaMemcpyAsync(obs + g0 * (size_t)D, b->d_obs + g0 * (size_t)D, n * (size_t)D, cudaMemcpyDeviceToHost, s));
-      else
-        HB_CUDA(cudaMemcpy2DAsync(obs + g0 * (size_t)row_pitch, (size_t)row_pitch, b->d_obs + g0 * (size_t)D,
-                                  (size_t)D, (size_t)D, n, cudaMemcpyDeviceToHost, s));
-    }
-    if (mask) HB_CUDA(cudaMemcpyAsync(mask + g0 * (size_t)A, b->d_mask + g0 * (size_t)A, n * (size_t)A, cudaMemcpyDeviceToHost, s));
-    if (rewards) HB_CUDA(cudaMemcpyAsync(rewards + g0, b->d_rewards + g0, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-    if (dones) HB_CUDA(cudaMemcpyAsync(dones + g0, b->d_dones + g0, n, cudaMemcpyDeviceToHost, s));
-    if (scores) HB_CUDA(cudaMemcpyAsync(scores + g0, b->d_scores + g0, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-    if (cur_player) HB_CUDA(cudaMemcpyAsync(cur_player + g0, b->d_cur + g0, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+    if (EnqueueHostRange(b, g0, g1, actions, rewards, dones, scores, obs, row_pitch, obs_bits, mask,
+                         cur_player, auto_reset, b->h_streams[c % 3]))
+      return 1;
   }
   for (int i = 0; i < 3; ++i) HB_CUDA(cudaStreamSynchronize(b->h_streams[i]));
   return 0;
+}
+
+// Asynchronous, ranged form for callers that pipeline their own host work: games
+// [first_game, first_game + num_games) only (first_game a multiple of 128), pointers are
+// the bases of the whole arrays.  Returns as soon as the work is queued; the range's host
+// buffers are complete after BatchHostWait(batch, first_game).  While one range is in
+// flight the caller can prepare the actions of the next (the policy of range c overlaps the
+// transfers of range c-1), which keeps the PCIe link busy for the whole step.
+int BatchStepEncodeHostRange(pyhanabi_batch_t* h, int64_t first_game, int64_t num_games,
+                             const int32_t* actions, int32_t* rewards, uint8_t* dones,
+                             int32_t* scores, uint8_t* obs, int64_t row_pitch, uint8_t* mask,
+                             int32_t* cur_player, int auto_reset) {
+  HB_BATCH(h);
+  if (!actions) return Fail("BatchStepEncodeHostRange: actions is null");
+  if (obs && row_pitch < b->spec.obs_size) return Fail("BatchStepEncodeHostRange: row_pitch smaller than the observation");
+  if (first_game < 0 || num_games <= 0 || first_game + num_games > b->N || (first_game & 127))
+    return Fail("BatchStepEncodeHostRange: range must lie in the batch and start at a multiple of 128");
+  if (HostSetup(b)) return 1;
+  const int slot = b->range_next++ % Batch::kRangeSlots;
+  cudaStream_t s = b->h_streams[slot % 3];
+  if (EnqueueHostRange(b, (size_t)first_game, (size_t)(first_game + num_games), actions, rewards, dones,
+                       scores, obs, row_pitch, nullptr, mask, cur_player, auto_reset, s))
+    return 1;
+  HB_CUDA(cudaEventRecord(b->range_events[slot], s));
+  b->range_first[slot] = first_game;
+  return 0;
+}
+
+// Blocks until the most recent BatchStepEncodeHostRange call that started at first_game has
+// delivered its host buffers; first_game < 0 waits for everything queued.
+int BatchHostWait(pyhanabi_batch_t* h, int64_t first_game) {
+  HB_BATCH(h);
+  if (!b->h_streams[0]) return 0;
+  if (first_game < 0) {
+    for (int i = 0; i < 3; ++i) HB_CUDA(cudaStreamSynchronize(b->h_streams[i]));
+    return 0;
+  }
+  for (int k = 1; k <= Batch::kRangeSlots; ++k) {  // newest first
+    if (b->range_next - k < 0) break;
+    const int slot = (b->range_next - k) % Batch::kRangeSlots;
+    if (b->range_first[slot] == first_game) {
+      HB_CUDA(cudaEventSynchronize(b->range_events[slot]));
+      return 0;
+    }
+  }
+  return 0;  // nothing queued for that range
 }
 
 int BatchStepEncodeHost(pyhanabi_batch_t* h, const int32_t* actions, int32_t* rewards,

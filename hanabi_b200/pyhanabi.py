@@ -913,6 +913,32 @@ class HanabiBatch(object):
         self._h(cur_player, torch.int32, n, "int32_t*"), int(bool(auto_reset)), self._stream()),
            "BatchStepEncodeHostPacked")
 
+  def bind_step_encode_host_range(self, actions, rewards=None, dones=None, obs=None, mask=None,
+                                  cur_player=None, scores=None, auto_reset=True):
+    """Pre-bound BatchStepEncodeHostRange: returns (launch(first, count), wait(first)).
+    launch queues the step of games [first, first + count) and returns at once; wait
+    blocks until that range's host buffers are filled (first < 0: everything)."""
+    torch = self._torch
+    n = self.num_games
+    optr, pitch = self._h_obs(obs)
+    args = (self._h(actions, torch.int32, n, "int32_t*"), self._h(rewards, torch.int32, n, "int32_t*"),
+            self._h(dones, torch.uint8, n, "uint8_t*"), self._h(scores, torch.int32, n, "int32_t*"),
+            optr, pitch,
+            self._h(mask, torch.uint8, n * self.max_moves, "uint8_t*"),
+            self._h(cur_player, torch.int32, n, "int32_t*"), int(bool(auto_reset)))
+    keep = (actions, rewards, dones, obs, mask, cur_player, scores)
+    c = self._c
+
+    def launch(first, count, _args=args, _keep=keep):
+      if lib.BatchStepEncodeHostRange(c, first, count, *_args) != 0:
+        raise RuntimeError("BatchStepEncodeHostRange failed: %s" %
+                           encode_ffi_string(lib.BatchLastError()))
+
+    def wait(first=-1):
+      if lib.BatchHostWait(c, first) != 0:
+        raise RuntimeError("BatchHostWait failed: %s" % encode_ffi_string(lib.BatchLastError()))
+    return launch, wait
+
   def reset_host(self, obs=None, mask=None, cur_player=None):
     torch = self._torch
     n = self.num_games

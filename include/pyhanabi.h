@@ -270,6 +270,16 @@ int BatchStepEncodeHostPacked(pyhanabi_batch_t* batch, const int32_t* actions,
                               int32_t* rewards, uint8_t* dones, int32_t* scores,
                               uint32_t* obs_bits, uint8_t* mask, int32_t* cur_player,
                               int auto_reset, void* stream);
+/* Asynchronous, ranged BatchStepEncodeHost for callers that pipeline their own host
+   work: games [first_game, first_game + num_games) only (first_game % 128 == 0), the
+   pointers are the bases of the whole arrays.  Returns once the work is queued; the
+   range's host buffers are complete after BatchHostWait(batch, first_game)
+   (first_game < 0: everything queued). */
+int BatchStepEncodeHostRange(pyhanabi_batch_t* batch, int64_t first_game, int64_t num_games,
+                             const int32_t* actions, int32_t* rewards, uint8_t* dones,
+                             int32_t* scores, uint8_t* obs, int64_t row_pitch, uint8_t* mask,
+                             int32_t* cur_player, int auto_reset);
+int BatchHostWait(pyhanabi_batch_t* batch, int64_t first_game);
 int BatchResetHost(pyhanabi_batch_t* batch, uint8_t* obs, int64_t row_pitch, uint8_t* mask,
                    int32_t* cur_player, void* stream);
 

@@ -264,3 +264,37 @@ def test_exported_game_gives_the_reference_observation_dict(players):
         alive.discard(i)  # the batch re-deals on the same RNG stream; the single env would re-seed
     if not alive:
       break
+
+
+def test_ranged_async_host_step_matches_the_synchronous_call():
+  import torch
+  from hanabi_b200 import pyhanabi as ph
+  n = 40000
+  params = CONFIGS["full2"]
+  seeds = common.seeds_for(n, base=77)
+  a, b = ph.HanabiBatch(params, n, seeds), ph.HanabiBatch(params, n, seeds)
+  D, A = a.obs_size, a.max_moves
+  pin = lambda *shape, dt: torch.zeros(shape, dtype=dt).pin_memory()
+  bufs = []
+  for x in (a, b):
+    t = dict(obs=pin(n, D, dt=torch.uint8), mask=pin(n, A, dt=torch.uint8), cur=pin(n, dt=torch.int32),
+             rew=pin(n, dt=torch.int32), done=pin(n, dt=torch.uint8), act=pin(n, dt=torch.int32),
+             score=pin(n, dt=torch.int32))
+    x.reset_host(t["obs"], t["mask"], t["cur"])
+    bufs.append(t)
+  ta, tb = bufs
+  launch, wait = b.bind_step_encode_host_range(tb["act"], tb["rew"], tb["done"], tb["obs"], tb["mask"],
+                                               tb["cur"], scores=tb["score"])
+  ranges = [(0, 12800), (12800, 12800), (25600, n - 25600)]  # ragged last range
+  for t in range(10):
+    ph.host_random_legal_actions(ta["mask"], seed=3, step=t, out=ta["act"])
+    a.step_encode_host(ta["act"], ta["rew"], ta["done"], ta["obs"], ta["mask"], ta["cur"], scores=ta["score"])
+    for lo, cnt in ranges:
+      wait(lo)
+      tb["act"][lo:lo + cnt].copy_(ta["act"][lo:lo + cnt])
+      launch(lo, cnt)
+    wait(-1)
+    for k in ("obs", "mask", "cur", "rew", "done", "score"):
+      assert torch.equal(ta[k], tb[k]), (k, t)
+  with pytest.raises(RuntimeError, match="multiple of 128"):
+    launch(64, 128)
