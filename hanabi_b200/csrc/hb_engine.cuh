@@ -230,9 +230,10 @@ HB_DEV void mt_load5(const uint32_t* x, int k, Prefetch& f) {
 }
 
 // Takes outputs k and k+1 of the game's stream (tempered) and regenerates both slots.
-HB_DEV void mt_take2(uint32_t* x, int& k, uint32_t& w0, uint32_t& w1, Prefetch* pre) {
+HB_DEV void mt_take2(uint32_t* x, int& k, uint32_t& w0, uint32_t& w1, Prefetch& pre) {
+  // `pre` by reference (never by address) so that it stays in registers
   Prefetch f;
-  if (pre != nullptr && pre->at == k) { f = *pre; pre->at = -1; }
+  if (pre.at == k) { f = pre; pre.at = -1; }
   else mt_load5(x, k, f);
   w0 = mt_temper(f.a);
   w1 = mt_temper(f.b);
@@ -601,7 +602,7 @@ HB_DEV void init_fresh(V v, const Spec& spec, Game& G, int start_player) {
 // cards.  Purely per-thread.
 template <class V>
 HB_DEV void deal_loop(V v, const Spec& spec, Game& G, bool restart, int64_t g, uint32_t* mt_all,
-                      int sampler_mode, Prefetch* pre = nullptr) {
+                      int sampler_mode, Prefetch& pre) {
   uint32_t* x = mt_all + g * (int64_t)kMtN;
   for (;;) {
     bool need = needs_deal(v, G);
