@@ -56,6 +56,9 @@ def parse_args():
                        "kernel's fused random-action output (BatchStepEncodeRandom)")
   ap.add_argument("--mlp-dtype", choices=["fp32", "tf32", "bf16", "fp16"], default="tf32",
                   help="element type of the Rainbow policy's two library GEMMs (accumulation is fp32)")
+  ap.add_argument("--adhoc-all-rows", action="store_true",
+                  help="ad-hoc team: run the Rainbow MLP on every game instead of only those whose "
+                       "player to act is the Rainbow seat")
   ap.add_argument("--shards", type=int, default=2,
                   help="random policy only: split each GPU's games into this many independent "
                        "batches on their own CUDA streams, so that one launch's last, partly "
@@ -393,9 +396,29 @@ def main():
       seat_mask = sum(1 << s for s in range(1, batch.num_players))
       launches_per_step = 4
 
-      def select(t):
+      def select_all(t):
         rainbow(t)
         batch.agent_act(0, seat_mask, act, agent_state=agent_state)
+
+      def select_compact(t):
+        # only the games whose player to act is seat 0 go through the network: gather
+        # their packed rows and masks, run the MLP on that many rows, scatter the actions
+        idx = (cur == 0).nonzero().squeeze(1)  # one host sync per step (the row count)
+        m = int(idx.numel())
+        if m:
+          # row count rounded up to a multiple of 2048: few distinct GEMM shapes, so the
+          # library's per-shape kernel selection is paid once each
+          mp = (m + 2047) // 2048 * 2048
+          xb = torch.zeros((mp, Kp), dtype=tdt, device=dev)
+          ph.expand_packed(bits.index_select(0, idx), D, xb[:m])
+          hh = torch._addmm_activation(b1, xb, w1)
+          lg = torch.addmm(b2, hh, w2)
+          am = ph.select_action_c51(lg[:m], atoms, mask.index_select(0, idx), 0.0, seed=7, step=t,
+                                    support=support)
+          act.index_copy_(0, idx, am)
+        batch.agent_act(0, seat_mask, act, agent_state=agent_state)
+
+      select = select_all if args.adhoc_all_rows else select_compact
 
   def one_step(t):
     select(t)
@@ -605,7 +628,9 @@ def main():
                             "Rainbow C51 MLP %d->512->%dx51 (cuBLASLt %s GEMMs via torch) on "
                             "BatchExpandPacked input + BatchSelectActionC51 (epsilon=0)"
                             % (D, A, args.mlp_dtype) +
-                            ("; seats 1.. = batched RuleBasedAgent (BatchAgentAct)"
+                            ("; seats 1.. = batched RuleBasedAgent (BatchAgentAct); MLP on %s"
+                             % ("all games" if args.adhoc_all_rows else
+                                "the games whose player to act is seat 0 (gathered rows)")
                              if args.policy == "adhoc" else "")),
                  "auto_reset": True, "seeds": "1 + global game index",
                  "l2": "outputs per step (%.0f MB) exceed the 126 MB L2" % (n * (D + A) / 1e6),
