@@ -288,6 +288,7 @@ def main():
   if world > 1:
     import torch.distributed as dist
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the one JSON line
     dist.init_process_group("nccl", device_id=dev)
 
   params = WORKLOADS[args.workload]
