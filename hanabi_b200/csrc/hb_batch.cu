@@ -479,6 +479,22 @@ __global__ void k_export(KArgs a, int64_t g, int32_t* out) {
   out[kDumpLen + 7] = G.eplen;
 }
 
+// Per-game error flags (an illegal action was submitted since the last clear).
+__global__ void k_errors(uint4* state, int64_t N, int col, uint8_t* flags, int clear,
+                         unsigned long long* count) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool err = false;
+  if (g < N) {
+    uint32_t* x = &state[(int64_t)col * N + g].x;
+    const uint32_t v = *x;
+    err = (v >> 31) & 1u;
+    if (flags) flags[g] = err ? 1 : 0;
+    if (clear && err) *x = v & 0x7fffffffu;
+  }
+  const unsigned m = __ballot_sync(kFull, err);
+  if (count && m && (threadIdx.x & 31) == 0) atomicAdd(count, (unsigned long long)__popc(m));
+}
+
 // Canonical dump -> packed state (keeps each game's RNG position).  The dump does
 // not carry turns_to_play / last action; they arrive in `extra[g*2+{0,1}]`
 // (turns_to_play, packed last-action record or 0).
@@ -1210,6 +1226,18 @@ int BatchUnpackState(pyhanabi_batch_t* h, int32_t* dump, void* stream) {
   hb::KArgs a = BaseArgs(b);
   const unsigned grid = (unsigned)((b->N + 127) / 128);
   hb::k_unpack<<<grid, 128, 0, (cudaStream_t)stream>>>(a, dump);
+  HB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Illegal actions do not abort: the game is left unchanged and flagged.  Writes the
+// flags (device uint8[num_games], nullable), adds their number to *count (device
+// uint64, nullable; the caller zeroes it) and optionally clears them.
+int BatchErrorFlags(pyhanabi_batch_t* h, uint8_t* flags, uint64_t* count, int clear, void* stream) {
+  HB_BATCH(h);
+  const unsigned grid = (unsigned)((b->N + 127) / 128);
+  hb::k_errors<<<grid, 128, 0, (cudaStream_t)stream>>>(b->state, b->N, b->spec.P + 1, flags, clear,
+                                                       reinterpret_cast<unsigned long long*>(count));
   HB_CUDA(cudaGetLastError());
   return 0;
 }

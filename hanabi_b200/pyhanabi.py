@@ -1011,6 +1011,15 @@ class HanabiBatch(object):
     return {"episodes": vals[0], "score_sum": vals[1], "length_sum": vals[2],
             "score_hist": vals[3:29]}
 
+  def error_flags(self, clear=True):
+    """uint8[num_games] CUDA tensor: 1 where an illegal action was submitted (the game
+    was left unchanged) since the flags were last cleared (BatchErrorFlags)."""
+    torch = self._torch
+    flags = torch.zeros(self.num_games, dtype=torch.uint8, device=self.device)
+    _check(lib.BatchErrorFlags(self._c, self._p(flags, torch.uint8, self.num_games, "uint8_t*"),
+                               ffi.NULL, int(bool(clear)), self._stream()), "BatchErrorFlags")
+    return flags
+
   def export_state(self, game_index):
     """Game `game_index` as a single-game HanabiState (BatchExportGame +
     StateFromBatchGame): observations, encoders, rule-based agents and the GUI layer

@@ -413,6 +413,12 @@ int ReplaySetPriority(pyhanabi_replay_t* replay, const int32_t* indices,
 int ReplayGetPriority(pyhanabi_replay_t* replay, const int32_t* indices, int count,
                       float* priorities, void* stream);
 
+/* Illegal actions do not abort a batch: the game stays unchanged and is flagged.
+   flags: device uint8[num_games] (nullable), count: device uint64 that the number of
+   flagged games is added to (nullable), clear != 0 resets the flags. */
+int BatchErrorFlags(pyhanabi_batch_t* batch, uint8_t* flags, uint64_t* count, int clear,
+                    void* stream);
+
 /* One game of a batch for the per-object API above (debugging, the GUI layer, the
    rule-based agents): BatchExportGame copies game `game` into host_record (280
    int32: the canonical state dump, turns_to_play, the last player move and -- with

@@ -234,6 +234,13 @@ def test_no_auto_reset_illegal_actions_and_partial_reset():
   r = gpu.step(bad)
   assert (r[0] == 0).all() and (r[1] == 0).all()
   common.assert_same(before, gpu.dump(), "illegal actions leave the games unchanged")
+  assert bool(gpu.b.error_flags(clear=False).all())
+  half = bad.copy()
+  half[::2] = p["hand_size"]  # uid H = play slot 0: always legal in a fresh game
+  assert bool(gpu.b.error_flags(clear=True).all()) and not bool(gpu.b.error_flags().any())
+  r = gpu.step(half)
+  flags = gpu.b.error_flags().cpu().numpy()
+  assert (flags[1::2] == 1).all() and (flags[::2] == 0).all()
   del torch
 
 
