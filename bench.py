@@ -56,6 +56,9 @@ def parse_args():
                        "kernel's fused random-action output (BatchStepEncodeRandom)")
   ap.add_argument("--mlp-dtype", choices=["fp32", "tf32", "bf16", "fp16"], default="tf32",
                   help="element type of the Rainbow policy's two library GEMMs (accumulation is fp32)")
+  ap.add_argument("--no-graph", action="store_true",
+                  help="rainbow / adhoc (all rows) policies: launch every kernel of a step from the "
+                       "host instead of replaying one captured CUDA graph per step")
   ap.add_argument("--adhoc-all-rows", action="store_true",
                   help="ad-hoc team: run the Rainbow MLP on every game instead of only those whose "
                        "player to act is the Rainbow seat")
@@ -291,6 +294,13 @@ def main():
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the one JSON line
     dist.init_process_group("nccl", device_id=dev)
 
+  # ad-hoc team: below 32 768 games per GPU the host sync of the row gather costs more than
+  # running the MLP on every game
+  adhoc_all_rows = args.adhoc_all_rows or args.games < 32768
+  use_graph = (not args.no_graph) and (args.policy == "rainbow" or
+                                       (args.policy == "adhoc" and adhoc_all_rows))
+  if use_graph:
+    torch.cuda.set_stream(torch.cuda.Stream(device=dev))  # capture needs a non-default stream
   params = WORKLOADS[args.workload]
   n = args.games
   from hanabi_b200 import sharding
@@ -419,7 +429,7 @@ def main():
           act.index_copy_(0, idx, am)
         batch.agent_act(0, seat_mask, act, agent_state=agent_state)
 
-      select = select_all if args.adhoc_all_rows else select_compact
+      select = select_all if adhoc_all_rows else select_compact
 
   def one_step(t):
     select(t)
@@ -433,6 +443,25 @@ def main():
   torch.cuda.synchronize()
   if dist:
     dist.barrier()
+    torch.cuda.synchronize()
+
+  graph_kernel_ms = None
+  if use_graph:
+    # the step kernel's own duration from a short evented pass, then one step captured
+    pre_ev = []
+    for t in range(20):
+      select(W + t)
+      e_a, e_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      e_a.record(); step_encode(W + t); e_b.record()
+      pre_ev.append((e_a, e_b))
+    torch.cuda.synchronize()
+    graph_kernel_ms = sum(x.elapsed_time(y) for x, y in pre_ev) / len(pre_ev)
+    step_graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(step_graph, stream=torch.cuda.current_stream()):
+      one_step(0)
+    for _ in range(3):
+      step_graph.replay()
+    stats.zero_()
     torch.cuda.synchronize()
 
   sampler = ClockSampler(local_rank)
@@ -453,6 +482,9 @@ def main():
     if S > 1:
       for st in streams:
         main_stream.wait_stream(st)
+  elif use_graph:
+    for g_i in range(K):
+      step_graph.replay()
   else:
     for t in range(K):
       select(W + t)
@@ -466,7 +498,12 @@ def main():
   elapsed_ms = ev0.elapsed_time(ev1)
   # fused policy: S concurrent launches cover one step of all games, so the step time is
   # the launch time of the kernel over n games
-  kernel_ms = elapsed_ms / K if fused_policy else sum(a.elapsed_time(b) for a, b in k_ev) / K
+  if fused_policy:
+    kernel_ms = elapsed_ms / K
+  elif use_graph:
+    kernel_ms = graph_kernel_ms
+  else:
+    kernel_ms = sum(a.elapsed_time(b) for a, b in k_ev) / K
   if dist:
     tmax = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
     dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -630,9 +667,10 @@ def main():
                             "BatchExpandPacked input + BatchSelectActionC51 (epsilon=0)"
                             % (D, A, args.mlp_dtype) +
                             ("; seats 1.. = batched RuleBasedAgent (BatchAgentAct); MLP on %s"
-                             % ("all games" if args.adhoc_all_rows else
+                             % ("all games" if adhoc_all_rows else
                                 "the games whose player to act is seat 0 (gathered rows)")
                              if args.policy == "adhoc" else "")),
+                 "cuda_graph": bool(use_graph),
                  "auto_reset": True, "seeds": "1 + global game index",
                  "l2": "outputs per step (%.0f MB) exceed the 126 MB L2" % (n * (D + A) / 1e6),
                  "parallelism": "games sharded over %d GPU(s), no step-path collective" % world +
@@ -651,7 +689,7 @@ def main():
   }
   if packed is not None:
     line["packed_obs"] = packed
-  if not args.no_cpu_baseline:
+  if not args.no_cpu_baseline and world == 1:  # the CPU leg runs at N = 1 only
     line["cpu_baseline"] = cpu_reference_rate(args.workload, args.cpu_seconds)
     if args.python_baselines:
       line["cpu_baseline"]["python_paths"] = python_baselines(args.workload)
