@@ -87,6 +87,75 @@ class SelfPlayRecorder(object):
     return obs, action, reward_out, terminal, legal
 
 
+class DeviceRecorder(object):
+  """The same bookkeeping as SelfPlayRecorder in hand-written kernels (NewRecorder /
+  RecorderBeforeStep / RecorderAfterStep, hb_replay.cu): episode buffers keep the
+  observations bit-packed, finished episodes are written straight into the device
+  replay memory's ring.  One stream synchronisation per step (the number of posted
+  transitions), no torch indexing."""
+
+  def __init__(self, num_games, num_players, observation_size, num_actions, replay,
+               max_turns_per_seat=64, device=0):
+    import torch
+    from hanabi_b200 import pyhanabi
+    pyhanabi._require_lib()  # pylint: disable=protected-access
+    self._torch, self._ph = torch, pyhanabi
+    self._lib, self._ffi = pyhanabi.lib, pyhanabi.ffi
+    self.N, self.P, self.D, self.A = int(num_games), int(num_players), int(observation_size), int(num_actions)
+    self.replay = replay
+    self.device = torch.device("cuda", int(device))
+    self._c = self._ffi.new("pyhanabi_recorder_t*")
+    self._check(self._lib.NewRecorder(self._c, self.N, self.P, self.D, self.A,
+                                      int(max_turns_per_seat), int(device)), "NewRecorder")
+    self.packed_words = int(self._lib.RecorderPackedWords(self._c))
+    self._posted = self._ffi.new("int64_t*")
+
+  def __del__(self):
+    c, lib = getattr(self, "_c", None), getattr(self, "_lib", None)
+    if c is not None and lib is not None:
+      try:
+        lib.DeleteRecorder(c)
+      except Exception:  # interpreter shutdown
+        pass
+      self._c = None
+
+  def _check(self, rc, what):
+    if rc != 0:
+      raise RuntimeError("%s failed: %s" % (what, self._ph.encode_ffi_string(self._lib.BatchLastError())))
+
+  def _p(self, t, dtype, ctype, numel):
+    if not t.is_cuda or t.dtype != dtype or not t.is_contiguous() or t.numel() < numel:
+      raise ValueError("expected a contiguous CUDA %s tensor with >= %d elements" % (dtype, numel))
+    return self._ffi.cast(ctype, t.data_ptr())
+
+  def _stream(self):
+    return self._ffi.cast("void*", self._torch.cuda.current_stream(self.device).cuda_stream)
+
+  def before_step(self, current_player, obs_bits, legal_mask, action):
+    """obs_bits: int32 [N, packed_words] as step_encode_packed / observe_packed write them."""
+    torch = self._torch
+    self._check(self._lib.RecorderBeforeStep(
+        self._c, self._p(current_player, torch.int32, "int32_t*", self.N),
+        self._p(obs_bits, torch.int32, "uint32_t*", self.N * self.packed_words),
+        self._p(legal_mask, torch.uint8, "uint8_t*", self.N * self.A),
+        self._p(action, torch.int32, "int32_t*", self.N), self._stream()), "RecorderBeforeStep")
+
+  def after_step(self, reward, done, priority=None):
+    """reward int32 [N], done uint8 [N]; returns the number of transitions appended to
+    the replay memory."""
+    torch = self._torch
+    self._check(self._lib.RecorderAfterStep(
+        self._c, self._p(reward, torch.int32, "int32_t*", self.N),
+        self._p(done, torch.uint8, "uint8_t*", self.N), self.replay._c,  # pylint: disable=protected-access
+        -1.0 if priority is None else float(priority), self._posted, self._stream()),
+                "RecorderAfterStep")
+    return int(self._posted[0])
+
+  @property
+  def dropped(self):
+    return int(self._lib.RecorderDropped(self._c, self._stream()))
+
+
 def linearly_decaying_epsilon(decay_period, step, warmup_steps, epsilon):
   """Epsilon schedule of the DQN/Rainbow agents
   (agents/rainbow_copy/dqn_agent.py:44-59): 1.0 during warm-up, then linear decay to

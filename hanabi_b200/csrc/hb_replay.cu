@@ -211,6 +211,169 @@ __global__ void k_gather(View v, const int32_t* indices, int count, uint8_t* sta
   }
 }
 
+
+// ---- self-play recorder -------------------------------
+// Per (game, seat) episode buffers on the device: what DQNAgent.begin_episode / step /
+// end_episode keep around the network (agents/rainbow_copy/dqn_agent.py:286-385) and
+// what run_one_episode does with the rewards (agents/run_experiment.py:344-403), for N
+// games at once.  Observations are kept bit-packed (16-byte multiples) and expanded to
+// the replay memory's uint8 rows when an episode is posted.
+struct RecView {
+  int N, P, L, W, A, D;
+  uint32_t* obs;     // [N][P][L][W]
+  uint64_t* legal;   // [N][P][L]
+  int32_t* action;   // [N][P][L]
+  float* reward;     // [N][P][L]
+  int32_t* count;    // [N][P]
+  float* since;      // [N][P]  reward since the seat's last action
+  int32_t* run_len;  // [N][P]  snapshot of a finished game's episode lengths
+  float* run_since;  // [N][P]
+  int32_t* lens;     // [N] transitions a game posts this step; scanned in place
+  int32_t* block_sums;
+  unsigned long long* total;    // transitions posted this step
+  unsigned long long* dropped;  // transitions beyond L turns of a seat (never, for L = 64)
+};
+
+// begin_episode / step -> _record_transition for the acting seat of every game
+// (dqn_agent.py:286-357): the reward handed to step() closes the seat's previous
+// transition, then (o_t, l_t, a_t) opens a new one.
+__global__ void k_rec_before(RecView v, const int32_t* __restrict__ cur, const uint32_t* __restrict__ bits,
+                             const uint8_t* __restrict__ mask, const int32_t* __restrict__ actions) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= v.N) return;
+  const int c = cur[g];
+  if (c < 0 || c >= v.P) return;
+  const int64_t gp = (int64_t)g * v.P + c;
+  const int k = v.count[gp];
+  if (k > 0 && k <= v.L) v.reward[gp * v.L + (k - 1)] = v.since[gp];
+  v.since[gp] = 0.f;
+  if (k >= v.L) {
+    atomicAdd(v.dropped, 1ull);
+    v.count[gp] = k + 1;
+    return;
+  }
+  const uint4* src = reinterpret_cast<const uint4*>(bits + (int64_t)g * v.W);
+  uint4* dst = reinterpret_cast<uint4*>(v.obs + (gp * v.L + k) * v.W);
+  for (int j = 0; j < v.W / 4; ++j) dst[j] = src[j];
+  uint64_t legal = 0;
+  for (int a = 0; a < v.A; ++a) legal |= (uint64_t)(mask[(int64_t)g * v.A + a] != 0) << a;
+  v.legal[gp * v.L + k] = legal;
+  v.action[gp * v.L + k] = actions[g];
+  v.count[gp] = k + 1;
+}
+
+// After the environment step: every seat's pending reward grows by the step's reward
+// (run_experiment.py:374-377); a finished game snapshots its episodes for posting and
+// starts empty.
+__global__ void k_rec_after(RecView v, const int32_t* __restrict__ rewards, const uint8_t* __restrict__ dones) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= v.N) return;
+  const float r = (float)rewards[g];
+  const bool done = dones[g] != 0;
+  int total = 0;
+  for (int p = 0; p < v.P; ++p) {
+    const int64_t gp = (int64_t)g * v.P + p;
+    const float s = v.since[gp] + r;
+    if (done) {
+      const int k = v.count[gp] < v.L ? v.count[gp] : v.L;
+      v.run_len[gp] = k;
+      v.run_since[gp] = s;
+      v.count[gp] = 0;
+      v.since[gp] = 0.f;
+      total += k;
+    } else {
+      v.since[gp] = s;
+      v.run_len[gp] = 0;  // nothing to post for this seat
+    }
+  }
+  v.lens[g] = total;
+}
+
+// Exclusive prefix sum of lens[N] in three small passes (1024 elements per block).
+__device__ __forceinline__ int block_exclusive_scan(int x, int* warp_sums, int& block_total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = x;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int y = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += y;
+  }
+  if (lane == 31) warp_sums[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int w = lane < (int)(blockDim.x >> 5) ? warp_sums[lane] : 0;
+    int wi = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += y;
+    }
+    warp_sums[lane] = wi - w;          // exclusive offset of each warp
+    if (lane == 31) warp_sums[32] = wi;  // block total
+  }
+  __syncthreads();
+  block_total = warp_sums[32];
+  return incl - x + warp_sums[warp];
+}
+__global__ void k_scan_blocks(int32_t* data, int n, int32_t* block_sums) {
+  __shared__ int warp_sums[33];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int x = i < n ? data[i] : 0;
+  int total;
+  const int ex = block_exclusive_scan(x, warp_sums, total);
+  if (i < n) data[i] = ex;
+  if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+__global__ void k_scan_sums(int32_t* block_sums, int nblocks, unsigned long long* total_out) {
+  __shared__ int warp_sums[33];
+  int carry = 0;
+  for (int base = 0; base < nblocks; base += blockDim.x) {  // one block; loops when > 1024 block sums
+    const int i = base + threadIdx.x;
+    const int x = i < nblocks ? block_sums[i] : 0;
+    int total;
+    const int ex = block_exclusive_scan(x, warp_sums, total);
+    if (i < nblocks) block_sums[i] = ex + carry;
+    carry += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total_out = (unsigned long long)carry;
+}
+__global__ void k_scan_add(int32_t* data, int n, const int32_t* block_sums) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) data[i] += block_sums[blockIdx.x];
+}
+
+// _post_transitions (dqn_agent.py:359-385) for the finished games: one warp per (game,
+// seat) writes the seat's episode as a contiguous run of replay slots -- runs ordered by
+// game, then seat -- (o_t, a_t, r_{t+1}, terminal, l_t); the last transition carries the
+// seat's pending reward and the terminal flag.  Slots are (cursor + offset) mod capacity.
+__global__ void k_rec_post(RecView v, int64_t cursor, int64_t cap, uint8_t* r_obs, int32_t* r_actions,
+                           float* r_rewards, uint8_t* r_terminals, float* r_legal) {
+  const int lane = threadIdx.x & 31;
+  const int64_t gp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (gp >= (int64_t)v.N * v.P) return;
+  const int g = (int)(gp / v.P), p = (int)(gp - (int64_t)g * v.P);
+  const int len = v.run_len[gp];
+  if (len <= 0) return;
+  int64_t off = v.lens[g];  // exclusive prefix over games
+  for (int q = 0; q < p; ++q) off += v.run_len[(int64_t)g * v.P + q];
+  for (int k = 0; k < len; ++k) {
+    const int64_t slot = (cursor + off + k) % cap;
+    const uint32_t* row = v.obs + (gp * v.L + k) * v.W;
+    uint8_t* dst = r_obs + slot * v.D;
+    for (int b = lane; b < v.D; b += 32) dst[b] = (uint8_t)((row[b >> 5] >> (b & 31)) & 1u);
+    const uint64_t legal = v.legal[gp * v.L + k];
+    for (int a = lane; a < v.A; a += 32)
+      r_legal[slot * v.A + a] = ((legal >> a) & 1ull) ? 0.f : -CUDART_INF_F;  // format_legal_moves
+    if (lane == 0) {
+      const bool last = k == len - 1;
+      r_actions[slot] = v.action[gp * v.L + k];
+      r_rewards[slot] = last ? v.run_since[gp] : v.reward[gp * v.L + k];
+      r_terminals[slot] = last ? 1 : 0;
+    }
+  }
+}
+
 }  // namespace hbr
 
 namespace {
@@ -423,6 +586,146 @@ int ReplaySampleTransitionBatch(pyhanabi_replay_t* h, const int32_t* indices, in
       MakeView(r), indices, count, states, actions, rewards, next_states, terminals, next_legal_actions);
   HBR_CUDA(cudaGetLastError());
   return 0;
+}
+
+
+// ---- self-play recorder -------------------------------------------------------------
+struct Recorder {
+  int device = 0;
+  hbr::RecView v;
+  int nblocks = 0;
+  unsigned long long* h_total = nullptr;  // pinned
+};
+
+int NewRecorder(pyhanabi_recorder_t* out, int num_games, int num_players, int observation_size,
+                int num_actions, int max_turns_per_seat, int device) {
+  if (!out) return HbFail("NewRecorder: null handle");
+  out->recorder = nullptr;
+  if (num_games <= 0 || num_players < 2 || num_players > 5 || observation_size <= 0 ||
+      num_actions <= 0 || num_actions > 64 || max_turns_per_seat <= 0)
+    return HbFail("NewRecorder: bad sizes (players 2..5, actions <= 64)");
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count)
+    return HbFail("NewRecorder: no such CUDA device (the recorder has no CPU fallback)");
+  Recorder* r = new Recorder;
+  r->device = device;
+  Guard guard(device);
+  hbr::RecView& v = r->v;
+  std::memset(&v, 0, sizeof(v));
+  v.N = num_games; v.P = num_players; v.L = max_turns_per_seat; v.A = num_actions; v.D = observation_size;
+  v.W = 4 * ((observation_size + 127) / 128);
+  const size_t NP = (size_t)v.N * v.P, NPL = NP * v.L;
+  r->nblocks = (v.N + 1023) / 1024;
+  cudaError_t e = cudaSuccess;
+  auto alloc = [&](void** p, size_t bytes) {
+    if (e == cudaSuccess) e = cudaMalloc(p, bytes);
+    if (e == cudaSuccess) e = cudaMemset(*p, 0, bytes);
+  };
+  alloc((void**)&v.obs, NPL * v.W * sizeof(uint32_t));
+  alloc((void**)&v.legal, NPL * sizeof(uint64_t));
+  alloc((void**)&v.action, NPL * sizeof(int32_t));
+  alloc((void**)&v.reward, NPL * sizeof(float));
+  alloc((void**)&v.count, NP * sizeof(int32_t));
+  alloc((void**)&v.since, NP * sizeof(float));
+  alloc((void**)&v.run_len, NP * sizeof(int32_t));
+  alloc((void**)&v.run_since, NP * sizeof(float));
+  alloc((void**)&v.lens, (size_t)v.N * sizeof(int32_t));
+  alloc((void**)&v.block_sums, (size_t)r->nblocks * sizeof(int32_t));
+  alloc((void**)&v.total, sizeof(unsigned long long));
+  alloc((void**)&v.dropped, sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMallocHost((void**)&r->h_total, 2 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaDeviceSynchronize();
+  out->recorder = r;
+  if (e != cudaSuccess) {
+    DeleteRecorder(out);
+    return Check(e, "NewRecorder");
+  }
+  return 0;
+}
+
+void DeleteRecorder(pyhanabi_recorder_t* h) {
+  if (!h || !h->recorder) return;
+  Recorder* r = static_cast<Recorder*>(h->recorder);
+  Guard guard(r->device);
+  hbr::RecView& v = r->v;
+  cudaFree(v.obs); cudaFree(v.legal); cudaFree(v.action); cudaFree(v.reward); cudaFree(v.count);
+  cudaFree(v.since); cudaFree(v.run_len); cudaFree(v.run_since); cudaFree(v.lens);
+  cudaFree(v.block_sums); cudaFree(v.total); cudaFree(v.dropped);
+  if (r->h_total) cudaFreeHost(r->h_total);
+  delete r;
+  h->recorder = nullptr;
+}
+
+int RecorderPackedWords(pyhanabi_recorder_t* h) {
+  return (h && h->recorder) ? static_cast<Recorder*>(h->recorder)->v.W : -1;
+}
+
+// The acting seat's observation (bit-packed rows as BatchStepEncodePacked /
+// BatchObservePacked write them), legal mask and chosen action of every game, before the
+// environment step.  Asynchronous on `stream`.
+int RecorderBeforeStep(pyhanabi_recorder_t* h, const int32_t* cur_player, const uint32_t* obs_bits,
+                       const uint8_t* mask, const int32_t* actions, void* stream) {
+  if (!h || !h->recorder) return HbFail("null recorder handle");
+  Recorder* r = static_cast<Recorder*>(h->recorder);
+  if (!cur_player || !obs_bits || !mask || !actions) return HbFail("RecorderBeforeStep: null argument");
+  Guard guard(r->device);
+  hbr::k_rec_before<<<(r->v.N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(r->v, cur_player, obs_bits, mask, actions);
+  return Check(cudaGetLastError(), "RecorderBeforeStep");
+}
+
+// reward / done of the environment step just taken.  The episodes of the finished games
+// are appended to `replay` (each seat's episode one contiguous run, runs ordered by game
+// then seat; new transitions enter the sum tree with `priority`, < 0 = the default 100).
+// Synchronises once on `stream` to learn how many transitions were posted (*posted).
+int RecorderAfterStep(pyhanabi_recorder_t* h, const int32_t* rewards, const uint8_t* dones,
+                      pyhanabi_replay_t* replay, float priority, int64_t* posted, void* stream) {
+  if (!h || !h->recorder) return HbFail("null recorder handle");
+  Recorder* rec = static_cast<Recorder*>(h->recorder);
+  if (!rewards || !dones) return HbFail("RecorderAfterStep: null argument");
+  if (!replay || !replay->replay) return HbFail("RecorderAfterStep: null replay handle");
+  Replay* r = static_cast<Replay*>(replay->replay);
+  if (r->device != rec->device) return HbFail("RecorderAfterStep: recorder and replay memory sit on different devices");
+  if (r->A != rec->v.A || r->D != rec->v.D) return HbFail("RecorderAfterStep: replay memory has other observation / action sizes");
+  Guard guard(rec->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  hbr::RecView& v = rec->v;
+  hbr::k_rec_after<<<(v.N + 127) / 128, 128, 0, s>>>(v, rewards, dones);
+  hbr::k_scan_blocks<<<rec->nblocks, 1024, 0, s>>>(v.lens, v.N, v.block_sums);
+  hbr::k_scan_sums<<<1, 1024, 0, s>>>(v.block_sums, rec->nblocks, v.total);
+  hbr::k_scan_add<<<rec->nblocks, 1024, 0, s>>>(v.lens, v.N, v.block_sums);
+  HBR_CUDA(cudaGetLastError());
+  HBR_CUDA(cudaMemcpyAsync(rec->h_total, v.total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+  HBR_CUDA(cudaStreamSynchronize(s));
+  const int64_t total = (int64_t)rec->h_total[0];
+  if (posted) *posted = total;
+  if (total == 0) return 0;
+  if (total > r->cap) return HbFail("RecorderAfterStep: more transitions in one step than the replay capacity");
+  const int64_t cursor = r->add_count % r->cap;
+  const int64_t warps = (int64_t)v.N * v.P;
+  hbr::k_rec_post<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, s>>>(v, cursor, r->cap, r->obs, r->actions,
+                                                                       r->rewards, r->terminals, r->legal);
+  HBR_CUDA(cudaGetLastError());
+  r->add_count += total;
+  if (r->prioritized) {
+    const double p = priority < 0.f ? 100.0 : (double)priority;  // DEFAULT_PRIORITY
+    if (p > r->max_recorded_priority) r->max_recorded_priority = p;
+    hbr::k_set_leaves_range<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(r->tree, r->depth, r->cap, cursor, (int)total, p);
+    HBR_CUDA(cudaGetLastError());
+    if (RebuildRange(r, cursor, (int)total, s)) return 1;
+  }
+  return 0;
+}
+
+// Transitions that did not fit a seat's max_turns_per_seat slots (0 for the default 64).
+int64_t RecorderDropped(pyhanabi_recorder_t* h, void* stream) {
+  if (!h || !h->recorder) return -1;
+  Recorder* r = static_cast<Recorder*>(h->recorder);
+  Guard guard(r->device);
+  if (cudaMemcpyAsync(r->h_total + 1, r->v.dropped, sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                      (cudaStream_t)stream) != cudaSuccess ||
+      cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess)
+    return -1;
+  return (int64_t)r->h_total[1];
 }
 
 }  // extern "C"

@@ -437,6 +437,31 @@ void StateFromBatchGame(pyhanabi_game_t* game, const int32_t* host_record,
    negative = off.  *covered (nullable) receives the state bytes held. */
 int BatchSetL2Residency(pyhanabi_batch_t* batch, int64_t max_bytes, int64_t* covered);
 
+/* ===== device-side self-play recorder (the transition bookkeeping of
+ * DQNAgent.begin_episode / step / end_episode, dqn_agent.py:286-385, and the per-player
+ * "reward since my last action" of run_one_episode, run_experiment.py:344-403) ===== */
+typedef struct PyHanabiRecorder {
+  void* recorder;
+} pyhanabi_recorder_t;
+int NewRecorder(pyhanabi_recorder_t* recorder, int num_games, int num_players,
+                int observation_size, int num_actions, int max_turns_per_seat, int device);
+void DeleteRecorder(pyhanabi_recorder_t* recorder);
+int RecorderPackedWords(pyhanabi_recorder_t* recorder);
+/* Before the environment step: the acting seat's observation (bit-packed rows of
+ * BatchStepEncodePacked / BatchObservePacked), legal mask and chosen action of every
+ * game.  Device buffers, asynchronous on stream. */
+int RecorderBeforeStep(pyhanabi_recorder_t* recorder, const int32_t* cur_player,
+                       const uint32_t* obs_bits, const uint8_t* mask, const int32_t* actions,
+                       void* stream);
+/* After it: rewards int32[num_games] and dones uint8[num_games] of the step.  The
+ * episodes of finished games go into `replay`, each seat's episode as one contiguous
+ * run (runs ordered by game, then seat), last transition terminal with the seat's
+ * pending reward; *posted (host, nullable) = number of transitions appended. */
+int RecorderAfterStep(pyhanabi_recorder_t* recorder, const int32_t* rewards,
+                      const uint8_t* dones, pyhanabi_replay_t* replay, float priority,
+                      int64_t* posted, void* stream);
+int64_t RecorderDropped(pyhanabi_recorder_t* recorder, void* stream);
+
 /* Test hooks. */
 int BatchSetDebug(pyhanabi_batch_t* batch, int sampler_mode, int generic);
 int BatchDebugDeal(pyhanabi_batch_t* batch, const uint64_t* decks, const int32_t* sizes,

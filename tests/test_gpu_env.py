@@ -298,3 +298,56 @@ def test_ranged_async_host_step_matches_the_synchronous_call():
       assert torch.equal(ta[k], tb[k]), (k, t)
   with pytest.raises(RuntimeError, match="multiple of 128"):
     launch(64, 128)
+
+
+@pytest.mark.parametrize("players,game", [(3, "Hanabi-Small"), (2, "Hanabi-Full")])
+def test_device_recorder_posts_the_reference_trajectories(players, game):
+  """The kernel recorder (hanabi_b200.actor.DeviceRecorder) vs the per-game restatement of
+  the agent's transition bookkeeping (oracle/actor_oracle.py): the replay ring holds exactly
+  the posted stream -- observation bytes, action, reward, terminal, legal vector -- in the
+  same order (games that finish in a step by index, then seat, then time)."""
+  import torch
+  from hanabi_b200 import actor, replay, rl_env
+  from hanabi_b200 import pyhanabi as ph
+  from oracle import actor_oracle
+  n, steps = 1500, 70  # more than one scan block
+  env = rl_env.make_batched(game, num_players=players, num_games=n, seed=77)
+  D, A, P = env.batch.obs_size, env.batch.max_moves, env.players
+  mem = replay.DeviceReplayMemory(A, D, 1 << 18, update_horizon=1, gamma=0.99)
+  rec = actor.DeviceRecorder(n, P, D, A, mem)
+  books = [actor_oracle.EpisodeBook(P) for _ in range(n)]
+  obs = env.reset()
+  bits = torch.zeros((n, env.batch.packed_words), dtype=torch.int32, device=env.device)
+  act = torch.zeros(n, dtype=torch.int32, device=env.device)
+  want = []
+  for t in range(steps):
+    env.batch.observe_packed(bits)
+    ph.select_action(None, obs["legal_moves_mask"], 1.0, seed=5, step=t, out=act)
+    cur = obs["current_player"].clone()
+    rec.before_step(cur, bits, obs["legal_moves_mask"], act)
+    o_h, m_h, c_h, a_h = (obs["vectorized"].cpu().numpy(), obs["legal_moves_mask"].cpu().numpy(),
+                          cur.cpu().numpy(), act.cpu().numpy())
+    for i in range(n):
+      books[i].act(int(c_h[i]), o_h[i], m_h[i], int(a_h[i]))
+    obs, reward, done, _ = env.step(act)
+    before = mem.add_count
+    posted = rec.after_step(reward, done)
+    r_h, d_h = reward.cpu().numpy(), done.cpu().numpy()
+    want_now = []
+    for i in range(n):
+      p = books[i].env_result(float(r_h[i]), bool(d_h[i]))
+      if p:
+        want_now.extend(p)
+    assert posted == len(want_now) and mem.add_count == before + posted
+    want.extend(want_now)
+  assert len(want) > 2000 and rec.dropped == 0 and len(want) < (1 << 18)
+  # read the ring back: with update_horizon 1, slot i gives (obs_i, a_i, r_i, obs_{i+1}, t_i, ., legal_{i+1})
+  idx = torch.arange(0, len(want) - 1, dtype=torch.int32, device=env.device)
+  state, action, reward1, next_state, terminal, _, next_legal = mem.sample_transition_batch(indices=idx)
+  state, action, reward1, terminal, next_legal = [x.cpu().numpy() for x in (state, action, reward1, terminal, next_legal)]
+  for i in range(len(want) - 1):
+    o, a, r, term, legal = want[i]
+    assert state[i].tobytes() == o and int(action[i]) == a and np.float32(reward1[i]) == r and int(terminal[i]) == term, i
+    assert (next_legal[i] == 0).astype(np.uint8).tobytes() == want[i + 1][4], i
+  pri = mem.get_priority(idx).cpu().numpy()
+  assert (pri == 100.0).all()
