@@ -56,6 +56,10 @@ def parse_args():
                        "kernel's fused random-action output (BatchStepEncodeRandom)")
   ap.add_argument("--mlp-dtype", choices=["fp32", "tf32", "bf16", "fp16"], default="tf32",
                   help="element type of the Rainbow policy's two library GEMMs (accumulation is fp32)")
+  ap.add_argument("--record", action="store_true",
+                  help="rainbow policy: run the whole actor loop -- the device recorder keeps every "
+                       "seat's episode and appends finished episodes to a device replay memory")
+  ap.add_argument("--replay-capacity", type=int, default=1 << 22)
   ap.add_argument("--no-graph", action="store_true",
                   help="rainbow / adhoc (all rows) policies: launch every kernel of a step from the "
                        "host instead of replaying one captured CUDA graph per step")
@@ -334,6 +338,7 @@ def main():
   bound_step = batch.bind_step_encode(act, rew, done, obs, mask, cur)
   step_encode = lambda t: bound_step()
   launches_per_step = 2
+  recorder = None
   if fused_policy:
     # the uniform-random policy rides in the step kernel: it applies act[i] and leaves
     # the next random legal move in act[i] (same draw as BatchSelectAction, epsilon >= 1).
@@ -395,6 +400,19 @@ def main():
       greedy(t)
 
     select = rainbow
+    if args.record and args.policy == "rainbow":
+      # the complete actor loop: policy -> record (o, l, a) of the acting seat -> env step ->
+      # rewards to every seat, finished episodes into the device replay memory
+      from hanabi_b200 import actor, replay as replay_mod
+      memory = replay_mod.DeviceReplayMemory(A, D, args.replay_capacity, update_horizon=1, gamma=0.99,
+                                             device=local_rank)
+      recorder = actor.DeviceRecorder(n, batch.num_players, D, A, memory, device=local_rank)
+      launches_per_step = 9  # + record, 3 scan passes, post, 2 sum-tree kernels (first level)
+
+      def select(t):
+        rainbow(t)
+        recorder.before_step(cur, bits, mask, act)
+
     if args.policy == "adhoc":
       # ad-hoc team 1: seat 0 = Rainbow, every other seat = RuleBasedAgent, one shared
       # object (training/run_adhoc_experiment.py:195-258); the rule-based kernel
@@ -431,15 +449,24 @@ def main():
 
       select = select_all if adhoc_all_rows else select_compact
 
+  posted_total = [0]
+
+  def after_step():
+    # rewards to the seats, finished episodes into the replay: asynchronous, device-driven
+    if recorder is not None:
+      recorder.after_step(rew, done, return_count=False)
+
   def one_step(t):
     select(t)
     step_encode(t)
+    after_step()
 
   W = max(args.warmup, 3)
   K = args.steps
   for t in range(W):
     one_step(t)
   stats.zero_()
+  posted_total[0] = 0
   torch.cuda.synchronize()
   if dist:
     dist.barrier()
@@ -453,6 +480,7 @@ def main():
       select(W + t)
       e_a, e_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
       e_a.record(); step_encode(W + t); e_b.record()
+      after_step()
       pre_ev.append((e_a, e_b))
     torch.cuda.synchronize()
     graph_kernel_ms = sum(x.elapsed_time(y) for x, y in pre_ev) / len(pre_ev)
@@ -462,6 +490,7 @@ def main():
     for _ in range(3):
       step_graph.replay()
     stats.zero_()
+    posted_total[0] = 0
     torch.cuda.synchronize()
 
   sampler = ClockSampler(local_rank)
@@ -491,6 +520,7 @@ def main():
       k_ev[t][0].record()
       step_encode(W + t)
       k_ev[t][1].record()
+      after_step()
   sharding.reduce_episode_statistics(stats)  # the only collective: 256 B over NCCL (no-op at N=1)
   ev1.record()
   torch.cuda.synchronize()
@@ -689,6 +719,10 @@ def main():
   }
   if packed is not None:
     line["packed_obs"] = packed
+  if recorder is not None:
+    line["actor_loop"] = {"transitions_in_replay": memory.add_count, "replay_capacity": args.replay_capacity,
+                          "transitions_dropped": recorder.dropped,
+                          "note": "DeviceRecorder + DeviceReplayMemory inside the timed region"}
   if not args.no_cpu_baseline and world == 1:  # the CPU leg runs at N = 1 only
     line["cpu_baseline"] = cpu_reference_rate(args.workload, args.cpu_seconds)
     if args.python_baselines:

@@ -140,16 +140,18 @@ class DeviceRecorder(object):
         self._p(legal_mask, torch.uint8, "uint8_t*", self.N * self.A),
         self._p(action, torch.int32, "int32_t*", self.N), self._stream()), "RecorderBeforeStep")
 
-  def after_step(self, reward, done, priority=None):
-    """reward int32 [N], done uint8 [N]; returns the number of transitions appended to
-    the replay memory."""
+  def after_step(self, reward, done, priority=None, return_count=True):
+    """reward int32 [N], done uint8 [N].  Finished episodes go into the replay memory; the
+    whole update is driven from device memory (cursor and count never visit the host), so
+    with return_count=False the call is asynchronous and can be captured in a CUDA graph.
+    return_count=True synchronises once and returns the number of transitions appended."""
     torch = self._torch
     self._check(self._lib.RecorderAfterStep(
         self._c, self._p(reward, torch.int32, "int32_t*", self.N),
         self._p(done, torch.uint8, "uint8_t*", self.N), self.replay._c,  # pylint: disable=protected-access
-        -1.0 if priority is None else float(priority), self._posted, self._stream()),
-                "RecorderAfterStep")
-    return int(self._posted[0])
+        -1.0 if priority is None else float(priority),
+        self._posted if return_count else self._ffi.NULL, self._stream()), "RecorderAfterStep")
+    return int(self._posted[0]) if return_count else None
 
   @property
   def dropped(self):

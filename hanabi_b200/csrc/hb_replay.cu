@@ -50,6 +50,11 @@ struct Replay {
   float* legal = nullptr;
   double* tree = nullptr;  // heap layout: level l (2^l nodes) starts at 2^l - 1; leaves at level `depth`
   double max_recorded_priority = 1.0;
+  // Device copy of add_count ([0]) for appends that are driven entirely from the device
+  // (the recorder's asynchronous posting); `dirty` = the host value is behind it.
+  unsigned long long* d_counts = nullptr;
+  unsigned long long* h_counts = nullptr;  // pinned
+  bool dirty = false;
 };
 
 struct View {
@@ -133,6 +138,94 @@ __global__ void k_rebuild_level_range(double* tree, int depth, int l, int64_t ca
   const int64_t node = leaf >> (depth - l);
   const double* child = tree + (((int64_t)1 << (l + 1)) - 1);
   tree[((int64_t)1 << l) - 1 + node] = child[2 * node] + child[2 * node + 1];
+}
+// ---- the same updates with cursor and count read from device memory (no host round
+// trip): the leaf range [cursor, cursor + total) mod capacity is one or two contiguous
+// pieces; launches use a fixed grid and stride over whatever the device says.
+struct Pieces {
+  int64_t a[2], n[2];
+};
+__device__ __forceinline__ Pieces range_pieces(const unsigned long long* counts, const unsigned long long* total,
+                                               int64_t cap) {
+  Pieces p;
+  const int64_t cursor = (int64_t)(counts[0] % (unsigned long long)cap);
+  int64_t t = (int64_t)*total;
+  if (t > cap) t = cap;
+  p.a[0] = cursor; p.n[0] = t < cap - cursor ? t : cap - cursor;
+  p.a[1] = 0; p.n[1] = t - p.n[0];
+  return p;
+}
+__global__ void k_set_leaves_dev(double* tree, int depth, int64_t cap, const unsigned long long* counts,
+                                 const unsigned long long* total, double value) {
+  const Pieces p = range_pieces(counts, total, cap);
+  const int64_t t = p.n[0] + p.n[1];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < t; i += (int64_t)gridDim.x * blockDim.x)
+    tree[((int64_t)1 << depth) - 1 + (p.a[0] + i) % cap] = value;
+}
+__global__ void k_rebuild_span_dev(double* tree, int depth, int l, int64_t cap, const unsigned long long* counts,
+                                   const unsigned long long* total) {
+  const Pieces p = range_pieces(counts, total, cap);
+  const int sh = depth - l;
+  const double* child = tree + (((int64_t)1 << (l + 1)) - 1);
+  for (int piece = 0; piece < 2; ++piece) {
+    if (p.n[piece] <= 0) continue;
+    const int64_t first = p.a[piece] >> sh, cnt = ((p.a[piece] + p.n[piece] - 1) >> sh) - first + 1;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t node = first + i;
+      tree[((int64_t)1 << l) - 1 + node] = child[2 * node] + child[2 * node + 1];
+    }
+  }
+}
+__global__ void k_rebuild_top_dev(double* tree, int depth, int l_start, int64_t cap, const unsigned long long* counts,
+                                  const unsigned long long* total) {
+  const Pieces p = range_pieces(counts, total, cap);
+  if (p.n[0] + p.n[1] <= 0) return;
+  for (int l = l_start; l >= 0; --l) {
+    const int sh = depth - l;
+    const double* child = tree + (((int64_t)1 << (l + 1)) - 1);
+    for (int piece = 0; piece < 2; ++piece) {
+      if (p.n[piece] <= 0) continue;
+      const int64_t first = p.a[piece] >> sh, cnt = ((p.a[piece] + p.n[piece] - 1) >> sh) - first + 1;
+      for (int64_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+        const int64_t node = first + i;
+        tree[((int64_t)1 << l) - 1 + node] = child[2 * node] + child[2 * node + 1];
+      }
+    }
+    __syncthreads();
+  }
+}
+__global__ void k_commit_count(unsigned long long* counts, const unsigned long long* total, int64_t cap) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long t = *total;
+    if (t > (unsigned long long)cap) t = (unsigned long long)cap;
+    counts[0] += t;
+  }
+}
+__global__ void k_store_count(unsigned long long* counts, unsigned long long value) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) counts[0] = value;
+}
+
+// Contiguous leaf range: level l touches the contiguous nodes [first, first + count).
+__global__ void k_rebuild_span(double* tree, int l, int64_t first, int64_t count) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const int64_t node = first + i;
+  const double* child = tree + (((int64_t)1 << (l + 1)) - 1);
+  tree[((int64_t)1 << l) - 1 + node] = child[2 * node] + child[2 * node + 1];
+}
+// The upper levels of the same range (at most blockDim.x nodes each) in one launch:
+// one block walks from level l_start up to the root.
+__global__ void k_rebuild_top(double* tree, int depth, int l_start, int64_t first_leaf, int64_t last_leaf) {
+  for (int l = l_start; l >= 0; --l) {
+    const int sh = depth - l;
+    const int64_t first = first_leaf >> sh, count = (last_leaf >> sh) - first + 1;
+    const double* child = tree + (((int64_t)1 << (l + 1)) - 1);
+    for (int64_t i = threadIdx.x; i < count; i += blockDim.x) {
+      const int64_t node = first + i;
+      tree[((int64_t)1 << l) - 1 + node] = child[2 * node] + child[2 * node + 1];
+    }
+    __syncthreads();
+  }
 }
 __global__ void k_rebuild_level(double* tree, int depth, int l, const int32_t* indices, int count) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -228,8 +321,10 @@ struct RecView {
   float* since;      // [N][P]  reward since the seat's last action
   int32_t* run_len;  // [N][P]  snapshot of a finished game's episode lengths
   float* run_since;  // [N][P]
-  int32_t* lens;     // [N] transitions a game posts this step; scanned in place
+  int32_t* lens;     // [N][P] run lengths, scanned in place into the runs' offsets
   int32_t* block_sums;
+  int32_t* owner;    // [owner_cap] run (game * P + seat) of every transition posted this step
+  int64_t owner_cap;
   unsigned long long* total;    // transitions posted this step
   unsigned long long* dropped;  // transitions beyond L turns of a seat (never, for L = 64)
 };
@@ -256,7 +351,18 @@ __global__ void k_rec_before(RecView v, const int32_t* __restrict__ cur, const u
   uint4* dst = reinterpret_cast<uint4*>(v.obs + (gp * v.L + k) * v.W);
   for (int j = 0; j < v.W / 4; ++j) dst[j] = src[j];
   uint64_t legal = 0;
-  for (int a = 0; a < v.A; ++a) legal |= (uint64_t)(mask[(int64_t)g * v.A + a] != 0) << a;
+  const uint8_t* m = mask + (int64_t)g * v.A;
+  if ((v.A & 3) == 0 && (reinterpret_cast<uintptr_t>(mask) & 3) == 0) {
+    const uint32_t* m4 = reinterpret_cast<const uint32_t*>(m);
+    for (int j = 0; j < (v.A >> 2); ++j) {
+      uint32_t wv = m4[j];
+      wv |= wv >> 4; wv |= wv >> 2; wv |= wv >> 1;  // byte != 0 -> bit 0 of the byte
+      wv &= 0x01010101u;
+      legal |= (uint64_t)((wv * 0x10204080u) >> 28) << (4 * j);  // bits 0, 8, 16, 24 -> 4 bits
+    }
+  } else {
+    for (int a = 0; a < v.A; ++a) legal |= (uint64_t)(m[a] != 0) << a;
+  }
   v.legal[gp * v.L + k] = legal;
   v.action[gp * v.L + k] = actions[g];
   v.count[gp] = k + 1;
@@ -270,23 +376,21 @@ __global__ void k_rec_after(RecView v, const int32_t* __restrict__ rewards, cons
   if (g >= v.N) return;
   const float r = (float)rewards[g];
   const bool done = dones[g] != 0;
-  int total = 0;
   for (int p = 0; p < v.P; ++p) {
     const int64_t gp = (int64_t)g * v.P + p;
     const float s = v.since[gp] + r;
+    int k = 0;
     if (done) {
-      const int k = v.count[gp] < v.L ? v.count[gp] : v.L;
-      v.run_len[gp] = k;
+      k = v.count[gp] < v.L ? v.count[gp] : v.L;
       v.run_since[gp] = s;
       v.count[gp] = 0;
       v.since[gp] = 0.f;
-      total += k;
     } else {
       v.since[gp] = s;
-      v.run_len[gp] = 0;  // nothing to post for this seat
     }
+    v.run_len[gp] = k;
+    v.lens[gp] = k;
   }
-  v.lens[g] = total;
 }
 
 // Exclusive prefix sum of lens[N] in three small passes (1024 elements per block).
@@ -343,25 +447,53 @@ __global__ void k_scan_add(int32_t* data, int n, const int32_t* block_sums) {
   if (i < n) data[i] += block_sums[blockIdx.x];
 }
 
-// _post_transitions (dqn_agent.py:359-385) for the finished games: one warp per (game,
-// seat) writes the seat's episode as a contiguous run of replay slots -- runs ordered by
-// game, then seat -- (o_t, a_t, r_{t+1}, terminal, l_t); the last transition carries the
-// seat's pending reward and the terminal flag.  Slots are (cursor + offset) mod capacity.
-__global__ void k_rec_post(RecView v, int64_t cursor, int64_t cap, uint8_t* r_obs, int32_t* r_actions,
-                           float* r_rewards, uint8_t* r_terminals, float* r_legal) {
-  const int lane = threadIdx.x & 31;
-  const int64_t gp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+// Which run every posted transition belongs to: the non-empty runs write their index into
+// the slots [offset, offset + length) of the owner table.
+__global__ void k_rec_owner(RecView v) {
+  const int64_t gp = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gp >= (int64_t)v.N * v.P) return;
-  const int g = (int)(gp / v.P), p = (int)(gp - (int64_t)g * v.P);
   const int len = v.run_len[gp];
   if (len <= 0) return;
-  int64_t off = v.lens[g];  // exclusive prefix over games
-  for (int q = 0; q < p; ++q) off += v.run_len[(int64_t)g * v.P + q];
-  for (int k = 0; k < len; ++k) {
-    const int64_t slot = (cursor + off + k) % cap;
+  const int64_t off = v.lens[gp];
+  for (int k = 0; k < len; ++k)
+    if (off + k < v.owner_cap) v.owner[off + k] = (int32_t)gp;
+}
+
+// _post_transitions (dqn_agent.py:359-385) for the finished games: every seat's episode
+// becomes a contiguous run of replay slots -- runs ordered by game, then seat -- of
+// (o_t, a_t, r_{t+1}, terminal, l_t); the last transition carries the seat's pending
+// reward and the terminal flag.  One warp per posted transition (strided over a fixed
+// grid; cursor and count come from device memory): it expands the packed observation row
+// into the ring's uint8 row with 32-bit stores and writes the scalars.
+__global__ void k_rec_post(RecView v, const unsigned long long* counts, int64_t cap, uint8_t* r_obs,
+                           int32_t* r_actions, float* r_rewards, uint8_t* r_terminals, float* r_legal) {
+  const int lane = threadIdx.x & 31;
+  int64_t total = (int64_t)*v.total;
+  if (total > cap) total = cap;  // more than the ring holds: the tail is dropped (never in practice)
+  if (total > v.owner_cap) total = v.owner_cap;
+  const int64_t cursor = (int64_t)(counts[0] % (unsigned long long)cap);
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < total; w += n_warps) {
+    const int64_t gp = v.owner[w];
+    const int k = (int)(w - v.lens[gp]);
+    const int len = v.run_len[gp];
+    const int64_t slot = (cursor + w) % cap;
     const uint32_t* row = v.obs + (gp * v.L + k) * v.W;
     uint8_t* dst = r_obs + slot * v.D;
-    for (int b = lane; b < v.D; b += 32) dst[b] = (uint8_t)((row[b >> 5] >> (b & 31)) & 1u);
+    // bytes up to the first 4-byte boundary, then whole words, then the tail
+    const int lead = (int)((4 - (reinterpret_cast<uintptr_t>(dst) & 3)) & 3);
+    const int head = lead < v.D ? lead : v.D;
+    if (lane < head) dst[lane] = (uint8_t)((row[0] >> lane) & 1u);
+    const int words = (v.D - head) >> 2;
+    uint32_t* dst4 = reinterpret_cast<uint32_t*>(dst + head);
+    for (int j = lane; j < words; j += 32) {
+      const int bit = head + 4 * j;  // 4 consecutive bits, possibly across two row words
+      const int wi = bit >> 5;
+      const uint32_t lo = row[wi], hi = row[(wi + 1 < v.W && (bit & 31) > 28) ? wi + 1 : wi];
+      const uint32_t four = __funnelshift_r(lo, hi, bit & 31) & 15u;
+      dst4[j] = (four * 0x00204081u) & 0x01010101u;
+    }
+    for (int b = head + 4 * words + lane; b < v.D; b += 32) dst[b] = (uint8_t)((row[b >> 5] >> (b & 31)) & 1u);
     const uint64_t legal = v.legal[gp * v.L + k];
     for (int a = lane; a < v.A; a += 32)
       r_legal[slot * v.A + a] = ((legal >> a) & 1ull) ? 0.f : -CUDART_INF_F;  // format_legal_moves
@@ -407,10 +539,22 @@ int Check(cudaError_t e, const char* what) {
   do {                                       \
     if (Check((expr), #expr)) return 1;      \
   } while (0)
+// Brings the host's add_count up to date after device-driven appends.
+int SyncAddCount(Replay* r) {
+  if (!r->dirty) return 0;
+  cudaError_t e = cudaDeviceSynchronize();  // the appends may sit on any (non-blocking) stream
+  if (e == cudaSuccess)
+    e = cudaMemcpy(r->h_counts, r->d_counts, sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) return Check(e, "replay add_count read-back");
+  r->add_count = (int64_t)r->h_counts[0];
+  r->dirty = false;
+  return 0;
+}
 #define HBR_REPLAY(h)                                             \
   if (!(h) || !(h)->replay) return HbFail("null replay handle");  \
   Replay* r = static_cast<Replay*>((h)->replay);                  \
-  Guard guard__(r->device)
+  Guard guard__(r->device);                                       \
+  if (SyncAddCount(r)) return 1
 }  // namespace
 
 extern "C" {
@@ -438,7 +582,8 @@ int NewReplay(pyhanabi_replay_t* out, int num_actions, int observation_size, int
   const size_t cap = (size_t)capacity;
   auto fail = [&](const char* what, cudaError_t e) {
     cudaFree(r->obs); cudaFree(r->actions); cudaFree(r->rewards); cudaFree(r->terminals);
-    cudaFree(r->legal); cudaFree(r->tree);
+    cudaFree(r->legal); cudaFree(r->tree); cudaFree(r->d_counts);
+    if (r->h_counts) cudaFreeHost(r->h_counts);
     delete r;
     return Check(e, what);
   };
@@ -452,6 +597,9 @@ int NewReplay(pyhanabi_replay_t* out, int num_actions, int observation_size, int
   // the tree buffer also hosts the int32 "last writer" scratch behind the nodes
   if ((e = cudaMalloc(&r->tree, nodes * sizeof(double) + ((size_t)1 << r->depth) * sizeof(int32_t))) != cudaSuccess)
     return fail("cudaMalloc tree", e);
+  if ((e = cudaMalloc(&r->d_counts, 2 * sizeof(unsigned long long))) != cudaSuccess) return fail("cudaMalloc counters", e);
+  if ((e = cudaMallocHost(&r->h_counts, 2 * sizeof(unsigned long long))) != cudaSuccess) return fail("cudaMallocHost counters", e);
+  cudaMemset(r->d_counts, 0, 2 * sizeof(unsigned long long));
   cudaMemset(r->obs, 0, cap * (size_t)observation_size);
   cudaMemset(r->actions, 0, cap * sizeof(int32_t));
   cudaMemset(r->rewards, 0, cap * sizeof(float));
@@ -469,20 +617,44 @@ void DeleteReplay(pyhanabi_replay_t* h) {
   Replay* r = static_cast<Replay*>(h->replay);
   Guard guard(r->device);
   cudaFree(r->obs); cudaFree(r->actions); cudaFree(r->rewards); cudaFree(r->terminals);
-  cudaFree(r->legal); cudaFree(r->tree);
+  cudaFree(r->legal); cudaFree(r->tree); cudaFree(r->d_counts);
+  if (r->h_counts) cudaFreeHost(r->h_counts);
   delete r;
   h->replay = nullptr;
 }
 
-int64_t ReplayAddCount(pyhanabi_replay_t* h) { return (h && h->replay) ? static_cast<Replay*>(h->replay)->add_count : -1; }
+int64_t ReplayAddCount(pyhanabi_replay_t* h) {
+  if (!h || !h->replay) return -1;
+  Replay* r = static_cast<Replay*>(h->replay);
+  Guard guard(r->device);
+  if (SyncAddCount(r)) return -1;
+  return r->add_count;
+}
 int64_t ReplayCapacity(pyhanabi_replay_t* h) { return (h && h->replay) ? static_cast<Replay*>(h->replay)->cap : -1; }
 double ReplayMaxRecordedPriority(pyhanabi_replay_t* h) {
   return (h && h->replay) ? static_cast<Replay*>(h->replay)->max_recorded_priority : -1.0;
 }
 
+// Parents of the leaves [cursor, cursor + count) mod capacity: the range is one or two
+// contiguous leaf spans; per level the touched nodes are contiguous too, and once a
+// level has at most 1024 of them one block finishes the walk to the root.
 static int RebuildRange(Replay* r, int64_t cursor, int count, cudaStream_t s) {
-  for (int l = r->depth - 1; l >= 0; --l) {
-    hbr::k_rebuild_level_range<<<(count + 255) / 256, 256, 0, s>>>(r->tree, r->depth, l, r->cap, cursor, count);
+  const int64_t first_len = (cursor + count <= r->cap) ? count : (r->cap - cursor);
+  for (int piece = 0; piece < 2; ++piece) {
+    const int64_t a = piece == 0 ? cursor : 0;
+    const int64_t n = piece == 0 ? first_len : count - first_len;
+    if (n <= 0) continue;
+    const int64_t b = a + n - 1;
+    for (int l = r->depth - 1; l >= 0; --l) {
+      const int sh = r->depth - l;
+      const int64_t first = a >> sh, cnt = (b >> sh) - first + 1;
+      if (cnt > 1024) {
+        hbr::k_rebuild_span<<<(unsigned)((cnt + 255) / 256), 256, 0, s>>>(r->tree, l, first, cnt);
+      } else {
+        hbr::k_rebuild_top<<<1, 1024, 0, s>>>(r->tree, r->depth, l, a, b);
+        break;
+      }
+    }
   }
   return Check(cudaGetLastError(), "sum tree rebuild");
 }
@@ -512,6 +684,7 @@ int ReplayAdd(pyhanabi_replay_t* h, const uint8_t* obs, const int32_t* actions, 
       HBR_CUDA(cudaMemcpyAsync(r->terminals + dst, terminals + src, (size_t)cnt, cudaMemcpyDeviceToDevice, s));
     }
     r->add_count += part;
+    hbr::k_store_count<<<1, 1, 0, s>>>(r->d_counts, (unsigned long long)r->add_count);
     if (r->prioritized) {
       const double p = priority < 0.f ? 100.0 : (double)priority;  // DEFAULT_PRIORITY
       if (p > r->max_recorded_priority) r->max_recorded_priority = p;
@@ -594,6 +767,7 @@ struct Recorder {
   int device = 0;
   hbr::RecView v;
   int nblocks = 0;
+  int sm_count = 148;
   unsigned long long* h_total = nullptr;  // pinned
 };
 
@@ -610,12 +784,13 @@ int NewRecorder(pyhanabi_recorder_t* out, int num_games, int num_players, int ob
   Recorder* r = new Recorder;
   r->device = device;
   Guard guard(device);
+  cudaDeviceGetAttribute(&r->sm_count, cudaDevAttrMultiProcessorCount, device);
   hbr::RecView& v = r->v;
   std::memset(&v, 0, sizeof(v));
   v.N = num_games; v.P = num_players; v.L = max_turns_per_seat; v.A = num_actions; v.D = observation_size;
   v.W = 4 * ((observation_size + 127) / 128);
   const size_t NP = (size_t)v.N * v.P, NPL = NP * v.L;
-  r->nblocks = (v.N + 1023) / 1024;
+  r->nblocks = (int)((NP + 1023) / 1024);
   cudaError_t e = cudaSuccess;
   auto alloc = [&](void** p, size_t bytes) {
     if (e == cudaSuccess) e = cudaMalloc(p, bytes);
@@ -629,8 +804,10 @@ int NewRecorder(pyhanabi_recorder_t* out, int num_games, int num_players, int ob
   alloc((void**)&v.since, NP * sizeof(float));
   alloc((void**)&v.run_len, NP * sizeof(int32_t));
   alloc((void**)&v.run_since, NP * sizeof(float));
-  alloc((void**)&v.lens, (size_t)v.N * sizeof(int32_t));
+  alloc((void**)&v.lens, NP * sizeof(int32_t));
   alloc((void**)&v.block_sums, (size_t)r->nblocks * sizeof(int32_t));
+  v.owner_cap = (int64_t)(NPL < ((size_t)1 << 26) ? NPL : ((size_t)1 << 26));
+  alloc((void**)&v.owner, (size_t)v.owner_cap * sizeof(int32_t));
   alloc((void**)&v.total, sizeof(unsigned long long));
   alloc((void**)&v.dropped, sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMallocHost((void**)&r->h_total, 2 * sizeof(unsigned long long));
@@ -650,7 +827,7 @@ void DeleteRecorder(pyhanabi_recorder_t* h) {
   hbr::RecView& v = r->v;
   cudaFree(v.obs); cudaFree(v.legal); cudaFree(v.action); cudaFree(v.reward); cudaFree(v.count);
   cudaFree(v.since); cudaFree(v.run_len); cudaFree(v.run_since); cudaFree(v.lens);
-  cudaFree(v.block_sums); cudaFree(v.total); cudaFree(v.dropped);
+  cudaFree(v.block_sums); cudaFree(v.owner); cudaFree(v.total); cudaFree(v.dropped);
   if (r->h_total) cudaFreeHost(r->h_total);
   delete r;
   h->recorder = nullptr;
@@ -690,28 +867,34 @@ int RecorderAfterStep(pyhanabi_recorder_t* h, const int32_t* rewards, const uint
   cudaStream_t s = (cudaStream_t)stream;
   hbr::RecView& v = rec->v;
   hbr::k_rec_after<<<(v.N + 127) / 128, 128, 0, s>>>(v, rewards, dones);
-  hbr::k_scan_blocks<<<rec->nblocks, 1024, 0, s>>>(v.lens, v.N, v.block_sums);
+  const int np = v.N * v.P;
+  hbr::k_scan_blocks<<<rec->nblocks, 1024, 0, s>>>(v.lens, np, v.block_sums);
   hbr::k_scan_sums<<<1, 1024, 0, s>>>(v.block_sums, rec->nblocks, v.total);
-  hbr::k_scan_add<<<rec->nblocks, 1024, 0, s>>>(v.lens, v.N, v.block_sums);
+  hbr::k_scan_add<<<rec->nblocks, 1024, 0, s>>>(v.lens, np, v.block_sums);
   HBR_CUDA(cudaGetLastError());
-  HBR_CUDA(cudaMemcpyAsync(rec->h_total, v.total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
-  HBR_CUDA(cudaStreamSynchronize(s));
-  const int64_t total = (int64_t)rec->h_total[0];
-  if (posted) *posted = total;
-  if (total == 0) return 0;
-  if (total > r->cap) return HbFail("RecorderAfterStep: more transitions in one step than the replay capacity");
-  const int64_t cursor = r->add_count % r->cap;
-  const int64_t warps = (int64_t)v.N * v.P;
-  hbr::k_rec_post<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, s>>>(v, cursor, r->cap, r->obs, r->actions,
-                                                                       r->rewards, r->terminals, r->legal);
-  HBR_CUDA(cudaGetLastError());
-  r->add_count += total;
+  // everything below reads the cursor and the count from device memory: fixed launch
+  // geometry, no host round trip, capturable in a CUDA graph
+  const int sms = rec->sm_count;
+  hbr::k_rec_owner<<<(unsigned)((np + 255) / 256), 256, 0, s>>>(v);
+  hbr::k_rec_post<<<sms * 16, 256, 0, s>>>(v, r->d_counts, r->cap, r->obs, r->actions, r->rewards,
+                                           r->terminals, r->legal);
   if (r->prioritized) {
     const double p = priority < 0.f ? 100.0 : (double)priority;  // DEFAULT_PRIORITY
     if (p > r->max_recorded_priority) r->max_recorded_priority = p;
-    hbr::k_set_leaves_range<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(r->tree, r->depth, r->cap, cursor, (int)total, p);
-    HBR_CUDA(cudaGetLastError());
-    if (RebuildRange(r, cursor, (int)total, s)) return 1;
+    hbr::k_set_leaves_dev<<<sms * 2, 256, 0, s>>>(r->tree, r->depth, r->cap, r->d_counts, v.total, p);
+    // wide levels with strided grids, then one block walks the narrow ones to the root
+    int l = r->depth - 1;
+    for (; l >= 0 && (r->depth - l) <= 6; --l)
+      hbr::k_rebuild_span_dev<<<sms, 256, 0, s>>>(r->tree, r->depth, l, r->cap, r->d_counts, v.total);
+    if (l >= 0) hbr::k_rebuild_top_dev<<<1, 1024, 0, s>>>(r->tree, r->depth, l, r->cap, r->d_counts, v.total);
+  }
+  hbr::k_commit_count<<<1, 1, 0, s>>>(r->d_counts, v.total, r->cap);
+  HBR_CUDA(cudaGetLastError());
+  r->dirty = true;
+  if (posted) {  // the caller wants the number now: one synchronisation
+    HBR_CUDA(cudaMemcpyAsync(rec->h_total, v.total, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+    HBR_CUDA(cudaStreamSynchronize(s));
+    *posted = (int64_t)rec->h_total[0];
   }
   return 0;
 }
