@@ -223,9 +223,12 @@ template <> __device__ __forceinline__ float2 unpack2<__half>(uint32_t w) {
 
 // sum_i e_i and sum_i e_i * support_i over one action's atoms, e_i = 2^(v_i * log2e + nm),
 // from the staged row.  s_sup[0..63] = support, s_sup[64..127] = support shifted by one.
-template <class T>
+// KA > 0: the number of atoms is the compile-time constant KA (the usual 51), so the loops
+// unroll completely; KA == 0: taken from `atoms`.
+template <class T, int KA>
 __device__ __forceinline__ void action_sums(const T* row, int start, int atoms, float nm,
                                             const float* s_sup, float& se, float& sw) {
+  if (KA > 0) atoms = KA;
   constexpr float kL2e = 1.4426950408889634f;
   se = 0.f; sw = 0.f;
   if (sizeof(T) == 4) {
@@ -246,8 +249,9 @@ __device__ __forceinline__ void action_sums(const T* row, int start, int atoms, 
     }
     w += odd;
     const float2* sp = reinterpret_cast<const float2*>(s_sup + (odd ? 64 : 0));
-    const int pairs = (atoms - odd) >> 1;
-#pragma unroll 5
+    // an odd atom count gives the same number of whole pairs for either alignment
+    const int pairs = (KA > 0 && (KA & 1)) ? (KA >> 1) : ((atoms - odd) >> 1);
+#pragma unroll
     for (int j = 0; j < pairs; ++j) {
       const float2 v = unpack2<typename std::conditional<sizeof(T) == 4, __half, T>::type>(w[j]);
       const float2 sv = sp[j];
@@ -272,7 +276,7 @@ __device__ __forceinline__ void action_sums(const T* row, int start, int atoms, 
 // underflow against M is redone against its own maximum.
 // Needs 16-byte aligned rows (base and pitch) and atoms <= 63;
 // smem: 128 floats + warps * row_smem_bytes.
-template <class T>
+template <class T, int KA>
 __global__ void k_select_c51_rows(const T* __restrict__ logits, int64_t row_pitch,
                                   const float* __restrict__ support,
                                   const uint8_t* __restrict__ mask, int n, int A, int atoms,
@@ -328,11 +332,11 @@ __global__ void k_select_c51_rows(const T* __restrict__ logits, int64_t row_pitc
     n_legal += legal;
     if (!legal && q_out == nullptr) continue;
     float se, sw;
-    action_sums<T>(row, a * atoms, atoms, nm, s_sup, se, sw);
+    action_sums<T, KA>(row, a * atoms, atoms, nm, s_sup, se, sw);
     if (!(se > 0.f)) {  // everything underflowed against the row maximum
       float am = -CUDART_INF_F;
       for (int i = 0; i < atoms; ++i) am = fmaxf(am, to_f32<T>(row[a * atoms + i]));
-      action_sums<T>(row, a * atoms, atoms, -am * 1.4426950408889634f, s_sup, se, sw);
+      action_sums<T, 0>(row, a * atoms, atoms, -am * 1.4426950408889634f, s_sup, se, sw);
     }
     const float qa = sw / se;
     if (q_out) q_out[(int64_t)g * A + a] = qa;
@@ -389,18 +393,22 @@ template <> struct Vec8<__half> {
 template <class T>
 __global__ void k_expand_bits(const uint32_t* __restrict__ bits, int packed_words, int obs_size,
                               int64_t n, T* __restrict__ out, int64_t row_pitch) {
-  const int groups = (int)(row_pitch >> 3);  // row_pitch is a multiple of 8
+  // one thread per 32 bits of a row: one word load, four (16-bit types) or eight
+  // (float32) independent 128-bit stores; a ragged last group of 8 when the pitch is
+  // not a multiple of 32
+  const int words = (int)((row_pitch + 31) >> 5);
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n * groups) return;
-  const int64_t g = idx / groups;
-  const int j = (int)(idx - g * groups);
-  uint32_t b = 0;
-  if (8 * j < obs_size) {
-    b = (bits[g * packed_words + (j >> 2)] >> (8 * (j & 3))) & 0xffu;
-    const int rem = obs_size - 8 * j;
-    if (rem < 8) b &= (1u << rem) - 1u;
-  }
-  Vec8<T>::store(out + g * row_pitch + 8 * j, b);
+  if (idx >= n * words) return;
+  const int64_t g = idx / words;
+  const int j = (int)(idx - g * words);
+  uint32_t w = j < packed_words ? __ldcs(bits + g * packed_words + j) : 0u;
+  const int rem = obs_size - 32 * j;
+  if (rem < 32) w = rem > 0 ? (w & ((1u << rem) - 1u)) : 0u;
+  T* dst = out + g * row_pitch + 32 * j;
+  const int groups = (int)((row_pitch - 32 * j) >> 3) < 4 ? (int)((row_pitch - 32 * j) >> 3) : 4;
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    if (q < groups) Vec8<T>::store(dst + 8 * q, (w >> (8 * q)) & 0xffu);
 }
 
 // project_distribution, one warp per batch row, op for op in fp32:
@@ -511,9 +519,14 @@ cudaError_t LaunchSelectC51(const T* logits, int64_t row_pitch, const float* sup
   const size_t row_bytes = (((size_t)A * atoms * sizeof(T)) + 15) / 16 * 16;
   const bool aligned = (reinterpret_cast<uintptr_t>(logits) & 15) == 0 && ((row_pitch * sizeof(T)) & 15) == 0;
   if (aligned && atoms <= 63 && 512 + 8 * row_bytes <= 48 * 1024) {
-    hbp::k_select_c51_rows<T><<<grid, 256, 512 + 8 * row_bytes, s>>>(logits, row_pitch, support, mask, n, A, atoms,
-                                                               epsilon, seed, step, actions, nullptr,
-                                                               (int)row_bytes);
+    if (atoms == 51)
+      hbp::k_select_c51_rows<T, 51><<<grid, 256, 512 + 8 * row_bytes, s>>>(logits, row_pitch, support, mask, n, A,
+                                                                          atoms, epsilon, seed, step, actions,
+                                                                          nullptr, (int)row_bytes);
+    else
+      hbp::k_select_c51_rows<T, 0><<<grid, 256, 512 + 8 * row_bytes, s>>>(logits, row_pitch, support, mask, n, A,
+                                                                         atoms, epsilon, seed, step, actions,
+                                                                         nullptr, (int)row_bytes);
   } else {
     hbp::k_select_c51<T><<<grid, 256, 0, s>>>(logits, row_pitch, support, mask, n, A, atoms, epsilon, seed,
                                               step, actions, nullptr);
@@ -588,7 +601,7 @@ int BatchExpandPacked(const uint32_t* obs_bits, int packed_words, int obs_size, 
   if (row_pitch < obs_size || (row_pitch & 7)) return PFail("BatchExpandPacked: row_pitch must be >= obs_size and a multiple of 8");
   if (reinterpret_cast<uintptr_t>(out) & 15) return PFail("BatchExpandPacked: out must be 16-byte aligned");
   cudaStream_t s = (cudaStream_t)stream;
-  const int64_t threads = (int64_t)n * (row_pitch >> 3);
+  const int64_t threads = (int64_t)n * ((row_pitch + 31) >> 5);
   const unsigned grid = (unsigned)((threads + 255) / 256);
   switch (dtype) {
     case 0: hbp::k_expand_bits<float><<<grid, 256, 0, s>>>(obs_bits, packed_words, obs_size, n, static_cast<float*>(out), row_pitch); break;

@@ -177,7 +177,7 @@ def test_expand_packed_and_c51_select_on_gemm_outputs(dtype_name):
   ph.expand_packed(bits, D, x)
   assert torch.equal(x[:, :D].float(), obs.float()) and not x[:, D:].any()
   # a wider pitch: every column from obs_size up to the pitch is zeroed
-  wide = torch.full((n, K + 32), 7, dtype=dt, device=dev)
+  wide = torch.full((n, K + 8), 7, dtype=dt, device=dev)  # pitch not a multiple of 32
   ph.expand_packed(bits, D, wide)
   assert torch.equal(wide[:, :D].float(), obs.float()) and not wide[:, D:].any()
   atoms = 51
