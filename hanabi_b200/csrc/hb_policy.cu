@@ -399,7 +399,9 @@ __global__ void k_expand_bits(const uint32_t* __restrict__ bits, int packed_word
   const int words = (int)((row_pitch + 31) >> 5);
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n * words) return;
-  const int64_t g = idx / words;
+  int64_t g;
+  if (n * words < 0x7fffffffll) g = (int64_t)((uint32_t)idx / (uint32_t)words);  // 32-bit divide
+  else g = idx / words;
   const int j = (int)(idx - g * words);
   uint32_t w = j < packed_words ? __ldcs(bits + g * packed_words + j) : 0u;
   const int rem = obs_size - 32 * j;
