@@ -363,9 +363,8 @@ def main():
     select = ph.bind_select_action(None, mask, 1.0, seed=7, out=act)
   else:
     # Rainbow actor (agents/rainbow_copy/rainbow_agent.py:36-68,163-172): MLP
-    # obs_dim -> 512 -> A x 51 with fixed random weights.  The step kernel writes
-    # bit-packed observation rows, BatchExpandPacked turns them into the first GEMM's
-    # input (0/1 in the GEMM's element type, K zero-padded to a multiple of 32), the two
+    # obs_dim -> 512 -> A x 51 with fixed random weights.  The step kernel writes the first
+    # GEMM's input (0/1 in the GEMM's element type, K zero-padded to a multiple of 32), the two
     # GEMMs are library calls (cuBLASLt through torch; bias + ReLU in the first one's
     # epilogue), and BatchSelectActionC51 reads the N-padded logits in place:
     # softmax . support, legal mask, argmax.
@@ -387,14 +386,21 @@ def main():
     bits = torch.empty((n, batch.packed_words), dtype=torch.int32, device=dev)
     x = torch.empty((n, Kp), dtype=tdt, device=dev)
     logits = torch.empty((n, Np), dtype=tdt, device=dev)
-    batch.observe_packed(bits)
-    expand = ph.bind_expand_packed(bits, D, x)
+    # the step kernel writes the first GEMM's input itself (BatchStepEncodeNet); the packed
+    # rows ride along for the recorder
+    want_bits = args.record or args.policy == "adhoc"
+    batch.observe_net(x, obs_bits=bits if want_bits else None)
     greedy = ph.bind_select_action_c51(logits, atoms, mask, 0.0, seed=7, out=act, support=support)
-    step_encode = lambda t: batch.step_encode_packed(act, rew, done, bits, mask, cur)
-    launches_per_step = 3  # ours: step, expand, select (+ 2 library GEMMs)
+    if args.policy == "adhoc" and not adhoc_all_rows:
+      # the gathered-rows mode expands only the Rainbow seat's rows: packed rows suffice
+      step_encode = lambda t: batch.step_encode_packed(act, rew, done, bits, mask, cur)
+    else:
+      step_encode = lambda t: batch.step_encode_net(act, x, rew, done,
+                                                    obs_bits=bits if want_bits else None,
+                                                    mask=mask, cur_player=cur)
+    launches_per_step = 2  # ours: step (+ network input), select (+ 2 library GEMMs)
 
     def rainbow(t):
-      expand()
       h = torch._addmm_activation(b1, x, w1)  # relu(x @ w1 + b1), one cuBLASLt call
       torch.addmm(b2, h, w2, out=logits)
       greedy(t)
@@ -407,7 +413,7 @@ def main():
       memory = replay_mod.DeviceReplayMemory(A, D, args.replay_capacity, update_horizon=1, gamma=0.99,
                                              device=local_rank)
       recorder = actor.DeviceRecorder(n, batch.num_players, D, A, memory, device=local_rank)
-      launches_per_step = 9  # + record, 3 scan passes, post, 2 sum-tree kernels (first level)
+      launches_per_step = 18  # + record, after, 3 scan passes, owner, post, leaves, 6 + 1 tree levels, commit
 
       def select(t):
         rainbow(t)
@@ -420,10 +426,10 @@ def main():
       batch.enable_history()
       batch.reset()
       batch.observe(obs, mask, cur)
-      batch.observe_packed(bits)
+      batch.observe_net(x, obs_bits=bits)
       agent_state = torch.zeros((n, 1), dtype=torch.int32, device=dev)
       seat_mask = sum(1 << s for s in range(1, batch.num_players))
-      launches_per_step = 4
+      launches_per_step = 3
 
       def select_all(t):
         rainbow(t)
@@ -693,8 +699,9 @@ def main():
                             "(BatchStepEncodeRandom)" if fused_policy else
                             "uniform random legal (BatchSelectAction, epsilon=1)"
                             if args.policy == "random" else
-                            "Rainbow C51 MLP %d->512->%dx51 (cuBLASLt %s GEMMs via torch) on "
-                            "BatchExpandPacked input + BatchSelectActionC51 (epsilon=0)"
+                            "Rainbow C51 MLP %d->512->%dx51 (cuBLASLt %s GEMMs via torch) on the "
+                            "step kernel's own network-input rows (BatchStepEncodeNet) + "
+                            "BatchSelectActionC51 (epsilon=0)"
                             % (D, A, args.mlp_dtype) +
                             ("; seats 1.. = batched RuleBasedAgent (BatchAgentAct); MLP on %s"
                              % ("all games" if adhoc_all_rows else

@@ -69,6 +69,12 @@ struct KArgs {
   uint8_t* obs;
   int64_t obs_pitch;
   uint32_t* obs_bits;  // alternative to obs: bit-packed rows of packed_words 32-bit words
+  // alternative to obs, may accompany obs_bits: the network's input rows, 0/1 elements of
+  // net_dtype (0 float32, 1 bfloat16, 2 float16), net_pitch elements per row (multiple of 8)
+  void* net_in;
+  int net_dtype, net_chunks, net_lut_offset_words;
+  uint32_t net_magic;
+  int64_t net_pitch;
   int packed_words;
   uint8_t* mask;
   // optional fused random policy: after the step, a uniformly random legal move of the
@@ -94,7 +100,9 @@ struct KArgs {
 //   B  the first n threads of the CTA draw the initial deals of the n queued games
 //   C  install new games, store state, encode observation + legal mask into the
 //      warp's packed bit stream, expand to bytes with 128-bit stores
-template <class V, int MODE>
+// NET: the instantiation that also writes network-input rows (BatchStepEncodeNet /
+// BatchObserveNet); kept out of the plain kernels so that their code stays as small as it was.
+template <class V, int MODE, bool NET = false>
 __global__ void __launch_bounds__(kBlock, (MODE == kModeStep) ? HB_MIN_CTAS_STEP : HB_MIN_CTAS) k_main(const __grid_constant__ KArgs a) {
   extern __shared__ uint32_t smem[];
   __shared__ int s_stats[kNumStats];
@@ -103,6 +111,20 @@ __global__ void __launch_bounds__(kBlock, (MODE == kModeStep) ? HB_MIN_CTAS_STEP
   __shared__ int s_q_mti[kQueueCap];
   __shared__ ResetResult s_res[kQueueCap];
   __shared__ uint32_t s_spread[32];
+  // byte -> its eight 16-bit elements: 4 KB of dynamic shared memory that only the launches
+  // writing network-input rows ask for
+  uint4* s_net_lut = reinterpret_cast<uint4*>(smem + a.net_lut_offset_words);
+  if (NET) {
+    const uint32_t one = a.net_dtype == 2 ? 0x3c00u : 0x3f80u;  // float16 / bfloat16 (and float32 >> 16)
+    for (int b = threadIdx.x; b < 256; b += kBlock) {
+      uint4 e;
+      e.x = ((b & 1) ? one : 0u) | ((b & 2) ? one << 16 : 0u);
+      e.y = ((b & 4) ? one : 0u) | ((b & 8) ? one << 16 : 0u);
+      e.z = ((b & 16) ? one : 0u) | ((b & 32) ? one << 16 : 0u);
+      e.w = ((b & 64) ? one : 0u) | ((b & 128) ? one << 16 : 0u);
+      s_net_lut[b] = e;
+    }
+  }
 #if HB_EXPAND_LUT
   __shared__ uint2 s_lut[256];
   for (int i = threadIdx.x; i < 256; i += kBlock)
@@ -375,10 +397,10 @@ __global__ void __launch_bounds__(kBlock, (MODE == kModeStep) ? HB_MIN_CTAS_STEP
   const int n_valid = (int)((a.g_end - tile0) < 32 ? (a.g_end - tile0) : 32);
   uint32_t* obs_stream = smem + (size_t)warp * a.warp_smem_words;
   uint32_t* mask_stream = obs_stream + a.obs_stream_words + kStreamPad;
-  if (a.obs || a.obs_bits) {
+  if (a.obs || a.obs_bits || NET) {
     const int observer = a.observer < 0 ? G.cur : a.observer;
     encode_obs(v, a.spec, G, observer, obs_stream, lane, s_spread,
-               a.obs_bits ? a.packed_words * 32 : a.spec.obs_size);
+               (a.obs_bits || NET) ? a.packed_words * 32 : a.spec.obs_size);
   }
   if (a.mask || a.random_actions) {
     const uint64_t legal = legal_bits(v, G);
@@ -395,6 +417,11 @@ __global__ void __launch_bounds__(kBlock, (MODE == kModeStep) ? HB_MIN_CTAS_STEP
                   lane, lut);
   if (a.obs_bits)
     store_packed_rows(obs_stream, a.packed_words, a.obs_bits + tile0 * a.packed_words, n_valid, lane);
+  if (NET) {
+    const int esz = a.net_dtype == 0 ? 4 : 2;
+    expand_net_rows(obs_stream, a.packed_words, static_cast<uint8_t*>(a.net_in) + tile0 * a.net_pitch * esz,
+                    a.net_pitch, a.net_chunks, a.net_magic, n_valid, lane, s_net_lut, a.net_dtype == 0);
+  }
   if (a.mask)
     expand_stream(mask_stream, a.spec.max_moves, a.mask + tile0 * a.spec.max_moves,
                   a.spec.max_moves, n_valid, lane);
@@ -690,27 +717,28 @@ hb::KArgs BaseArgs(const Batch* b) {
   return a;
 }
 
-template <class V, int MODE>
-cudaError_t LaunchOne(const Batch* b, const hb::KArgs& a, cudaStream_t stream) {
+template <class V, int MODE, bool NET>
+cudaError_t LaunchKernel(const Batch* b, const hb::KArgs& a, cudaStream_t stream) {
   const unsigned grid = (unsigned)((a.g_end - a.g_begin + hb::kBlock - 1) / hb::kBlock);
   static size_t allowed[16] = {0};  // per device: dynamic shared memory already opted in
   const int dev = b->device & 15;
-  if (b->smem_bytes > allowed[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(hb::k_main<V, MODE>,
+  const size_t smem_bytes = a.net_in ? (size_t)a.net_lut_offset_words * 4 + 256 * sizeof(uint4) : b->smem_bytes;
+  if (smem_bytes > allowed[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(hb::k_main<V, MODE, NET>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)b->smem_bytes);
+                                         (int)smem_bytes);
     if (e != cudaSuccess) return e;
-    allowed[dev] = b->smem_bytes;
+    allowed[dev] = smem_bytes;
   }
   if (b->l2_window_bytes == 0) {
-    hb::k_main<V, MODE><<<grid, hb::kBlock, b->smem_bytes, stream>>>(a);
+    hb::k_main<V, MODE, NET><<<grid, hb::kBlock, smem_bytes, stream>>>(a);
     return cudaGetLastError();
   }
   cudaLaunchConfig_t cfg;
   std::memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(hb::kBlock);
-  cfg.dynamicSmemBytes = b->smem_bytes;
+  cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr;
   std::memset(&attr, 0, sizeof(attr));
@@ -722,7 +750,13 @@ cudaError_t LaunchOne(const Batch* b, const hb::KArgs& a, cudaStream_t stream) {
   attr.val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
   cfg.attrs = &attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, hb::k_main<V, MODE>, a);
+  return cudaLaunchKernelEx(&cfg, hb::k_main<V, MODE, NET>, a);
+}
+
+template <class V, int MODE>
+cudaError_t LaunchOne(const Batch* b, const hb::KArgs& a, cudaStream_t stream) {
+  if (a.net_in != nullptr && MODE != hb::kModeReset) return LaunchKernel<V, MODE, MODE != hb::kModeReset>(b, a, stream);
+  return LaunchKernel<V, MODE, false>(b, a, stream);
 }
 
 template <int MODE>
@@ -1171,6 +1205,52 @@ int BatchStepEncodePacked(pyhanabi_batch_t* h, const int32_t* actions, int32_t* 
   a.actions = actions; a.rewards = rewards; a.dones = dones; a.scores = scores;
   a.obs_bits = obs_bits; a.mask = mask; a.cur_player = cur_player; a.auto_reset = auto_reset;
   HB_CUDA(Launch<hb::kModeStep>(b, a, (cudaStream_t)stream));
+  return 0;
+}
+
+namespace {
+int SetNetOutput(const Batch* b, hb::KArgs* a, void* net_input, int dtype, int64_t row_pitch, const char* who) {
+  if (!net_input) return Fail(std::string(who) + ": net_input is null");
+  if (dtype < 0 || dtype > 2) return Fail(std::string(who) + ": dtype must be 0 (float32), 1 (bfloat16) or 2 (float16)");
+  if (row_pitch < b->spec.obs_size || (row_pitch & 7)) return Fail(std::string(who) + ": row_pitch must be >= the observation size and a multiple of 8");
+  if (reinterpret_cast<uintptr_t>(net_input) & 15) return Fail(std::string(who) + ": net_input must be 16-byte aligned");
+  a->net_in = net_input; a->net_dtype = dtype; a->net_pitch = row_pitch;
+  a->net_chunks = (int)(row_pitch >> 3);
+  a->net_lut_offset_words = (int)(((b->smem_bytes + 15) / 16 * 16) / 4);
+  a->net_magic = (uint32_t)((((uint64_t)1 << 32) + a->net_chunks - 1) / a->net_chunks);
+  return 0;
+}
+}  // namespace
+
+// The fused step writing the observation as the NETWORK'S INPUT: rows of 0/1 in float32 /
+// bfloat16 / float16 (dtype 0 / 1 / 2), row_pitch elements per game (>= observation size,
+// multiple of 8; the columns beyond the observation are zero, so K can be padded to the
+// GEMM's alignment) -- BatchStepEncodePacked + BatchExpandPacked in one kernel.  obs_bits
+// (nullable) receives the bit-packed rows as well (what the recorder keeps).
+int BatchStepEncodeNet(pyhanabi_batch_t* h, const int32_t* actions, int32_t* rewards, uint8_t* dones,
+                       int32_t* scores, void* net_input, int dtype, int64_t row_pitch,
+                       uint32_t* obs_bits, uint8_t* mask, int32_t* cur_player, int auto_reset,
+                       void* stream) {
+  HB_BATCH(h);
+  if (!actions) return Fail("BatchStepEncodeNet: actions is null");
+  if (obs_bits && (reinterpret_cast<uintptr_t>(obs_bits) & 15)) return Fail("BatchStepEncodeNet: obs_bits must be 16-byte aligned");
+  hb::KArgs a = BaseArgs(b);
+  if (SetNetOutput(b, &a, net_input, dtype, row_pitch, "BatchStepEncodeNet")) return 1;
+  a.actions = actions; a.rewards = rewards; a.dones = dones; a.scores = scores;
+  a.obs_bits = obs_bits; a.mask = mask; a.cur_player = cur_player; a.auto_reset = auto_reset;
+  HB_CUDA(Launch<hb::kModeStep>(b, a, (cudaStream_t)stream));
+  return 0;
+}
+
+int BatchObserveNet(pyhanabi_batch_t* h, int observer, void* net_input, int dtype, int64_t row_pitch,
+                    uint32_t* obs_bits, uint8_t* mask, int32_t* cur_player, void* stream) {
+  HB_BATCH(h);
+  if (observer >= b->spec.P) return Fail("BatchObserveNet: observer out of range");
+  if (obs_bits && (reinterpret_cast<uintptr_t>(obs_bits) & 15)) return Fail("BatchObserveNet: obs_bits must be 16-byte aligned");
+  hb::KArgs a = BaseArgs(b);
+  if (SetNetOutput(b, &a, net_input, dtype, row_pitch, "BatchObserveNet")) return 1;
+  a.obs_bits = obs_bits; a.observer = observer; a.mask = mask; a.cur_player = cur_player;
+  HB_CUDA(Launch<hb::kModeObserve>(b, a, (cudaStream_t)stream));
   return 0;
 }
 

@@ -922,6 +922,34 @@ HB_DEV void pack_mask_stream(uint32_t* stream, int A, uint64_t bits, bool valid,
   }
 }
 
+// Network-input rows: the tile's packed rows (row_words 32-bit words per game, bit j =
+// observation bit j, padding zero) expanded to 0/1 elements of a GEMM input type, K padded
+// with zeros up to `pitch` elements.  lut16[b] holds the eight 16-bit elements of byte b
+// (bfloat16 or float16 ones); float32 rows use the same table: a float32 1.0 is a bfloat16
+// 1.0 in the upper half of the word.  One 128-bit store per 8 elements (two for float32).
+// `magic` = ceil(2^32 / chunks) with chunks = pitch / 8 turns the flat chunk index into
+// (game, chunk) with one multiply.
+HB_DEV void expand_net_rows(const uint32_t* stream, int row_words, void* out, int64_t pitch, int chunks,
+                            uint32_t magic, int n_valid, int lane, const uint4* lut16, bool f32) {
+  const uint8_t* bytes = reinterpret_cast<const uint8_t*>(stream);
+  const int row_bytes = row_words * 4;
+  const int total = n_valid * chunks;
+#pragma unroll 2
+  for (int idx = lane; idx < total; idx += 32) {
+    const int game = (int)__umulhi((uint32_t)idx, magic);
+    const int j = idx - game * chunks;
+    const uint32_t b = j < row_bytes ? bytes[game * row_bytes + j] : 0u;
+    const uint4 v = lut16[b];
+    if (!f32) {
+      store_out(reinterpret_cast<uint4*>(static_cast<uint16_t*>(out) + (int64_t)game * pitch) + j, v);
+    } else {
+      uint4* dst = reinterpret_cast<uint4*>(static_cast<float*>(out) + (int64_t)game * pitch) + 2 * j;
+      store_out(dst, make_uint4(v.x << 16, v.x & 0xffff0000u, v.y << 16, v.y & 0xffff0000u));
+      store_out(dst + 1, make_uint4(v.z << 16, v.z & 0xffff0000u, v.w << 16, v.w & 0xffff0000u));
+    }
+  }
+}
+
 // 4 bits -> 4 bytes of 0/1 (little-endian byte i = bit i).
 HB_DEV uint32_t nibble_to_bytes(uint32_t n) { return ((n & 15u) * 0x00204081u) & 0x01010101u; }
 

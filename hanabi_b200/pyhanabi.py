@@ -845,6 +845,42 @@ class HanabiBatch(object):
         self._p(mask, torch.uint8, n * self.max_moves, "uint8_t*"),
         self._p(cur_player, torch.int32, n, "int32_t*"), self._stream()), "BatchObservePacked")
 
+  # -- the observation as the network's input (float32 / bfloat16 / float16 rows, K padded)
+  def _net(self, net_input):
+    n = self.num_games
+    if (net_input.dim() != 2 or net_input.stride(1) != 1 or int(net_input.shape[0]) != n or
+        not net_input.is_cuda):
+      raise ValueError("net_input must be a CUDA tensor [num_games, pitch] with unit column stride")
+    return (ffi.cast("void*", net_input.data_ptr()), _gemm_dtype_code(net_input),
+            int(net_input.stride(0)))
+
+  def step_encode_net(self, actions, net_input, rewards=None, dones=None, obs_bits=None, mask=None,
+                      cur_player=None, scores=None, auto_reset=True):
+    """step_encode writing the observation straight into the first GEMM's input matrix
+    `net_input` [num_games, pitch] (BatchStepEncodeNet); obs_bits optionally gets the
+    bit-packed rows too."""
+    torch = self._torch
+    n = self.num_games
+    ptr, code, pitch = self._net(net_input)
+    _check(lib.BatchStepEncodeNet(
+        self._c, self._p(actions, torch.int32, n, "int32_t*"),
+        self._p(rewards, torch.int32, n, "int32_t*"), self._p(dones, torch.uint8, n, "uint8_t*"),
+        self._p(scores, torch.int32, n, "int32_t*"), ptr, code, pitch,
+        self._p(obs_bits, torch.int32, n * self.packed_words, "uint32_t*"),
+        self._p(mask, torch.uint8, n * self.max_moves, "uint8_t*"),
+        self._p(cur_player, torch.int32, n, "int32_t*"), int(bool(auto_reset)), self._stream()),
+           "BatchStepEncodeNet")
+
+  def observe_net(self, net_input, obs_bits=None, mask=None, cur_player=None, observer=-1):
+    torch = self._torch
+    n = self.num_games
+    ptr, code, pitch = self._net(net_input)
+    _check(lib.BatchObserveNet(
+        self._c, int(observer), ptr, code, pitch,
+        self._p(obs_bits, torch.int32, n * self.packed_words, "uint32_t*"),
+        self._p(mask, torch.uint8, n * self.max_moves, "uint8_t*"),
+        self._p(cur_player, torch.int32, n, "int32_t*"), self._stream()), "BatchObserveNet")
+
   def bind_step_encode(self, actions, rewards=None, dones=None, obs=None, mask=None,
                        cur_player=None, scores=None, auto_reset=True, stream=None):
     """Pre-validated, pre-cast variant of step_encode for tight loops: returns a

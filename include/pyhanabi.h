@@ -258,6 +258,19 @@ int BatchStepEncodePacked(pyhanabi_batch_t* batch, const int32_t* actions, int32
 int BatchObservePacked(pyhanabi_batch_t* batch, int observer, uint32_t* obs_bits,
                        uint8_t* mask, int32_t* cur_player, void* stream);
 
+/* The observation as the NETWORK'S INPUT, written by the step kernel itself: rows of
+ * 0/1 in float32 / bfloat16 / float16 (dtype 0 / 1 / 2), row_pitch elements per game
+ * (>= observation size, multiple of 8, columns beyond the observation zero -- K padded
+ * to the GEMM's alignment); obs_bits (nullable) also receives the bit-packed rows.
+ * net_input must be 16-byte aligned. */
+int BatchStepEncodeNet(pyhanabi_batch_t* batch, const int32_t* actions, int32_t* rewards,
+                       uint8_t* dones, int32_t* scores, void* net_input, int dtype,
+                       int64_t row_pitch, uint32_t* obs_bits, uint8_t* mask,
+                       int32_t* cur_player, int auto_reset, void* stream);
+int BatchObserveNet(pyhanabi_batch_t* batch, int observer, void* net_input, int dtype,
+                    int64_t row_pitch, uint32_t* obs_bits, uint8_t* mask, int32_t* cur_player,
+                    void* stream);
+
 /* The same two verbs with HOST buffers (pinned memory recommended), for callers
  * that keep their data on the CPU like the reference's trainers do: uploads the
  * actions, runs the fused kernel and downloads the results, chunked over

@@ -197,3 +197,49 @@ def test_expand_packed_and_c51_select_on_gemm_outputs(dtype_name):
   top = q.max(dim=1).values
   picked = q.gather(1, got.long().view(-1, 1)).view(-1)
   assert bool(((top - picked).abs() <= 1e-4 * top.abs().clamp(min=1)).all())
+
+
+@pytest.mark.parametrize("dtype_name,name", [("bfloat16", "full2"), ("float32", "full2"), ("float16", "small2"),
+                                             ("bfloat16", "full5")])
+def test_step_kernel_writes_the_network_input(dtype_name, name):
+  """BatchStepEncodeNet / BatchObserveNet: the step kernel's own 0/1 rows in the GEMM's element
+  type (K zero-padded) equal the byte observation of a twin batch, step after step; the packed
+  rows written alongside are the ones BatchStepEncodePacked writes."""
+  import torch
+  from hanabi_b200 import pyhanabi as ph
+  from tests import common
+  dt = getattr(torch, dtype_name)
+  n = 2100  # ragged last tile
+  params = common.CONFIGS[name]
+  seeds = common.seeds_for(n, base=21)
+  a, b = ph.HanabiBatch(params, n, seeds), ph.HanabiBatch(params, n, seeds)
+  dev = torch.device("cuda:0")
+  D, A, W = a.obs_size, a.max_moves, a.packed_words
+  K = (D + 31) // 32 * 32
+  obs = torch.zeros((n, D), dtype=torch.uint8, device=dev)
+  mask_a = torch.zeros((n, A), dtype=torch.uint8, device=dev)
+  mask_b = torch.zeros((n, A), dtype=torch.uint8, device=dev)
+  cur_a = torch.zeros(n, dtype=torch.int32, device=dev)
+  cur_b = torch.zeros(n, dtype=torch.int32, device=dev)
+  rew_a, rew_b = torch.zeros(n, dtype=torch.int32, device=dev), torch.zeros(n, dtype=torch.int32, device=dev)
+  done_a, done_b = torch.zeros(n, dtype=torch.uint8, device=dev), torch.zeros(n, dtype=torch.uint8, device=dev)
+  act = torch.zeros(n, dtype=torch.int32, device=dev)
+  x = torch.full((n, K), 7, dtype=dt, device=dev)
+  bits = torch.full((n, W), -1, dtype=torch.int32, device=dev)
+  want_bits = torch.zeros((n, W), dtype=torch.int32, device=dev)
+  a.reset(); b.reset()
+  a.observe(obs, mask_a, cur_a)
+  b.observe_net(x, obs_bits=bits, mask=mask_b, cur_player=cur_b)
+  for t in range(25):
+    assert torch.equal(x[:, :D].float(), obs.float()) and not x[:, D:].any(), t
+    a.observe_packed(want_bits)
+    assert torch.equal(bits, want_bits) and torch.equal(mask_a, mask_b) and torch.equal(cur_a, cur_b)
+    ph.select_action(None, mask_a, 1.0, seed=2, step=t, out=act)
+    a.step_encode(act, rew_a, done_a, obs, mask_a, cur_a)
+    x.fill_(7)
+    b.step_encode_net(act, x, rew_b, done_b, obs_bits=bits, mask=mask_b, cur_player=cur_b)
+    assert torch.equal(rew_a, rew_b) and torch.equal(done_a, done_b)
+  # a wider pitch (not a multiple of 32) and no packed rows
+  wide = torch.full((n, K + 8), 7, dtype=dt, device=dev)
+  b.observe_net(wide)
+  assert torch.equal(wide[:, :D].float(), obs.float()) and not wide[:, D:].any()
