@@ -13,6 +13,7 @@
 #include <math_constants.h>
 #include <stdint.h>
 
+#include <cstdlib>
 #include <string>
 #include <thread>
 #include <type_traits>
@@ -276,6 +277,160 @@ __device__ __forceinline__ void action_sums(const T* row, int start, int atoms, 
 // underflow against M is redone against its own maximum.
 // Needs 16-byte aligned rows (base and pitch) and atoms <= 63;
 // smem: 128 floats + warps * row_smem_bytes.
+// action_sums for a slice of an action's atoms: `len` atoms starting at row element `start`,
+// the first of which has support index `sup_idx` (row alignment and support alignment are
+// independent here: the pair loads pick the copy of the support whose pairs are 8-byte
+// aligned for this slice).
+template <class T, int KL>
+__device__ __forceinline__ void slice_sums(const T* row, int start, int len, float nm,
+                                           const float* s_sup, int sup_idx, float& se, float& sw) {
+  if (KL > 0) len = KL;
+  constexpr float kL2e = 1.4426950408889634f;
+  se = 0.f; sw = 0.f;
+  if (sizeof(T) == 4) {
+    const float* r = reinterpret_cast<const float*>(row) + start;
+#pragma unroll
+    for (int i = 0; i < len; ++i) {
+      const float e = ex2_fast(fmaf(r[i], kL2e, nm));
+      se += e;
+      sw = fmaf(e, s_sup[sup_idx + i], sw);
+    }
+  } else {
+    typedef typename std::conditional<sizeof(T) == 4, __half, T>::type T16;
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(row) + (start >> 1);
+    const int odd = start & 1;
+    if (odd) {
+      const float e = ex2_fast(fmaf(unpack2<T16>(w[0]).y, kL2e, nm));
+      se = e;
+      sw = e * s_sup[sup_idx];
+    }
+    w += odd;
+    const int p0 = sup_idx + odd;  // support index of the first pair
+    const float2* sp = reinterpret_cast<const float2*>(s_sup + ((p0 & 1) ? 64 + p0 - 1 : p0));
+    const int pairs = (KL > 0 && (KL & 1)) ? (KL >> 1) : ((len - odd) >> 1);
+#pragma unroll
+    for (int j = 0; j < pairs; ++j) {
+      const float2 v = unpack2<T16>(w[j]);
+      const float2 sv = sp[j];
+      const float e0 = ex2_fast(fmaf(v.x, kL2e, nm)), e1 = ex2_fast(fmaf(v.y, kL2e, nm));
+      se += e0 + e1;
+      sw = fmaf(e0, sv.x, sw);
+      sw = fmaf(e1, sv.y, sw);
+    }
+    if ((len - odd) & 1) {
+      const float e = ex2_fast(fmaf(unpack2<T16>(w[pairs]).x, kL2e, nm));
+      se += e;
+      sw = fmaf(e, s_sup[sup_idx + len - 1], sw);
+    }
+  }
+}
+
+// k_select_c51_rows with every action cut into three slices of atoms, so that 3 * A work
+// units (60 for Hanabi-Full 2p) keep all 32 lanes busy for two short passes instead of A
+// lanes for one long one; the partial sums meet in shared memory.  KC = slice length when
+// it is a compile-time constant (17 for 51 atoms), else 0.
+// smem: 128 floats + warps * row_smem_bytes + warps * 3 * A float2.
+template <class T, int KC>
+__global__ void k_select_c51_thirds(const T* __restrict__ logits, int64_t row_pitch,
+                                    const float* __restrict__ support,
+                                    const uint8_t* __restrict__ mask, int n, int A, int atoms,
+                                    float epsilon, uint64_t seed, uint64_t step,
+                                    int32_t* __restrict__ actions, float* __restrict__ q_out,
+                                    int row_smem_bytes) {
+  extern __shared__ uint4 s_rows[];
+  float* s_sup = reinterpret_cast<float*>(s_rows);  // [0,64): support, [64,128): shifted by one
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+  if (threadIdx.x < 128) {
+    const int i = threadIdx.x & 63, sh = threadIdx.x >> 6;
+    s_sup[threadIdx.x] = i + sh < atoms ? support[i + sh] : 0.f;
+  }
+  __syncthreads();
+  const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (g >= n) return;
+  uint8_t* base = reinterpret_cast<uint8_t*>(s_rows) + 512;
+  T* row = reinterpret_cast<T*>(base + (size_t)warp * row_smem_bytes);
+  float2* part = reinterpret_cast<float2*>(base + (size_t)warps * row_smem_bytes) + (size_t)warp * 3 * A;
+  const T* src = logits + (int64_t)g * row_pitch;
+  const int len_row = A * atoms;
+  constexpr int kPer = 16 / (int)sizeof(T);
+  const int full = len_row / kPer;
+  float mx = -CUDART_INF_F;
+  for (int k = lane; k < full; k += 32) {
+    const uint4 v = __ldcs(reinterpret_cast<const uint4*>(src) + k);
+    reinterpret_cast<uint4*>(row)[k] = v;
+    if (sizeof(T) == 4) {
+      mx = fmaxf(fmaxf(mx, __uint_as_float(v.x)), fmaxf(__uint_as_float(v.y), fmaxf(__uint_as_float(v.z), __uint_as_float(v.w))));
+    } else {
+      typedef typename std::conditional<sizeof(T) == 4, __half, T>::type T16;
+      const float2 a = unpack2<T16>(v.x), b = unpack2<T16>(v.y), c = unpack2<T16>(v.z), d = unpack2<T16>(v.w);
+      mx = fmaxf(fmaxf(fmaxf(mx, a.x), fmaxf(a.y, b.x)), fmaxf(fmaxf(b.y, c.x), fmaxf(c.y, fmaxf(d.x, d.y))));
+    }
+  }
+  for (int i = full * kPer + lane; i < len_row; i += 32) {
+    const T v = src[i];
+    row[i] = v;
+    mx = fmaxf(mx, to_f32<T>(v));
+  }
+  mx = warp_max(mx);
+  __syncwarp();
+  const uint8_t* m = mask + (int64_t)g * A;
+  const uint64_t bits = policy_bits(seed, step, (uint64_t)g);
+  const float u01 = (float)(bits >> 40) * (1.0f / 16777216.0f);
+  const bool explore = (u01 <= epsilon && epsilon > 0.0f);
+  const float nm = -mx * 1.4426950408889634f;
+  const int chunk = KC > 0 ? KC : (atoms + 2) / 3;
+  const int units = 3 * A;
+  for (int u0 = 0; u0 < units; u0 += 32) {
+    const int u = u0 + lane;
+    if (u < units) {
+      const int a = u / 3, c = u - 3 * a;
+      float se = 0.f, sw = 0.f;
+      if (q_out != nullptr || m[a] != 0) {
+        const int off = c * chunk;
+        const int len = atoms - off < chunk ? atoms - off : chunk;
+        if (KC > 0 && len == KC) slice_sums<T, KC>(row, a * atoms + off, len, nm, s_sup, off, se, sw);
+        else if (len > 0) slice_sums<T, 0>(row, a * atoms + off, len, nm, s_sup, off, se, sw);
+      }
+      part[u] = make_float2(se, sw);
+    }
+  }
+  __syncwarp();
+  float best = -CUDART_INF_F;
+  int choice = -1, n_legal = 0;
+  for (int a = lane; a < A; a += 32) {
+    const bool legal = m[a] != 0;
+    n_legal += legal;
+    if (!legal && q_out == nullptr) continue;
+    const float2 p0 = part[3 * a], p1 = part[3 * a + 1], p2 = part[3 * a + 2];
+    float se = p0.x + p1.x + p2.x, sw = p0.y + p1.y + p2.y;
+    if (!(se > 0.f)) {  // everything underflowed against the row maximum
+      float am = -CUDART_INF_F;
+      for (int i = 0; i < atoms; ++i) am = fmaxf(am, to_f32<T>(row[a * atoms + i]));
+      slice_sums<T, 0>(row, a * atoms, atoms, -am * 1.4426950408889634f, s_sup, 0, se, sw);
+    }
+    const float qa = sw / se;
+    if (q_out) q_out[(int64_t)g * A + a] = qa;
+    if (legal && (choice < 0 || qa > best)) { best = qa; choice = a; }
+  }
+  n_legal = __reduce_add_sync(kFull, n_legal);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float oq = __shfl_xor_sync(kFull, best, o);
+    const int oa = __shfl_xor_sync(kFull, choice, o);
+    if (oa >= 0 && (choice < 0 || oq > best || (oq == best && oa < choice))) { best = oq; choice = oa; }
+  }
+  if (n_legal == 0) choice = -1;
+  else if (explore) {
+    uint64_t legal_set = 0;
+    for (int a0 = 0; a0 < A; a0 += 32) {
+      const int a = a0 + lane;
+      legal_set |= (uint64_t)__ballot_sync(kFull, a < A && m[a] != 0) << a0;
+    }
+    choice = kth_set_bit(legal_set, random_legal_rank(bits, n_legal));
+  }
+  if (lane == 0) actions[g] = choice;
+}
+
 template <class T, int KA>
 __global__ void k_select_c51_rows(const T* __restrict__ logits, int64_t row_pitch,
                                   const float* __restrict__ support,
@@ -520,7 +675,19 @@ cudaError_t LaunchSelectC51(const T* logits, int64_t row_pitch, const float* sup
   const unsigned grid = (unsigned)(((int64_t)n * 32 + 255) / 256);
   const size_t row_bytes = (((size_t)A * atoms * sizeof(T)) + 15) / 16 * 16;
   const bool aligned = (reinterpret_cast<uintptr_t>(logits) & 15) == 0 && ((row_pitch * sizeof(T)) & 15) == 0;
-  if (aligned && atoms <= 63 && 512 + 8 * row_bytes <= 48 * 1024) {
+  const size_t thirds_bytes = 512 + 8 * row_bytes + 8 * (size_t)3 * A * sizeof(float2);
+  static const bool use_thirds = std::getenv("HANABI_B200_SELECT_THIRDS") == nullptr ||
+                                 std::atoi(std::getenv("HANABI_B200_SELECT_THIRDS")) != 0;
+  if (use_thirds && aligned && atoms <= 63 && thirds_bytes <= 48 * 1024) {
+    if (atoms == 51)
+      hbp::k_select_c51_thirds<T, 17><<<grid, 256, thirds_bytes, s>>>(logits, row_pitch, support, mask, n, A, atoms,
+                                                                     epsilon, seed, step, actions, nullptr,
+                                                                     (int)row_bytes);
+    else
+      hbp::k_select_c51_thirds<T, 0><<<grid, 256, thirds_bytes, s>>>(logits, row_pitch, support, mask, n, A, atoms,
+                                                                    epsilon, seed, step, actions, nullptr,
+                                                                    (int)row_bytes);
+  } else if (aligned && atoms <= 63 && 512 + 8 * row_bytes <= 48 * 1024) {
     if (atoms == 51)
       hbp::k_select_c51_rows<T, 51><<<grid, 256, 512 + 8 * row_bytes, s>>>(logits, row_pitch, support, mask, n, A,
                                                                           atoms, epsilon, seed, step, actions,
