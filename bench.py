@@ -31,11 +31,14 @@ WORKLOADS = {
     "hanabi_full_5p": dict(players=5),
     "hanabi_small_2p": dict(players=2, colors=2, ranks=5, hand_size=2, max_information_tokens=3,
                             max_life_tokens=1),
+    # the PPO / REINFORCE scripts' default (training/hanabi_small/train_ppo_agent_small_env.py:111-112)
+    "hanabi_small_4p": dict(players=4, colors=2, ranks=5, hand_size=2, max_information_tokens=3,
+                            max_life_tokens=1),
 }
 # Algorithmic bytes per env-step (SURVEY.md section 8d / BASELINE.md section 4):
 # obs_dim + A (uint8 mask) + 4 (reward) + 1 (done) + 4 (action) + 2 * S (packed state r+w).
 ALGO_BYTES = {"hanabi_full_2p": 815, "hanabi_full_4p": 1248, "hanabi_full_5p": 1529,
-              "hanabi_small_2p": 255}
+              "hanabi_small_2p": 255, "hanabi_small_4p": 411}
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only without MEASURED_PEAKS.json
 
 
@@ -75,7 +78,7 @@ def parse_args():
   ap.add_argument("--python-baselines", action="store_true",
                   help="also time the Python paths of BASELINE.md section 3 (C1-C3) on the host")
   ap.add_argument("--cpu-python-worker", default=None, help=argparse.SUPPRESS)
-  ap.add_argument("--policy", default="random", choices=["random", "rainbow", "adhoc"],
+  ap.add_argument("--policy", default="random", choices=["random", "rainbow", "adhoc", "ppo"],
                   help="random: uniform legal (headline); rainbow: fixed-weight C51 MLP "
                        "obs->512->A*51 (torch GEMMs) + fused masked argmax, epsilon 0; adhoc: "
                        "seat 0 Rainbow, other seats the batched RuleBasedAgent sharing one object "
@@ -303,6 +306,7 @@ def main():
   adhoc_all_rows = args.adhoc_all_rows or args.games < 32768
   use_graph = (not args.no_graph) and (args.policy == "rainbow" or
                                        (args.policy == "adhoc" and adhoc_all_rows))
+  # (the ppo policy's categorical draw takes the step number as its random key: host launches)
   if use_graph:
     torch.cuda.set_stream(torch.cuda.Stream(device=dev))  # capture needs a non-default stream
   params = WORKLOADS[args.workload]
@@ -361,6 +365,36 @@ def main():
     launches_per_step = S
   elif args.policy == "random":
     select = ph.bind_select_action(None, mask, 1.0, seed=7, out=act)
+  elif args.policy == "ppo":
+    # the PPO / REINFORCE collect policy (training/hanabi_small/train_ppo_agent_small_env.py:116,
+    # tf_agents_lib/masked_networks.py): actor MLP obs -> 150 -> 75 -> A with fixed random weights
+    # (layer widths zero-padded to multiples of 32 for the library GEMMs), then the masked
+    # categorical draw + log-probability in BatchSampleMaskedCategorical
+    torch.manual_seed(0)
+    mlp = args.mlp_dtype
+    tdt = {"fp32": torch.float32, "tf32": torch.float32, "bf16": torch.bfloat16,
+           "fp16": torch.float16}[mlp]
+    torch.backends.cuda.matmul.allow_tf32 = mlp == "tf32"
+    pad = lambda v: (v + 31) // 32 * 32
+    Kp, H1, H2, Ap = pad(D), pad(150), pad(75), pad(A)
+
+    def dense(i, o, ip, op):
+      w = torch.zeros(ip, op, device=dev)
+      w[:i, :o] = torch.randn(i, o, device=dev) / i ** 0.5
+      return w.to(tdt), torch.zeros(op, device=dev, dtype=tdt)
+    (w1, c1), (w2, c2), (w3, c3) = dense(D, 150, Kp, H1), dense(150, 75, H1, H2), dense(75, A, H2, Ap)
+    x = torch.empty((n, Kp), dtype=tdt, device=dev)
+    logits = torch.empty((n, Ap), dtype=tdt, device=dev)
+    logp = torch.empty(n, dtype=torch.float32, device=dev)
+    batch.observe_net(x)
+    step_encode = lambda t: batch.step_encode_net(act, x, rew, done, mask=mask, cur_player=cur)
+    launches_per_step = 2  # ours: step (+ network input), masked categorical (+ 3 library GEMMs)
+
+    def select(t):
+      h1 = torch._addmm_activation(c1, x, w1)
+      h2 = torch._addmm_activation(c2, h1, w2)
+      torch.addmm(c3, h2, w3, out=logits)
+      ph.sample_masked_categorical(logits, mask, seed=7, step=t, actions=act, log_probs=logp)
   else:
     # Rainbow actor (agents/rainbow_copy/rainbow_agent.py:36-68,163-172): MLP
     # obs_dim -> 512 -> A x 51 with fixed random weights.  The step kernel writes the first
@@ -699,6 +733,9 @@ def main():
                             "(BatchStepEncodeRandom)" if fused_policy else
                             "uniform random legal (BatchSelectAction, epsilon=1)"
                             if args.policy == "random" else
+                            "PPO actor MLP %d->150->75->%d (cuBLASLt %s GEMMs via torch) on the step "
+                            "kernel's network-input rows + BatchSampleMaskedCategorical"
+                            % (D, A, args.mlp_dtype) if args.policy == "ppo" else
                             "Rainbow C51 MLP %d->512->%dx51 (cuBLASLt %s GEMMs via torch) on the "
                             "step kernel's own network-input rows (BatchStepEncodeNet) + "
                             "BatchSelectActionC51 (epsilon=0)"

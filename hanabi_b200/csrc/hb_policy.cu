@@ -517,6 +517,57 @@ __global__ void k_select_c51_rows(const T* __restrict__ logits, int64_t row_pitc
   if (lane == 0) actions[g] = choice;
 }
 
+// The PPO / REINFORCE actors' policy head (training/tf_agents_lib/masked_networks.py:26-50,
+// 108-132): masked_logits = logits + mask with mask in {0, float32.min}, then a categorical
+// draw.  One thread per game: softmax over the legal actions, inverse-CDF draw with the
+// counter-based generator keyed (seed, step, game), log-probability of the drawn action
+// (what the PPO loss needs from the collect policy).  greedy != 0 takes the mode instead
+// (the evaluation policy).  Illegal actions have probability exactly 0, as adding
+// float32.min to a logit makes its softmax term underflow to 0.
+template <class T>
+__global__ void k_sample_masked(const T* __restrict__ logits, int64_t row_pitch,
+                                const uint8_t* __restrict__ mask, int n, int A, int greedy,
+                                uint64_t seed, uint64_t step, int32_t* __restrict__ actions,
+                                float* __restrict__ log_probs) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n) return;
+  const T* row = logits + (int64_t)g * row_pitch;
+  const uint8_t* m = mask + (int64_t)g * A;
+  float mx = -CUDART_INF_F;
+  int first = -1, best = -1;
+  for (int a = 0; a < A; ++a)
+    if (m[a] != 0) {
+      const float v = to_f32<T>(row[a]);
+      if (first < 0) first = a;
+      if (best < 0 || v > mx) { mx = v; best = a; }
+    }
+  if (first < 0) {
+    actions[g] = -1;
+    if (log_probs) log_probs[g] = 0.f;
+    return;
+  }
+  float sum = 0.f;
+  for (int a = 0; a < A; ++a)
+    if (m[a] != 0) sum += expf(to_f32<T>(row[a]) - mx);
+  int choice = best;
+  if (!greedy) {
+    const uint64_t bits = policy_bits(seed, step, (uint64_t)g);
+    const float u = (float)(bits >> 40) * (1.0f / 16777216.0f) * sum;  // in [0, sum)
+    float acc = 0.f;
+    choice = -1;
+    int last = first;
+    for (int a = 0; a < A; ++a)
+      if (m[a] != 0) {
+        acc += expf(to_f32<T>(row[a]) - mx);
+        last = a;
+        if (u < acc) { choice = a; break; }
+      }
+    if (choice < 0) choice = last;  // rounding at the upper end
+  }
+  actions[g] = choice;
+  if (log_probs) log_probs[g] = to_f32<T>(row[choice]) - mx - logf(sum);
+}
+
 // Bit-packed observation rows -> rows of 0/1 in a GEMM input type, K padded with
 // zeros up to row_pitch.  One thread expands 8 bits into 8 elements.
 template <class T> struct Vec8;
@@ -757,6 +808,26 @@ int BatchSelectActionC51(const void* logits, int dtype, int64_t row_pitch, int n
       return PFail("BatchSelectActionC51: dtype must be 0 (float32), 1 (bfloat16) or 2 (float16)");
   }
   return e == cudaSuccess ? 0 : PFail(std::string("BatchSelectActionC51: ") + cudaGetErrorString(e));
+}
+
+// Masked categorical policy head of the PPO / REINFORCE actors: see k_sample_masked.
+// logits: float32 / bfloat16 / float16 (dtype 0 / 1 / 2) [n][row_pitch >= num_actions];
+// log_probs (nullable): float32[n], log pi(action | state) under the masked softmax.
+int BatchSampleMaskedCategorical(const void* logits, int dtype, int64_t row_pitch, const uint8_t* mask,
+                                 int n, int num_actions, int greedy, uint64_t seed, uint64_t step,
+                                 int32_t* actions, float* log_probs, void* stream) {
+  if (!logits || !mask || !actions) return PFail("BatchSampleMaskedCategorical: null argument");
+  if (n <= 0 || num_actions <= 0 || row_pitch < num_actions) return PFail("BatchSampleMaskedCategorical: bad sizes");
+  cudaStream_t s = (cudaStream_t)stream;
+  const unsigned grid = (unsigned)((n + 127) / 128);
+  switch (dtype) {
+    case 0: hbp::k_sample_masked<float><<<grid, 128, 0, s>>>(static_cast<const float*>(logits), row_pitch, mask, n, num_actions, greedy, seed, step, actions, log_probs); break;
+    case 1: hbp::k_sample_masked<__nv_bfloat16><<<grid, 128, 0, s>>>(static_cast<const __nv_bfloat16*>(logits), row_pitch, mask, n, num_actions, greedy, seed, step, actions, log_probs); break;
+    case 2: hbp::k_sample_masked<__half><<<grid, 128, 0, s>>>(static_cast<const __half*>(logits), row_pitch, mask, n, num_actions, greedy, seed, step, actions, log_probs); break;
+    default: return PFail("BatchSampleMaskedCategorical: dtype must be 0 (float32), 1 (bfloat16) or 2 (float16)");
+  }
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : PFail(std::string("BatchSampleMaskedCategorical: ") + cudaGetErrorString(e));
 }
 
 // Bit-packed observation rows (BatchStepEncodePacked / BatchObservePacked) -> the

@@ -1202,6 +1202,28 @@ def select_action_c51(logits, num_atoms, mask, epsilon, seed, step, support, out
   return out
 
 
+def sample_masked_categorical(logits, mask, seed, step, greedy=False, actions=None, log_probs=None):
+  """Masked categorical policy head of the PPO / REINFORCE actors
+  (BatchSampleMaskedCategorical): logits [n, >= A] float32 / bfloat16 / float16, mask uint8
+  [n, A].  Returns (actions int32 [n], log_probs float32 [n])."""
+  import torch
+  _require_lib()
+  n, A = int(mask.shape[0]), int(mask.shape[1])
+  if logits.dim() != 2 or logits.stride(1) != 1 or int(logits.shape[0]) != n:
+    raise ValueError("logits must be [n, pitch] with unit column stride")
+  if actions is None:
+    actions = torch.empty(n, dtype=torch.int32, device=mask.device)
+  if log_probs is None:
+    log_probs = torch.empty(n, dtype=torch.float32, device=mask.device)
+  with torch.cuda.device(mask.device):
+    _check(lib.BatchSampleMaskedCategorical(
+        ffi.cast("void*", logits.data_ptr()), _gemm_dtype_code(logits), int(logits.stride(0)),
+        _tp(mask, torch.uint8, "uint8_t*"), n, A, int(bool(greedy)), int(seed) & (2**64 - 1),
+        int(step) & (2**64 - 1), _tp(actions, torch.int32, "int32_t*"),
+        _tp(log_probs, torch.float32, "float*"), _cur_stream(mask)), "BatchSampleMaskedCategorical")
+  return actions, log_probs
+
+
 def bind_expand_packed(obs_bits, obs_size, out, stream=None):
   """Bit-packed observation rows (int32 [n, packed_words]) -> `out` [n, pitch] of 0/1 in
   float32 / bfloat16 / float16, columns beyond obs_size zeroed (BatchExpandPacked).

@@ -338,6 +338,15 @@ int BatchSelectActionC51(const void* logits, int dtype, int64_t row_pitch, int n
                          const float* support, const uint8_t* mask, int n, int num_actions,
                          float epsilon, uint64_t seed, uint64_t step, int32_t* actions,
                          void* stream);
+/* The PPO / REINFORCE actors' masked categorical policy head
+ * (training/tf_agents_lib/masked_networks.py:26-50): softmax over the legal actions of
+ * logits[n][row_pitch] (dtype as above), one draw per game from the counter-based
+ * generator keyed (seed, step, game) -- or the mode when greedy != 0 -- and optionally
+ * log pi(action | state) (float32[n], nullable). */
+int BatchSampleMaskedCategorical(const void* logits, int dtype, int64_t row_pitch,
+                                 const uint8_t* mask, int n, int num_actions, int greedy,
+                                 uint64_t seed, uint64_t step, int32_t* actions,
+                                 float* log_probs, void* stream);
 /* Bit-packed observation rows -> the network's input matrix: out[i][j] = bit j of
  * row i as 0/1 in float32 / bfloat16 / float16 (dtype as above), columns
  * [obs_size, row_pitch) zero (K padded to the GEMM's alignment).  row_pitch % 8 == 0,

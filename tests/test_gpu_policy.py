@@ -243,3 +243,42 @@ def test_step_kernel_writes_the_network_input(dtype_name, name):
   wide = torch.full((n, K + 8), 7, dtype=dt, device=dev)
   b.observe_net(wide)
   assert torch.equal(wide[:, :D].float(), obs.float()) and not wide[:, D:].any()
+
+
+def test_masked_categorical_policy_head():
+  """BatchSampleMaskedCategorical vs torch: log-probabilities equal log_softmax(logits + mask)
+  at the drawn action (masked_networks.py:45-50 with mask in {0, float32.min}), draws are
+  always legal, the empirical distribution over many draws matches the softmax, greedy takes
+  the mode."""
+  import torch
+  from hanabi_b200 import pyhanabi as ph
+  dev = torch.device("cuda:0")
+  torch.manual_seed(3)
+  n, A = 4096, 11
+  logits = torch.randn((n, A), device=dev) * 2
+  mask = (torch.rand((n, A), device=dev) < 0.6).to(torch.uint8)
+  mask[:, 0] |= (mask.sum(dim=1) == 0).to(torch.uint8)  # at least one legal action
+  fmin = torch.finfo(torch.float32).min
+  ref_logp = torch.log_softmax(logits + torch.where(mask.bool(), 0.0, fmin), dim=1)
+  act, logp = ph.sample_masked_categorical(logits, mask, seed=1, step=0)
+  assert bool(mask.gather(1, act.long().view(-1, 1)).all())
+  want = ref_logp.gather(1, act.long().view(-1, 1)).view(-1)
+  assert torch.allclose(logp, want, rtol=1e-5, atol=1e-5)
+  g_act, _ = ph.sample_masked_categorical(logits, mask, seed=1, step=0, greedy=True)
+  assert torch.equal(g_act.long(), ref_logp.argmax(dim=1))
+  # one game replicated: frequencies of 200 000 draws against its softmax
+  row, mrow = logits[:1].repeat(200000, 1).contiguous(), mask[:1].repeat(200000, 1).contiguous()
+  draws, _ = ph.sample_masked_categorical(row, mrow, seed=9, step=4)
+  freq = torch.bincount(draws.long(), minlength=A).float() / draws.numel()
+  assert float((freq - ref_logp[0].exp()).abs().max()) < 5e-3
+  # bfloat16 logits with a padded pitch, and a game without legal action
+  wide = torch.zeros((n, 16), dtype=torch.bfloat16, device=dev)
+  wide[:, :A] = logits.to(torch.bfloat16)
+  mask2 = mask.clone()
+  mask2[5] = 0
+  a2, lp2 = ph.sample_masked_categorical(wide, mask2, seed=1, step=0)
+  assert int(a2[5]) == -1
+  ok = torch.ones(n, dtype=torch.bool, device=dev)
+  ok[5] = False
+  ref2 = torch.log_softmax(wide[:, :A].float() + torch.where(mask2.bool(), 0.0, fmin), dim=1)
+  assert torch.allclose(lp2[ok], ref2.gather(1, a2.long().clamp(min=0).view(-1, 1)).view(-1)[ok], rtol=1e-4, atol=1e-4)
