@@ -716,6 +716,17 @@ def main():
   else:
     peak, peak_src = FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
   algo = ALGO_BYTES[args.workload]
+  algo_note = "uint8 observation rows"
+  if args.policy != "random":
+    # the step kernel of these modes writes other observation rows than one byte per bit
+    esz = {"fp32": 4, "tf32": 4, "bf16": 2, "fp16": 2}[args.mlp_dtype]
+    packed_bytes = 4 * batch.packed_words
+    if args.policy == "adhoc" and not adhoc_all_rows:
+      algo, algo_note = algo - D + packed_bytes, "bit-packed observation rows"
+    else:
+      with_bits = bool(args.record or args.policy == "adhoc")
+      algo = algo - D + Kp * esz + (packed_bytes if with_bits else 0)
+      algo_note = "network-input rows (%d x %d B)%s" % (Kp, esz, " + bit-packed rows" if with_bits else "")
   achieved = algo * n / (kernel_ms * 1e-3) / 1e9
   traffic = None
   tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -753,7 +764,7 @@ def main():
       "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                    "frac": achieved / peak, "traffic": traffic, "kernel": "k_main<step>",
                    "kernel_ms": kernel_ms, "launches_per_step": launches_per_step,
-                   "algorithmic_bytes_per_env_step": algo,
+                   "algorithmic_bytes_per_env_step": algo, "observation_output": algo_note,
                    "peak_source": peak_src},
       "e2e": e2e,
       "gpu_launches": launches_per_step * K,
