@@ -21,9 +21,6 @@
 namespace hb {
 
 enum Mode { kModeStep = 0, kModeReset = 1, kModeObserve = 2 };
-#ifndef HB_BLOCK
-#define HB_BLOCK 128
-#endif
 #ifndef HB_MIN_CTAS
 #define HB_MIN_CTAS 6
 #endif
@@ -48,9 +45,14 @@ enum Mode { kModeStep = 0, kModeReset = 1, kModeObserve = 2 };
 #ifndef HB_RESET_PREFETCH
 #define HB_RESET_PREFETCH 1
 #endif
-constexpr int kBlock = HB_BLOCK;  // games per CTA (measured best: 128 threads, 6 CTAs/SM, 80 registers)
-constexpr int kWarps = kBlock / 32;
-constexpr int kQueueCap = 64;    // finished games a CTA re-deals through the shared-memory queue
+// Games per CTA come with the rule-set view (V::kBlock); 768 threads are resident per SM.
+constexpr int kResidentThreads = 768;
+constexpr bool lehmer_for(int cards) {
+  return HB_RESET_LEHMER == 1 || (HB_RESET_LEHMER == 2 && cards >= HB_LEHMER_MIN_PAIRS);
+}
+constexpr int queue_cap(int block, int cards) {
+  return lehmer_for(cards) ? block / 2 : (block / 2 < 640 / cards ? block / 2 : 640 / cards);
+}
 constexpr int kStreamPad = 2;    // readable pad words after each packed bit stream
 constexpr int kNumStats = 32;    // [0] episodes [1] sum score [2] sum length [3..28] score histogram
 
@@ -103,7 +105,11 @@ struct KArgs {
 // NET: the instantiation that also writes network-input rows (BatchStepEncodeNet /
 // BatchObserveNet); kept out of the plain kernels so that their code stays as small as it was.
 template <class V, int MODE, bool NET = false>
-__global__ void __launch_bounds__(kBlock, (MODE == kModeStep) ? HB_MIN_CTAS_STEP : HB_MIN_CTAS) k_main(const __grid_constant__ KArgs a) {
+__global__ void __launch_bounds__(V::kBlock, kResidentThreads / V::kBlock) k_main(const __grid_constant__ KArgs a) {
+  constexpr int kBlock = V::kBlock, kWarps = kBlock / 32;
+  // finished games a CTA re-deals through the shared-memory queue (the serial path keeps three
+  // words per queued draw: bounded so that its table stays within 640 draws)
+  constexpr int kQueueCap = hb::queue_cap(kBlock, V::kP * V::kH);
   extern __shared__ uint32_t smem[];
   __shared__ int s_stats[kNumStats];
   __shared__ int s_nq;
@@ -113,7 +119,7 @@ __global__ void __launch_bounds__(kBlock, (MODE == kModeStep) ? HB_MIN_CTAS_STEP
   __shared__ uint32_t s_spread[32];
   // byte -> its eight 16-bit elements: 4 KB of dynamic shared memory that only the launches
   // writing network-input rows ask for
-  uint4* s_net_lut = reinterpret_cast<uint4*>(smem + a.net_lut_offset_words);
+  uint4* s_net_lut = reinterpret_cast<uint4*>(smem + a.net_lut_offset_words);  // behind this view's areas
   if (NET) {
     const uint32_t one = a.net_dtype == 2 ? 0x3c00u : 0x3f80u;  // float16 / bfloat16 (and float32 >> 16)
     for (int b = threadIdx.x; b < 256; b += kBlock) {
@@ -633,7 +639,7 @@ struct Batch {
   int force_generic = 0;
   int warp_smem_words = 0;
   int packed_words = 0, obs_stream_words = 0;
-  size_t smem_bytes = 0;
+  size_t smem_pad = 0;  // experiments: extra dynamic shared memory per CTA (fewer resident CTAs)
   // L2 residency of the packed game state (BatchSetL2Residency): launches carry an
   // access-policy window over `state` so that it stays in L2 between steps
   size_t l2_window_bytes = 0;
@@ -717,12 +723,26 @@ hb::KArgs BaseArgs(const Batch* b) {
   return a;
 }
 
+// Dynamic shared memory of k_main<V>: one packed-stream area per warp, the (index, lo, hi)
+// table of the serial re-deal path, and -- for the launches that write network-input rows
+// -- the 4 KB element table behind them.
+template <class V>
+size_t ViewSmemWords(const Batch* b) {
+  const bool lehmer = hb::lehmer_for(V::kP * V::kH);
+  const size_t words = (size_t)(V::kBlock / 32) * b->warp_smem_words +
+                       (lehmer ? 0 : (size_t)hb::queue_cap(V::kBlock, V::kP * V::kH) * 3 * b->spec.P * b->spec.H);
+  return (words + 3) & ~(size_t)3;
+}
+
 template <class V, int MODE, bool NET>
-cudaError_t LaunchKernel(const Batch* b, const hb::KArgs& a, cudaStream_t stream) {
-  const unsigned grid = (unsigned)((a.g_end - a.g_begin + hb::kBlock - 1) / hb::kBlock);
+cudaError_t LaunchKernel(const Batch* b, const hb::KArgs& a_in, cudaStream_t stream) {
+  hb::KArgs a = a_in;
+  const unsigned grid = (unsigned)((a.g_end - a.g_begin + V::kBlock - 1) / V::kBlock);
   static size_t allowed[16] = {0};  // per device: dynamic shared memory already opted in
   const int dev = b->device & 15;
-  const size_t smem_bytes = a.net_in ? (size_t)a.net_lut_offset_words * 4 + 256 * sizeof(uint4) : b->smem_bytes;
+  const size_t base_words = ViewSmemWords<V>(b);
+  a.net_lut_offset_words = (int)base_words;
+  const size_t smem_bytes = base_words * sizeof(uint32_t) + (NET ? 256 * sizeof(uint4) : 0) + b->smem_pad;
   if (smem_bytes > allowed[dev]) {
     cudaError_t e = cudaFuncSetAttribute(hb::k_main<V, MODE, NET>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -731,13 +751,13 @@ cudaError_t LaunchKernel(const Batch* b, const hb::KArgs& a, cudaStream_t stream
     allowed[dev] = smem_bytes;
   }
   if (b->l2_window_bytes == 0) {
-    hb::k_main<V, MODE, NET><<<grid, hb::kBlock, smem_bytes, stream>>>(a);
+    hb::k_main<V, MODE, NET><<<grid, V::kBlock, smem_bytes, stream>>>(a);
     return cudaGetLastError();
   }
   cudaLaunchConfig_t cfg;
   std::memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(hb::kBlock);
+  cfg.blockDim = dim3(V::kBlock);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr;
@@ -818,13 +838,9 @@ int NewBatch(pyhanabi_batch_t* out, int list_length, const char** param_list, in
   b->obs_stream_words = (b->obs_stream_words + 3) & ~3;
   // every warp's region starts 16-byte aligned (the packed rows are read as uint4)
   b->warp_smem_words = (b->obs_stream_words + b->spec.max_moves + 2 * hb::kStreamPad + 3) & ~3;
-  // the serial re-deal path keeps (index, lo, hi) of every queued draw after the streams
-  const bool lehmer = HB_RESET_LEHMER == 1 ||
-                      (HB_RESET_LEHMER == 2 && b->spec.P * b->spec.H >= HB_LEHMER_MIN_PAIRS);
-  b->smem_bytes = ((size_t)hb::kWarps * b->warp_smem_words +
-                   (lehmer ? 0 : (size_t)hb::kQueueCap * 3 * b->spec.P * b->spec.H)) * sizeof(uint32_t);
+  // (the CTA's total dynamic shared memory depends on the view's CTA size: ViewSmemWords)
   if (const char* pad = std::getenv("HANABI_B200_SMEM_PAD"))  // experiments: fewer resident CTAs
-    b->smem_bytes += (size_t)std::atoll(pad);
+    b->smem_pad = (size_t)std::atoll(pad);
   DeviceGuard guard(device);
   if (!guard.ok) { delete b; return Fail("NewBatch: cudaSetDevice failed"); }
   int32_t* d_seeds = nullptr;
@@ -1216,7 +1232,6 @@ int SetNetOutput(const Batch* b, hb::KArgs* a, void* net_input, int dtype, int64
   if (reinterpret_cast<uintptr_t>(net_input) & 15) return Fail(std::string(who) + ": net_input must be 16-byte aligned");
   a->net_in = net_input; a->net_dtype = dtype; a->net_pitch = row_pitch;
   a->net_chunks = (int)(row_pitch >> 3);
-  a->net_lut_offset_words = (int)(((b->smem_bytes + 15) / 16 * 16) / 4);
   a->net_magic = (uint32_t)((((uint64_t)1 << 32) + a->net_chunks - 1) / a->net_chunks);
   return 0;
 }

@@ -30,10 +30,20 @@ constexpr unsigned kFull = 0xffffffffu;
 // ------------------------------------------------------------------ spec views
 // Static view: every rule parameter that shapes the bit layout is a compile-time
 // constant so the encoder unrolls into straight-line shifts on register words.
+// Threads (= games) per CTA, measured per rule set with two launches in flight per GPU
+// (768 resident threads per SM in every case): 256 where the re-deal is the parallel
+// Lehmer decode (initial deals of 12+ cards), 192 for the short serial re-deals.
+#ifdef HB_BLOCK
+constexpr int block_for_deal(int) { return HB_BLOCK; }
+#else
+constexpr int block_for_deal(int cards) { return cards >= 12 ? 256 : 192; }
+#endif
+
 template <int P_, int H_, int C_, int R_, int IT_, int LT_>
 struct SView {
   static constexpr bool kStatic = true;
   static constexpr int kP = P_, kH = H_, kC = C_, kR = R_;
+  static constexpr int kBlock = block_for_deal(P_ * H_);
   HB_DEV explicit SView(const Spec&) {}
   HB_DEV constexpr int P() const { return P_; }
   HB_DEV constexpr int H() const { return H_; }
@@ -49,6 +59,7 @@ struct SView {
 struct DView {
   static constexpr bool kStatic = false;
   static constexpr int kP = kMaxPlayers, kH = kMaxHand, kC = kMaxColors, kR = kMaxRanks;
+  static constexpr int kBlock = block_for_deal(kMaxPlayers * kMaxHand);
   const Spec& s;
   HB_DEV explicit DView(const Spec& sp) : s(sp) {}
   HB_DEV int P() const { return s.P; }
