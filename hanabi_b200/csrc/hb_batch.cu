@@ -21,12 +21,6 @@
 namespace hb {
 
 enum Mode { kModeStep = 0, kModeReset = 1, kModeObserve = 2 };
-#ifndef HB_MIN_CTAS
-#define HB_MIN_CTAS 6
-#endif
-#ifndef HB_MIN_CTAS_STEP
-#define HB_MIN_CTAS_STEP HB_MIN_CTAS
-#endif
 // Re-deal of finished games: 2 = parallel Lehmer decode when an initial deal has
 // at least HB_LEHMER_MIN_PAIRS cards (measured: +23 % on Full 4p, -3 % on Full 2p,
 // -12 % on Small 2p against the serial draw chain), 1 = always, 0 = never.
@@ -38,9 +32,6 @@ enum Mode { kModeStep = 0, kModeReset = 1, kModeObserve = 2 };
 #endif
 #ifndef HB_EARLY_OUT
 #define HB_EARLY_OUT 0  // measured: -1.2 % on Full 2p, +1.1 % on Full 4p
-#endif
-#ifndef HB_EXPAND_LUT
-#define HB_EXPAND_LUT 0
 #endif
 #ifndef HB_RESET_PREFETCH
 #define HB_RESET_PREFETCH 1
@@ -131,14 +122,6 @@ __global__ void __launch_bounds__(V::kBlock, kResidentThreads / V::kBlock) k_mai
       s_net_lut[b] = e;
     }
   }
-#if HB_EXPAND_LUT
-  __shared__ uint2 s_lut[256];
-  for (int i = threadIdx.x; i < 256; i += kBlock)
-    s_lut[i] = make_uint2(nibble_to_bytes(i), nibble_to_bytes(i >> 4));
-  const uint2* lut = s_lut;
-#else
-  const uint2* lut = nullptr;
-#endif
   const V v(a.spec);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t cta0 = a.g_begin + (int64_t)blockIdx.x * kBlock;
@@ -397,9 +380,6 @@ __global__ void __launch_bounds__(V::kBlock, kResidentThreads / V::kBlock) k_mai
       }
     }
   }
-#ifdef HB_PROBE_LEAN_STEP
-  if (MODE == kModeStep) return;  // probe: the step kernel without any encoding code
-#endif
   const int n_valid = (int)((a.g_end - tile0) < 32 ? (a.g_end - tile0) : 32);
   uint32_t* obs_stream = smem + (size_t)warp * a.warp_smem_words;
   uint32_t* mask_stream = obs_stream + a.obs_stream_words + kStreamPad;
@@ -420,7 +400,7 @@ __global__ void __launch_bounds__(V::kBlock, kResidentThreads / V::kBlock) k_mai
   __syncwarp();
   if (a.obs)
     expand_stream(obs_stream, a.spec.obs_size, a.obs + tile0 * a.obs_pitch, a.obs_pitch, n_valid,
-                  lane, lut);
+                  lane);
   if (a.obs_bits)
     store_packed_rows(obs_stream, a.packed_words, a.obs_bits + tile0 * a.packed_words, n_valid, lane);
   if (NET) {
