@@ -30,6 +30,13 @@ enum Mode { kModeStep = 0, kModeReset = 1, kModeObserve = 2 };
 #ifndef HB_LEHMER_MIN_PAIRS
 #define HB_LEHMER_MIN_PAIRS 12
 #endif
+// Serial-path re-deal: 1 = one thread per game draws the cards one after the other,
+// 0 = one thread per (game, draw) decodes its card from the game's draw indices (two more
+// CTA barriers), 2 = the former for deals of 10+ cards, the latter below (measured: Full 2p
+// 1.6 % faster with the chain, Small 2p / 4p 1.2 % / 3 % faster with the decode).
+#ifndef HB_SERIAL_B2
+#define HB_SERIAL_B2 2
+#endif
 #ifndef HB_EARLY_OUT
 #define HB_EARLY_OUT 0  // measured: -1.2 % on Full 2p, +1.1 % on Full 4p
 #endif
@@ -347,10 +354,47 @@ __global__ void __launch_bounds__(V::kBlock, kResidentThreads / V::kBlock) k_mai
         }
       }
       __syncthreads();
+      constexpr bool kChain = HB_SERIAL_B2 == 1 || (HB_SERIAL_B2 == 2 && V::kP * V::kH >= 10);
+      if (kChain) {
       // B2: one thread per queued game runs the select chain on the precomputed indices
       for (int i = threadIdx.x; i < nq; i += kBlock)
         reset_draw(v, a.spec, s_words + i * pairs, s_words + cap + i * pairs,
                    s_words + 2 * cap + i * pairs, a.sampler_mode, s_res[i]);
+      } else {
+      // B2: the draw indices are all in shared memory, so the cards follow without a serial
+      // chain (Lehmer decode as above, through shared memory instead of shuffles): one thread
+      // per (game, draw) walks back through the game's earlier indices, then ORs its card into
+      // the game's hands and clears its deck bit.  A game with a draw that needs the exact
+      // fp64 sampler (or the exact-only test mode) is redone serially afterwards.
+      for (int i = threadIdx.x; i < nq; i += kBlock) {
+#pragma unroll
+        for (int p = 0; p < kMaxPlayers; ++p) s_res[i].cards[p] = 0;
+        s_res[i].deck_lo = (uint32_t)a.spec.full_deck;
+        s_res[i].deck_hi = (uint32_t)(a.spec.full_deck >> 32);
+      }
+      __syncthreads();
+      for (int k = threadIdx.x; k < nq * pairs; k += kBlock) {
+        const int e = k / pairs, r = k - e * pairs;
+        const uint32_t* qa = s_words + e * pairs;
+        int idx = (int)(qa[r] & 0xffu);
+        for (int j = r - 1; j >= 0; --j) idx += ((int)(qa[j] & 0xffu) <= idx) ? 1 : 0;
+        int color, rank;
+        card_of_position(v, idx, color, rank);
+        const int pl = r / v.H(), slot_i = r - pl * v.H();
+        atomicOr(&s_res[e].cards[pl], (uint32_t)(color | (rank << 3)) << (6 * slot_i));
+        if (idx < 32) atomicAnd(&s_res[e].deck_lo, ~(1u << idx));
+        else atomicAnd(&s_res[e].deck_hi, ~(1u << (idx - 32)));
+      }
+      __syncthreads();
+      for (int i = threadIdx.x; i < nq; i += kBlock) {
+        bool slow = a.sampler_mode == 1;
+        if (a.sampler_mode != 2)
+          for (int r = 0; r < pairs; ++r) slow |= (s_words[i * pairs + r] >> 8) != 0;
+        if (slow)
+          reset_draw(v, a.spec, s_words + i * pairs, s_words + cap + i * pairs,
+                     s_words + 2 * cap + i * pairs, a.sampler_mode, s_res[i]);
+      }
+      }
     }
     __syncthreads();
     if (MODE == kModeStep && a.stats && threadIdx.x < kNumStats && s_stats[threadIdx.x] != 0)
