@@ -338,3 +338,58 @@ def test_packed_observations_match_byte_form(name):
     b.observe_packed(bits, observer=observer)
     raw = np.unpackbits(bits.cpu().numpy().view(np.uint8).reshape(n, W * 4), axis=1, bitorder="little")
     common.assert_same(obs.cpu().numpy(), raw[:, :D], "packed observation of player %d" % observer)
+
+
+@pytest.mark.parametrize("name", ["full2", "full5", "small4"])
+def test_no_write_outside_the_output_buffers(name):
+  """compute-sanitizer is not available on this pool: every output buffer of every step
+  flavour sits between canary regions inside one allocation, with a ragged number of games;
+  the canaries must survive."""
+  import torch
+  from hanabi_b200 import pyhanabi as ph
+  n = 32 * 9 + 5
+  p = CONFIGS[name]
+  b = ph.HanabiBatch(p, n, common.seeds_for(n, base=17))
+  dev = torch.device("cuda:0")
+  D, A, W = b.obs_size, b.max_moves, b.packed_words
+  K = (D + 31) // 32 * 32
+  gap = 4096
+  sizes = dict(obs=n * D, mask=n * A, cur=4 * n, rew=4 * n, done=n, score=4 * n, act=4 * n,
+               bits=4 * n * W, x16=2 * n * K, x32=4 * n * K, flags=n)
+  total, offs = gap, {}
+  for k, v in sizes.items():
+    offs[k] = total
+    total += (v + 255) // 256 * 256 + gap
+  arena = torch.full((total,), 0xA5, dtype=torch.uint8, device=dev)
+  view = lambda k, dt, shape: arena[offs[k]:offs[k] + sizes[k]].view(dt).view(shape)
+  obs, mask = view("obs", torch.uint8, (n, D)), view("mask", torch.uint8, (n, A))
+  cur, rew = view("cur", torch.int32, (n,)), view("rew", torch.int32, (n,))
+  done, score = view("done", torch.uint8, (n,)), view("score", torch.int32, (n,))
+  act, bits = view("act", torch.int32, (n,)), view("bits", torch.int32, (n, W))
+  x16, x32 = view("x16", torch.bfloat16, (n, K)), view("x32", torch.float32, (n, K))
+  b.reset()
+  b.observe(obs, mask, cur)
+  for t in range(30):
+    ph.select_action(None, mask, 1.0, seed=4, step=t, out=act)
+    kind = t % 6
+    if kind == 0:
+      b.step_encode(act, rew, done, obs, mask, cur, scores=score)
+    elif kind == 1:
+      b.step_encode_random(act, 4, t, rew, done, obs, mask, cur, scores=score)
+      b.legal_mask(mask)
+    elif kind == 2:
+      b.step_encode_packed(act, rew, done, bits, mask, cur, scores=score)
+    elif kind == 3:
+      b.step_encode_net(act, x16, rew, done, obs_bits=bits, mask=mask, cur_player=cur, scores=score)
+    elif kind == 4:
+      b.step_encode_net(act, x32, rew, done, mask=mask, cur_player=cur)
+    else:
+      b.step(act, rew, done, score)
+      b.observe(obs, mask, cur)
+  b.observe_packed(bits, mask, cur)
+  b.observe_net(x16, obs_bits=bits)
+  ph.expand_packed(bits, D, x32)
+  keep = torch.ones(total, dtype=torch.bool, device=dev)
+  for k, v in sizes.items():
+    keep[offs[k]:offs[k] + v] = False
+  assert bool((arena[keep] == 0xA5).all()), "a kernel wrote outside its output buffers"
