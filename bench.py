@@ -700,9 +700,34 @@ def main():
       for t in range(args.e2e_steps):
         packed_host_step(3 + t)
       dtp = time.perf_counter() - t0
-      packed["e2e"] = {"value": world * ne * args.e2e_steps / dtp, "unit": "env-steps/s",
+      single_p = world * ne * args.e2e_steps / dtp
+      # pipelined (BatchStepEncodeHostRangePacked + BatchHostWait), as the byte-row e2e above
+      launch_p, wait_p = hb2.bind_step_encode_host_range(q_act, q_rew, q_done, None, q_mask, q_cur,
+                                                         obs_bits=q_bits)
+      rs_p = (ne // 8 + 127) // 128 * 128
+      ranges_p = [(lo, min(lo + rs_p, ne) - lo) for lo in range(0, ne, rs_p)]
+      views_p = [(q_mask[lo:lo + cnt], q_act[lo:lo + cnt]) for lo, cnt in ranges_p]
+
+      def piped_packed(t):
+        for (lo, cnt), (m_v, a_v) in zip(ranges_p, views_p):
+          wait_p(lo)
+          ph.host_random_legal_actions(m_v, seed=7, step=t, out=a_v)
+          launch_p(lo, cnt)
+
+      for t in range(3):
+        piped_packed(200 + t)
+      wait_p(-1)
+      steps_p = 3 * args.e2e_steps
+      t0 = time.perf_counter()
+      for t in range(steps_p):
+        piped_packed(203 + t)
+      wait_p(-1)
+      dtp = time.perf_counter() - t0
+      packed["e2e"] = {"value": world * ne * steps_p / dtp, "unit": "env-steps/s",
                        "d2h_bytes_per_step": ne * (4 * Wp + A + 9), "h2d_bytes_per_step": ne * 4,
-                       "games_per_step": ne}
+                       "games_per_step": ne, "ms_per_step": dtp / steps_p * 1e3,
+                       "single_call": single_p,
+                       "note": "BatchStepEncodeHostRangePacked/BatchHostWait, %d ranges per step" % len(ranges_p)}
       del hb2
 
   if rank != 0:

@@ -1143,10 +1143,10 @@ static int StepHost(pyhanabi_batch_t* h, const int32_t* actions, int32_t* reward
 // buffers are complete after BatchHostWait(batch, first_game).  While one range is in
 // flight the caller can prepare the actions of the next (the policy of range c overlaps the
 // transfers of range c-1), which keeps the PCIe link busy for the whole step.
-int BatchStepEncodeHostRange(pyhanabi_batch_t* h, int64_t first_game, int64_t num_games,
-                             const int32_t* actions, int32_t* rewards, uint8_t* dones,
-                             int32_t* scores, uint8_t* obs, int64_t row_pitch, uint8_t* mask,
-                             int32_t* cur_player, int auto_reset) {
+static int StepHostRange(pyhanabi_batch_t* h, int64_t first_game, int64_t num_games,
+                         const int32_t* actions, int32_t* rewards, uint8_t* dones,
+                         int32_t* scores, uint8_t* obs, int64_t row_pitch, uint32_t* obs_bits,
+                         uint8_t* mask, int32_t* cur_player, int auto_reset) {
   HB_BATCH(h);
   if (!actions) return Fail("BatchStepEncodeHostRange: actions is null");
   if (obs && row_pitch < b->spec.obs_size) return Fail("BatchStepEncodeHostRange: row_pitch smaller than the observation");
@@ -1156,11 +1156,28 @@ int BatchStepEncodeHostRange(pyhanabi_batch_t* h, int64_t first_game, int64_t nu
   const int slot = b->range_next++ % Batch::kRangeSlots;
   cudaStream_t s = b->h_streams[slot % 3];
   if (EnqueueHostRange(b, (size_t)first_game, (size_t)(first_game + num_games), actions, rewards, dones,
-                       scores, obs, row_pitch, nullptr, mask, cur_player, auto_reset, s))
+                       scores, obs, row_pitch, obs_bits, mask, cur_player, auto_reset, s))
     return 1;
   HB_CUDA(cudaEventRecord(b->range_events[slot], s));
   b->range_first[slot] = first_game;
   return 0;
+}
+
+int BatchStepEncodeHostRange(pyhanabi_batch_t* h, int64_t first_game, int64_t num_games,
+                             const int32_t* actions, int32_t* rewards, uint8_t* dones,
+                             int32_t* scores, uint8_t* obs, int64_t row_pitch, uint8_t* mask,
+                             int32_t* cur_player, int auto_reset) {
+  return StepHostRange(h, first_game, num_games, actions, rewards, dones, scores, obs, row_pitch, nullptr,
+                       mask, cur_player, auto_reset);
+}
+
+// Same with bit-packed observation rows in the host buffer (BatchStepEncodeHostPacked, ranged).
+int BatchStepEncodeHostRangePacked(pyhanabi_batch_t* h, int64_t first_game, int64_t num_games,
+                                   const int32_t* actions, int32_t* rewards, uint8_t* dones,
+                                   int32_t* scores, uint32_t* obs_bits, uint8_t* mask,
+                                   int32_t* cur_player, int auto_reset) {
+  return StepHostRange(h, first_game, num_games, actions, rewards, dones, scores, nullptr, 0, obs_bits,
+                       mask, cur_player, auto_reset);
 }
 
 // Blocks until the most recent BatchStepEncodeHostRange call that started at first_game has

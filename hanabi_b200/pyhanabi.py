@@ -950,23 +950,27 @@ class HanabiBatch(object):
            "BatchStepEncodeHostPacked")
 
   def bind_step_encode_host_range(self, actions, rewards=None, dones=None, obs=None, mask=None,
-                                  cur_player=None, scores=None, auto_reset=True):
+                                  cur_player=None, scores=None, auto_reset=True, obs_bits=None):
     """Pre-bound BatchStepEncodeHostRange: returns (launch(first, count), wait(first)).
     launch queues the step of games [first, first + count) and returns at once; wait
     blocks until that range's host buffers are filled (first < 0: everything)."""
     torch = self._torch
     n = self.num_games
-    optr, pitch = self._h_obs(obs)
-    args = (self._h(actions, torch.int32, n, "int32_t*"), self._h(rewards, torch.int32, n, "int32_t*"),
-            self._h(dones, torch.uint8, n, "uint8_t*"), self._h(scores, torch.int32, n, "int32_t*"),
-            optr, pitch,
-            self._h(mask, torch.uint8, n * self.max_moves, "uint8_t*"),
+    head = (self._h(actions, torch.int32, n, "int32_t*"), self._h(rewards, torch.int32, n, "int32_t*"),
+            self._h(dones, torch.uint8, n, "uint8_t*"), self._h(scores, torch.int32, n, "int32_t*"))
+    tail = (self._h(mask, torch.uint8, n * self.max_moves, "uint8_t*"),
             self._h(cur_player, torch.int32, n, "int32_t*"), int(bool(auto_reset)))
-    keep = (actions, rewards, dones, obs, mask, cur_player, scores)
+    if obs_bits is not None:  # bit-packed rows in the host buffer instead of bytes
+      fn = lib.BatchStepEncodeHostRangePacked
+      args = head + (self._h(obs_bits, torch.int32, n * self.packed_words, "uint32_t*"),) + tail
+    else:
+      fn = lib.BatchStepEncodeHostRange
+      args = head + self._h_obs(obs) + tail
+    keep = (actions, rewards, dones, obs, obs_bits, mask, cur_player, scores)
     c = self._c
 
-    def launch(first, count, _args=args, _keep=keep):
-      if lib.BatchStepEncodeHostRange(c, first, count, *_args) != 0:
+    def launch(first, count, _args=args, _keep=keep, _fn=fn):
+      if _fn(c, first, count, *_args) != 0:
         raise RuntimeError("BatchStepEncodeHostRange failed: %s" %
                            encode_ffi_string(lib.BatchLastError()))
 

@@ -292,6 +292,10 @@ int BatchStepEncodeHostRange(pyhanabi_batch_t* batch, int64_t first_game, int64_
                              const int32_t* actions, int32_t* rewards, uint8_t* dones,
                              int32_t* scores, uint8_t* obs, int64_t row_pitch, uint8_t* mask,
                              int32_t* cur_player, int auto_reset);
+int BatchStepEncodeHostRangePacked(pyhanabi_batch_t* batch, int64_t first_game,
+                                   int64_t num_games, const int32_t* actions, int32_t* rewards,
+                                   uint8_t* dones, int32_t* scores, uint32_t* obs_bits,
+                                   uint8_t* mask, int32_t* cur_player, int auto_reset);
 int BatchHostWait(pyhanabi_batch_t* batch, int64_t first_game);
 int BatchResetHost(pyhanabi_batch_t* batch, uint8_t* obs, int64_t row_pitch, uint8_t* mask,
                    int32_t* cur_player, void* stream);

@@ -298,6 +298,23 @@ def test_ranged_async_host_step_matches_the_synchronous_call():
       assert torch.equal(ta[k], tb[k]), (k, t)
   with pytest.raises(RuntimeError, match="multiple of 128"):
     launch(64, 128)
+  # the same ranges with bit-packed rows in the host buffer (BatchStepEncodeHostRangePacked)
+  bits = pin(n, b.packed_words, dt=torch.int32)
+  launch_p, wait_p = b.bind_step_encode_host_range(tb["act"], tb["rew"], tb["done"], None, tb["mask"],
+                                                   tb["cur"], scores=tb["score"], obs_bits=bits)
+  dev_bits = torch.zeros((n, b.packed_words), dtype=torch.int32, device="cuda")
+  for t in range(10, 14):
+    ph.host_random_legal_actions(ta["mask"], seed=3, step=t, out=ta["act"])
+    a.step_encode_host(ta["act"], ta["rew"], ta["done"], ta["obs"], ta["mask"], ta["cur"], scores=ta["score"])
+    for lo, cnt in ranges:
+      wait_p(lo)
+      tb["act"][lo:lo + cnt].copy_(ta["act"][lo:lo + cnt])
+      launch_p(lo, cnt)
+    wait_p(-1)
+    for k in ("mask", "cur", "rew", "done", "score"):
+      assert torch.equal(ta[k], tb[k]), (k, t)
+    a.observe_packed(dev_bits)
+    assert torch.equal(dev_bits.cpu(), bits), t
 
 
 @pytest.mark.parametrize("players,game", [(3, "Hanabi-Small"), (2, "Hanabi-Full")])
