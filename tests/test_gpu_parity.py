@@ -59,6 +59,22 @@ def test_keep_alive_policy_lockstep(name):
     assert max_score >= 15
 
 
+@pytest.mark.parametrize("name", ["small2", "full4"])
+def test_rng_stream_across_block_wraps(name):
+  """Long lock-step run: every game takes several thousand mt19937 words, i.e. its
+  624-word block is regenerated in place several times over (slot 623 / slot 0 boundary,
+  the 397-slot look-ahead wrapping), through in-game deals and re-deals alike."""
+  n = 96
+  seeds = common.seeds_for(n, base=31337)
+  cpu = _checker(CONFIGS[name], n, seeds)
+  gpu = GpuBatch(CONFIGS[name], n, seeds)
+  cpu.reset(); gpu.reset()
+  steps = 1200 if name == "small2" else 900
+  eps, _ = common.lockstep(cpu, gpu, steps, np.random.default_rng(13), False, CONFIGS[name],
+                           dump_every=150)
+  assert eps > n
+
+
 def test_full2_at_survey_size():
   """SURVEY.md section 8d parity run: 4096 games x 256 steps, Hanabi-Full 2p."""
   n = 4096
