@@ -540,16 +540,18 @@ __global__ void k_export(KArgs a, int64_t g, int32_t* out) {
 }
 
 // Per-game error flags (an illegal action was submitted since the last clear).
-__global__ void k_errors(uint4* state, int64_t N, int col, uint8_t* flags, int clear,
+// The flag is bit `bit` of word `word` of column `col` (general layout: column P + 1, x, bit 31;
+// compact layout: column P, y, bit 25).
+__global__ void k_errors(uint4* state, int64_t N, int col, int word, int bit, uint8_t* flags, int clear,
                          unsigned long long* count) {
   const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   bool err = false;
   if (g < N) {
-    uint32_t* x = &state[(int64_t)col * N + g].x;
+    uint32_t* x = &state[(int64_t)col * N + g].x + word;
     const uint32_t v = *x;
-    err = (v >> 31) & 1u;
+    err = (v >> bit) & 1u;
     if (flags) flags[g] = err ? 1 : 0;
-    if (clear && err) *x = v & 0x7fffffffu;
+    if (clear && err) *x = v & ~(1u << bit);
   }
   const unsigned m = __ballot_sync(kFull, err);
   if (count && m && (threadIdx.x & 31) == 0) atomicAdd(count, (unsigned long long)__popc(m));
@@ -859,7 +861,7 @@ int NewBatch(pyhanabi_batch_t* out, int list_length, const char** param_list, in
   }
   b->device = device;
   b->N = num_games;
-  b->ncols = b->spec.P + 2;
+  b->ncols = hb::state_columns(b->spec.P);
   b->packed_words = 4 * ((b->spec.obs_size + 127) / 128);
   b->obs_stream_words = b->spec.obs_size > 32 * b->packed_words ? b->spec.obs_size : 32 * b->packed_words;
   b->obs_stream_words = (b->obs_stream_words + 3) & ~3;
@@ -1375,7 +1377,9 @@ int BatchUnpackState(pyhanabi_batch_t* h, int32_t* dump, void* stream) {
 int BatchErrorFlags(pyhanabi_batch_t* h, uint8_t* flags, uint64_t* count, int clear, void* stream) {
   HB_BATCH(h);
   const unsigned grid = (unsigned)((b->N + 127) / 128);
-  hb::k_errors<<<grid, 128, 0, (cudaStream_t)stream>>>(b->state, b->N, b->spec.P + 1, flags, clear,
+  const bool compact = hb::state_columns(b->spec.P) == b->spec.P + 1;
+  hb::k_errors<<<grid, 128, 0, (cudaStream_t)stream>>>(b->state, b->N, compact ? b->spec.P : b->spec.P + 1,
+                                                       compact ? 1 : 0, compact ? 25 : 31, flags, clear,
                                                        reinterpret_cast<unsigned long long*>(count));
   HB_CUDA(cudaGetLastError());
   return 0;
@@ -1483,7 +1487,7 @@ int BatchReadStats(pyhanabi_batch_t* h, int64_t* host_stats, int clear, void* st
   return 0;
 }
 
-// Keeps the packed game state (16*(P+2) bytes per game) resident in the L2 cache
+// Keeps the packed game state (16 bytes per column and game) resident in the L2 cache
 // between steps: every launch on this batch carries an access-policy window over
 // the state array (persisting on hit, streaming on miss), and the device's
 // persisting-L2 carve-out is raised to `max_bytes` (0 = the device maximum,
