@@ -43,6 +43,9 @@ enum Mode { kModeStep = 0, kModeReset = 1, kModeObserve = 2 };
 #ifndef HB_RESET_PREFETCH
 #define HB_RESET_PREFETCH 1
 #endif
+#ifndef HB_RESET_PREFETCH_ALL
+#define HB_RESET_PREFETCH_ALL 0
+#endif
 // Games per CTA come with the rule-set view (V::kBlock); 768 threads are resident per SM.
 #ifndef HB_RESIDENT
 #define HB_RESIDENT 768  // measured again on the final kernel: 640 (90 registers, no spills) 0.5-0.7 % slower
@@ -203,7 +206,10 @@ __global__ void __launch_bounds__(V::kBlock, kResidentThreads / V::kBlock) k_mai
       }
 #endif
 #if HB_RESET_PREFETCH
-      if (restart && a.spec.fast_reset) mt_prefetch_deal(a.mt + g * (int64_t)kMtN, G.mti, v.P() * v.H());
+      // (only where the re-deal is the serial path: with the warp-parallel Lehmer decode the
+      // lines arrive by coalesced loads anyway and the prefetches only add traffic)
+      if (HB_RESET_PREFETCH_ALL || !hb::lehmer_for(V::kP * V::kH))
+        if (restart && a.spec.fast_reset) mt_prefetch_deal(a.mt + g * (int64_t)kMtN, G.mti, v.P() * v.H());
 #endif
       // episode statistics: warp aggregate -> CTA shared counters
       const unsigned tm = __ballot_sync(kFull, term);
@@ -1351,8 +1357,8 @@ int BatchSetState(pyhanabi_batch_t* h, const void* host_blob, int64_t nbytes) {
   int64_t header[8];
   std::memcpy(header, host_blob, 64);
   if (header[0] != 0x4842323030ll || header[1] != b->N || header[2] != b->spec.P ||
-      header[4] != b->spec.obs_size || header[5] != b->spec.max_moves)
-    return Fail("BatchSetState: blob does not match this batch (games / rules differ)");
+      header[3] != b->ncols || header[4] != b->spec.obs_size || header[5] != b->spec.max_moves)
+    return Fail("BatchSetState: blob does not match this batch (games / rules / state layout differ)");
   HB_CUDA(cudaDeviceSynchronize());
   const char* p = static_cast<const char*>(host_blob) + 64;
   const size_t sb = sizeof(uint4) * (size_t)b->ncols * (size_t)b->N;
