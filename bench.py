@@ -39,6 +39,8 @@ WORKLOADS = {
 # obs_dim + A (uint8 mask) + 4 (reward) + 1 (done) + 4 (action) + 2 * S (packed state r+w).
 ALGO_BYTES = {"hanabi_full_2p": 815, "hanabi_full_4p": 1248, "hanabi_full_5p": 1529,
               "hanabi_small_2p": 255, "hanabi_small_4p": 411}
+POLICY_SEED = 7
+INIT_POLICY_STEP = 1 << 40  # key of the rollout's first actions (the steps count from 0)
 FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md, used only without MEASURED_PEAKS.json
 
 
@@ -51,8 +53,18 @@ def parse_args():
   ap.add_argument("--workload", default="hanabi_full_2p", choices=sorted(WORKLOADS))
   ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
   ap.add_argument("--e2e-steps", type=int, default=12)
-  ap.add_argument("--e2e-games", type=int, default=1 << 18)
-  ap.add_argument("--cpu-seconds", type=float, default=12.0)
+  ap.add_argument("--e2e-games", type=int, default=0,
+                  help="games of the host-buffer leg (0 = the same games per GPU as the device leg)")
+  ap.add_argument("--cpu-seconds", type=float, default=8.0)
+  ap.add_argument("--reference-seconds", type=float, default=3.0,
+                  help="--impl reference: minimum wall time of the timed CPU rollout")
+  ap.add_argument("--python-seconds", type=float, default=2.0,
+                  help="seconds per Python-path CPU leg (BASELINE.md section 3, C1-C3); 0 = skip")
+  ap.add_argument("--no-parity-check", action="store_true",
+                  help="skip the replay of sampled games on the CPU reference after the timed region")
+  ap.add_argument("--parity-games", type=int, default=64)
+  ap.add_argument("--no-policy-extras", action="store_true",
+                  help="skip the short Rainbow-policy rollout reported under `policies`")
   ap.add_argument("--no-cpu-baseline", action="store_true")
   ap.add_argument("--separate-policy", action="store_true",
                   help="random policy as its own kernel (BatchSelectAction) instead of the step "
@@ -73,10 +85,10 @@ def parse_args():
                   help="random policy only: split each GPU's games into this many independent "
                        "batches on their own CUDA streams, so that one launch's last, partly "
                        "filled wave of CTAs overlaps the other's body (1 = one launch per step)")
-  ap.add_argument("--packed", action="store_true",
-                  help="also measure the optional bit-packed observation output (extra key)")
-  ap.add_argument("--python-baselines", action="store_true",
-                  help="also time the Python paths of BASELINE.md section 3 (C1-C3) on the host")
+  ap.add_argument("--packed", action="store_true", default=True, help=argparse.SUPPRESS)
+  ap.add_argument("--no-packed", dest="packed", action="store_false",
+                  help="skip the bit-packed observation output (the `packed_obs` extra key)")
+  ap.add_argument("--python-baselines", action="store_true", help=argparse.SUPPRESS)  # now the default
   ap.add_argument("--cpu-python-worker", default=None, help=argparse.SUPPRESS)
   ap.add_argument("--policy", default="random", choices=["random", "rainbow", "adhoc", "ppo"],
                   help="random: uniform legal (headline); rainbow: fixed-weight C51 MLP "
@@ -149,7 +161,9 @@ class ClockSampler(object):
 def cpu_reference_rate(workload, seconds, threads=None):
   """Times the reference's own CPU engine (oracle/_ref, unmodified sources) -- or
   the C port when it was not built -- on this box's host cores: random-legal
-  rollout with auto-reset, current-player observation + legal mask per step."""
+  rollout with auto-reset, current-player observation + legal mask per step.
+  One long threaded rollout of at least `seconds` wall time (thread start-up and
+  cache warm-up amortised), preceded by an untimed calibration pass."""
   import numpy as np
   from oracle import oracle as O
   threads = threads or os.cpu_count() or 1
@@ -159,16 +173,18 @@ def cpu_reference_rate(workload, seconds, threads=None):
   n = 512 * threads
   b = O.CpuBatch(kind, WORKLOADS[workload], n, (np.arange(n) + 1).astype(np.int32))
   b.reset()
+  b.rollout(4, threads)  # page in, desynchronise the games a little
   t0 = time.perf_counter()
-  b.rollout(8, threads)  # warm-up + calibration
-  per_pass = max((time.perf_counter() - t0) / 8, 1e-6)
-  steps = max(8, int(seconds / per_pass))
+  b.rollout(16, threads)  # calibration
+  per_pass = max((time.perf_counter() - t0) / 16, 1e-6)
+  steps = max(16, int(seconds / per_pass) + 1)
   t0 = time.perf_counter()
   total, episodes, score_sum = b.rollout(steps, threads)
   dt = time.perf_counter() - t0
   return {"value": total / dt, "unit": "env-steps/s", "cores": threads,
           "kind": "reference" if kind == "ref" else "port",
-          "sample": "%d games x %d steps, random-legal policy, auto-reset, %.1f s" % (n, steps, dt)}
+          "sample": "%d games x %d steps, random-legal policy, auto-reset, %.1f s" % (n, steps, dt),
+          "seconds": dt, "games": n, "steps": steps}
 
 
 def python_worker(mode, seconds, seed, workload):
@@ -212,7 +228,7 @@ def python_worker(mode, seconds, seed, workload):
   print(json.dumps({"steps": steps, "seconds": time.perf_counter() - t0}), flush=True)
 
 
-def python_baselines(workload, seconds=4.0):
+def python_baselines(workload, seconds=2.0):
   """BASELINE.md section 3, C1-C3, on this box's host cores."""
   import subprocess
   from oracle import oracle as O
@@ -236,40 +252,78 @@ def python_baselines(workload, seconds=4.0):
 
 
 def run_reference_arm(args, rank):
-  """--impl reference: the reference's CPU implementation of the path, all host threads."""
+  """--impl reference: the reference's CPU implementation of the path, all host
+  threads.  The driver's --steps/--warmup are echoed; the timed rollout itself runs
+  for at least --reference-seconds of wall time (a 20-step sample is 40 ms: thread
+  start-up and cold caches would dominate it), so `ms_per_step` is the steady-state
+  time of one step over `games_per_step` games."""
   if rank != 0:
     return
-  import numpy as np
-  from oracle import oracle as O
-  threads = os.cpu_count() or 1
-  kind = "ref" if O.have_ref() else "oracle"
-  if kind == "oracle":
-    threads = 1
-  n = 256 * threads  # bounded sample of the workload per step
-  b = O.CpuBatch(kind, WORKLOADS[args.workload], n, (np.arange(n) + 1).astype(np.int32))
-  b.reset()
-  steps = min(args.steps, 4000)
-  b.rollout(max(args.warmup, 3), threads)
-  t0 = time.perf_counter()
-  total, _, _ = b.rollout(steps, threads)
-  dt = time.perf_counter() - t0
-  value = total / dt
-  sample = "%d games x %d steps per run (bounded sample of %s), random-legal policy" % (
-      n, steps, args.workload)
+  r = cpu_reference_rate(args.workload, max(args.reference_seconds, 2.0))
+  value = r["value"]
+  sample = "%d games per step, %d steps timed in one threaded rollout of %.1f s (bounded sample of %s), random-legal policy" % (
+      r["games"], r["steps"], r["seconds"], args.workload)
   line = {
       "impl": "reference", "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s",
-      "n_gpus": args.gpus, "steps": steps, "warmup": max(args.warmup, 3),
-      "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak",
+      "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
+      "ms_per_step": r["seconds"] / r["steps"] * 1e3, "higher_is_better": True, "scaling": "weak",
       "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-      "config": {"workload": args.workload, "games_per_step": n, "policy": "uniform random legal",
-                 "note": "reference C++ engine (oracle/_ref) on host cores"},
-      "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": threads,
-                       "kind": "reference" if kind == "ref" else "port", "sample": sample},
+      "config": {"workload": args.workload, "games_per_step": r["games"], "steps_timed": r["steps"],
+                 "policy": "uniform random legal",
+                 "note": "reference C++ engine (oracle/_ref) on host cores; timed for >= %.0f s "
+                         "whatever --steps says" % max(args.reference_seconds, 2.0)},
+      "cpu_baseline": {"value": value, "unit": "env-steps/s", "cores": r["cores"],
+                       "kind": r["kind"], "sample": sample},
       "e2e": {"value": value, "unit": "env-steps/s", "h2d_bytes_per_step": 0,
               "d2h_bytes_per_step": 0},
       "gpu_launches": 0,
   }
   print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------ parity of sampled games (checker)
+def _mix64(z):
+  import numpy as np
+  with np.errstate(over="ignore"):
+    z = z + np.uint64(0x9E3779B97F4A7C15)
+    z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+    z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+    return z ^ (z >> np.uint64(31))
+
+
+def policy_draw(mask, seed, step, games):
+  """numpy twin of the engine's counter-based uniform-legal draw
+  (hanabi_b200/csrc/hb_policy_rng.h): action of every row of `mask` for the key
+  (seed, step, games[i]); -1 where nothing is legal."""
+  import numpy as np
+  with np.errstate(over="ignore"):
+    inner = _mix64(np.uint64(seed) ^ (np.uint64(step) * np.uint64(0xD1B54A32D192ED03)))
+    bits = _mix64(inner ^ (games.astype(np.uint64) * np.uint64(0x8CB92BA72F3D8DD7)))
+  n_legal = mask.sum(axis=1).astype(np.uint64)
+  k = (((bits & np.uint64(0xffffffff)) * n_legal) >> np.uint64(32)).astype(np.int64)
+  order = np.cumsum(mask != 0, axis=1) - 1  # rank of each legal move within its row
+  hit = (mask != 0) & (order == k[:, None])
+  act = np.where(hit.any(axis=1), hit.argmax(axis=1), -1).astype(np.int32)
+  return act
+
+
+def replay_on_cpu(workload, global_games, seed, init_step, num_steps):
+  """The sampled games stepped on the CPU checker (the reference engine from
+  oracle/_ref when it was built, else the C port) with the very policy keys the GPU
+  used: returns (obs, mask, cur_player, next_action) after num_steps env-steps."""
+  import numpy as np
+  from oracle import oracle as O
+  kind = "ref" if O.have_ref() else "oracle"
+  g = np.asarray(global_games, np.int64)
+  b = O.CpuBatch(kind, WORKLOADS[workload], len(g), (1 + g).astype(np.int32))
+  b.reset()
+  act = policy_draw(b.legal_mask(), seed, init_step, g)
+  for t in range(num_steps):
+    _, _, _, illegal = b.step(act)
+    if illegal.any():
+      raise AssertionError("CPU replay: illegal action at step %d" % t)
+    act = policy_draw(b.legal_mask(), seed, t, g)
+  return b.encode(), b.legal_mask(), b.cur_player(), act, kind
 
 
 # -------------------------------------------------------------------- GPU arm
@@ -286,9 +340,8 @@ def main():
     run_reference_arm(args, rank)
     return
 
-  import numpy as np
+  import copy
   import torch
-  from hanabi_b200 import pyhanabi as ph
 
   if not torch.cuda.is_available():
     raise SystemExit("bench.py needs a CUDA device; the engine has no CPU fallback")
@@ -300,6 +353,42 @@ def main():
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # keep stdout to the one JSON line
     dist.init_process_group("nccl", device_id=dev)
+  cores = None
+  if world > 1:
+    from hanabi_b200 import sharding
+    cores = sharding.bind_rank_to_local_cores(local_rank, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
+  ctx = dict(rank=rank, local_rank=local_rank, world=world, dev=dev, dist=dist,
+             cores=sorted(cores) if cores else None)
+
+  line = gpu_arm(args, ctx, extra=False)
+  if args.policy == "random" and args.workload == "hanabi_full_2p" and not args.no_policy_extras:
+    # BASELINE.json configs[3]: a short Rainbow-policy rollout (bf16 library GEMMs, our step /
+    # select kernels, one CUDA graph per step) on every rank, reported beside the headline
+    a2 = copy.copy(args)
+    a2.policy, a2.mlp_dtype, a2.games = "rainbow", "bf16", min(args.games, 1 << 18)
+    a2.steps, a2.warmup, a2.record = min(args.steps, 100), min(max(args.warmup, 3), 10), False
+    torch.cuda.empty_cache()
+    extra_line = gpu_arm(a2, ctx, extra=True)
+    if line is not None and extra_line is not None:
+      line["policies"] = {"rainbow": {k: extra_line[k] for k in
+                                      ("value", "unit", "ms_per_step", "steps", "warmup", "gpu_launches")}}
+      line["policies"]["rainbow"].update(
+          games_per_gpu=a2.games, mlp_dtype="bf16", policy=extra_line["config"]["policy"],
+          step_kernel_ms=extra_line["roofline"]["kernel_ms"],
+          step_kernel_frac=extra_line["roofline"]["frac"])
+  if line is not None:
+    print(json.dumps(line), flush=True)
+  if dist:
+    dist.destroy_process_group()
+
+
+def gpu_arm(args, ctx, extra):
+  """One measured configuration on this rank's GPU; returns the JSON line on rank 0
+  (None elsewhere).  extra=True: device-timed part only (no e2e, CPU legs, parity)."""
+  import numpy as np
+  import torch
+  from hanabi_b200 import pyhanabi as ph
+  rank, local_rank, world, dev, dist = (ctx[k] for k in ("rank", "local_rank", "world", "dev", "dist"))
 
   # ad-hoc team: below 32 768 games per GPU the host sync of the row gather costs more than
   # running the MLP on every game
@@ -322,6 +411,7 @@ def main():
   def make_shard(lo, hi):
     m = hi - lo
     b = ph.HanabiBatch(params, m, seeds[lo:hi], device=local_rank)
+    b.set_game_index_base(rank * n + lo)  # the policy key's game = global index
     t = dict(obs=torch.empty((m, b.obs_size), dtype=torch.uint8, device=dev),
              mask=torch.empty((m, b.max_moves), dtype=torch.uint8, device=dev),
              cur=torch.empty(m, dtype=torch.int32, device=dev),
@@ -353,8 +443,8 @@ def main():
     streams = [torch.cuda.Stream(device=dev) for _ in range(S)] if S > 1 else [torch.cuda.current_stream()]
     runs = []
     for (b_i, t_i), st in zip(shard_list, streams):
-      ph.select_action(None, t_i["mask"], 1.0, seed=7, step=0, out=t_i["act"])
-      runs.append(b_i.bind_step_encode_random(t_i["act"], 7, t_i["rew"], t_i["done"], t_i["obs"],
+      b_i.random_legal_actions(t_i["act"], POLICY_SEED, INIT_POLICY_STEP)
+      runs.append(b_i.bind_step_encode_random(t_i["act"], POLICY_SEED, t_i["rew"], t_i["done"], t_i["obs"],
                                               t_i["mask"], t_i["cur"], stream=st))
     torch.cuda.synchronize()
 
@@ -508,9 +598,6 @@ def main():
   stats.zero_()
   posted_total[0] = 0
   torch.cuda.synchronize()
-  if dist:
-    dist.barrier()
-    torch.cuda.synchronize()
 
   graph_kernel_ms = None
   if use_graph:
@@ -533,12 +620,29 @@ def main():
     posted_total[0] = 0
     torch.cuda.synchronize()
 
+  # Everything the timed region needs exists before the ranks line up: the NVML sampler, the
+  # events, and NCCL's kernels for the two collectives used below (a first use would load them).
   sampler = ClockSampler(local_rank)
   ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  ev2 = torch.cuda.Event(enable_timing=True)
   k_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-          for _ in range(K)]
-  sampler.start()
+          for _ in range(0 if (fused_policy or use_graph) else K)]
   main_stream = torch.cuda.current_stream()
+  line_up = torch.zeros(1, dtype=torch.int64, device=dev)
+  if dist:
+    warm_stats = torch.zeros_like(stats)
+    sharding.reduce_episode_statistics(warm_stats)  # int64 sum all-reduce, as after the steps
+    warm_max = torch.zeros(1, dtype=torch.float64, device=dev)
+    dist.all_reduce(warm_max, op=dist.ReduceOp.MAX)
+    dist.all_reduce(line_up)
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+  sampler.start()
+  if dist:
+    # the window opens in-stream behind one more tiny all-reduce: every rank's ev0 fires when
+    # that collective completes on its GPU, no host synchronisation in between
+    dist.all_reduce(line_up)
   ev0.record()
   if fused_policy:
     # one kind of launch in the timed region: its average duration is elapsed / launches,
@@ -561,11 +665,16 @@ def main():
       step_encode(W + t)
       k_ev[t][1].record()
       after_step()
-  sharding.reduce_episode_statistics(stats)  # the only collective: 256 B over NCCL (no-op at N=1)
   ev1.record()
+  # the only collective, off the step path: 256 B of episode statistics
+  # over NCCL (no-op at N=1), timed on its own
+  sharding.reduce_episode_statistics(stats)
+  ev2.record()
   torch.cuda.synchronize()
   clocks = sampler.stop()
   elapsed_ms = ev0.elapsed_time(ev1)
+  stats_allreduce_us = ev1.elapsed_time(ev2) * 1e3 if dist else 0.0
+  own_ms = elapsed_ms
   # fused policy: S concurrent launches cover one step of all games, so the step time is
   # the launch time of the kernel over n games
   if fused_policy:
@@ -574,31 +683,70 @@ def main():
     kernel_ms = graph_kernel_ms
   else:
     kernel_ms = sum(a.elapsed_time(b) for a, b in k_ev) / K
+  rank_ms = [elapsed_ms]
   if dist:
     tmax = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
-    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(tmax.item())
-    dist.barrier()
+    gathered = [torch.zeros_like(tmax) for _ in range(world)]
+    dist.all_gather(gathered, tmax)
+    rank_ms = [float(x.item()) for x in gathered]
+    elapsed_ms = max(rank_ms)  # the job is as fast as its slowest rank
   value = world * n * K / (elapsed_ms * 1e-3)
+  if fused_policy:
+    kernel_ms = elapsed_ms / K  # the slowest rank's, like the value
+  st = stats.cpu().tolist()  # episode statistics of the timed region, summed over the ranks
 
+  # ---- parity of sampled games: every rank replays some of ITS games (global indices,
+  # global policy keys) on the CPU reference and compares what the GPU holds after the
+  # W + K steps above -- a sharded run must equal the unsharded one game for game.
+  parity = None
+  if fused_policy and not extra and not args.no_parity_check:
+    torch.cuda.synchronize()
+    total_steps = W + K
+    m = n // S
+    per_shard = max(1, args.parity_games // S)
+    ok, checked, kind = True, 0, None
+    for si, (b_i, t_i) in enumerate(shard_list):
+      local = np.unique(np.concatenate([np.array([0, m - 1]),
+                                        np.linspace(0, m - 1, per_shard).astype(np.int64)]))
+      glob = rank * n + si * m + local
+      c_obs, c_mask, c_cur, c_act, kind = replay_on_cpu(args.workload, glob, POLICY_SEED,
+                                                        INIT_POLICY_STEP, total_steps)
+      idx = torch.as_tensor(local, device=dev)
+      ok = ok and bool((t_i["obs"][idx].cpu().numpy() == c_obs).all())
+      ok = ok and bool((t_i["mask"][idx].cpu().numpy() == c_mask).all())
+      ok = ok and bool((t_i["cur"][idx].cpu().numpy() == c_cur).all())
+      ok = ok and bool((t_i["act"][idx].cpu().numpy() == c_act).all())
+      checked += len(local)
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int64, device=dev)
+    if dist:
+      dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    parity = {"ok": bool(flag.item()), "games_per_rank": checked, "steps_replayed": total_steps,
+              "checker": "reference engine (oracle/_ref)" if kind == "ref" else "C port (oracle/)",
+              "compared": "observation bytes, legal mask, player to act, next random action",
+              "ranks": world}
+    if not parity["ok"]:
+      raise SystemExit("bench.py: rank %d: sampled games differ from the CPU reference" % rank)
   # ---- e2e: the same step through the C-ABI with HOST buffers (pinned); the
   # timed region holds the host policy, the action upload, the kernel and the
   # download of observation, mask, reward, done and player index.
-  ne = min(args.e2e_games, n)
+  ne = min(args.e2e_games, n) if args.e2e_games > 0 else n
   e2e = None
-  if args.e2e_steps > 0:
+  if args.e2e_steps > 0 and not extra:
     hb = ph.HanabiBatch(params, ne, seeds[:ne], device=local_rank)
+    hb.set_game_index_base(rank * n)
     pin = lambda *shape, dt: torch.empty(shape, dtype=dt).pin_memory()
     h_obs, h_mask = pin(ne, D, dt=torch.uint8), pin(ne, A, dt=torch.uint8)
     h_cur, h_rew = pin(ne, dt=torch.int32), pin(ne, dt=torch.int32)
     h_done, h_act = pin(ne, dt=torch.uint8), pin(ne, dt=torch.int32)
     hb.reset_host(h_obs, h_mask, h_cur)
     t_policy = [0.0]
+    g0 = rank * n  # global index of this rank's first game: the host policy's key
+    whole_policy = ph.bind_host_random_legal_actions(h_mask, POLICY_SEED, h_act, first_game=g0)
 
     def host_step(t):
       # uniform random legal move per game, chosen on the host from the host mask
       p0 = time.perf_counter()
-      ph.host_random_legal_actions(h_mask, seed=7, step=t, out=h_act)
+      whole_policy(t)
       t_policy[0] += time.perf_counter() - p0
       hb.step_encode_host(h_act, h_rew, h_done, h_obs, h_mask, h_cur)
 
@@ -619,19 +767,20 @@ def main():
                    "host_policy_ms_per_step": t_policy[0] / args.e2e_steps * 1e3,
                    "note": "one synchronous BatchStepEncodeHost call per step, host policy before it"}
     # pipelined form of the same step (BatchStepEncodeHostRange + BatchHostWait): the games go
-    # through in 8 ranges; the host policy of range c runs while the transfers of range c-1 are
+    # through in ranges; the host policy of range c runs while the transfers of range c-1 are
     # on the link.  Every step still uploads every action and downloads every observation,
     # mask, reward, done flag and player index into the host buffers.
     launch, wait = hb.bind_step_encode_host_range(h_act, h_rew, h_done, h_obs, h_mask, h_cur)
-    n_ranges = 8
+    n_ranges = 16 if ne >= (1 << 19) else 8
     rs = (ne // n_ranges + 127) // 128 * 128
     ranges = [(lo, min(lo + rs, ne) - lo) for lo in range(0, ne, rs)]
-    views = [(h_mask[lo:lo + cnt], h_act[lo:lo + cnt]) for lo, cnt in ranges]
+    policies = [ph.bind_host_random_legal_actions(h_mask[lo:lo + cnt], POLICY_SEED, h_act[lo:lo + cnt],
+                                                  first_game=g0 + lo) for lo, cnt in ranges]
 
     def piped_step(t):
-      for (lo, cnt), (m_v, a_v) in zip(ranges, views):
+      for (lo, cnt), pol in zip(ranges, policies):
         wait(lo)  # the previous step's results of this range are in host memory
-        ph.host_random_legal_actions(m_v, seed=7, step=t, out=a_v)
+        pol(t)
         launch(lo, cnt)
 
     e2e_steps = 3 * args.e2e_steps
@@ -645,24 +794,40 @@ def main():
       piped_step(103 + t)
     wait(-1)
     dt = time.perf_counter() - t0
+    own_dt = dt
     if dist:
       tm = torch.tensor([dt], dtype=torch.float64, device=dev)
       dist.all_reduce(tm, op=dist.ReduceOp.MAX)
       dt = float(tm.item())
+    d2h = ne * (D + A + 4 + 1 + 4)
+    # what one large pinned copy reaches on this box, for comparison
+    probe_d = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    probe_h = torch.empty(256 << 20, dtype=torch.uint8).pin_memory()
+    best = 0.0
+    for _ in range(3):
+      c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      c0.record(); probe_h.copy_(probe_d, non_blocking=True); c1.record()
+      torch.cuda.synchronize()
+      best = max(best, probe_d.numel() / (c0.elapsed_time(c1) * 1e-3) / 1e9)
+    del probe_d, probe_h
     e2e = {"value": world * ne * e2e_steps / dt, "unit": "env-steps/s",
-           "h2d_bytes_per_step": ne * 4, "d2h_bytes_per_step": ne * (D + A + 4 + 1 + 4),
+           "h2d_bytes_per_step": ne * 4, "d2h_bytes_per_step": d2h,
            "games_per_step": ne, "steps": e2e_steps,
            "ms_per_step": dt / e2e_steps * 1e3,
+           "pcie": {"d2h_gbs_achieved": d2h * e2e_steps / own_dt / 1e9, "d2h_gbs_one_large_memcpy": best,
+                    "note": "this rank's link; the step is bound by the observation download"},
+           "host_policy_threads": ph.host_policy_threads(),
+           "host_cores_of_rank0": ctx.get("cores"),
            "note": "BatchStepEncodeHostRange/BatchHostWait with pinned host buffers, %d ranges per "
-                   "step; host random-legal policy inside the timed region, overlapping the "
-                   "transfers of the previous range" % len(ranges),
+                   "step; host random-legal policy (persistent worker pool) inside the timed region, "
+                   "overlapping the transfers of the previous range" % len(ranges),
            "single_call": single_call}
     del hb
 
   # ---- optional extra, reported separately and never mixed into the headline:
   # bit-packed observation rows (16-byte multiples, 96 B instead of 658 B for 2p)
   packed = None
-  if args.packed:
+  if args.packed and not extra:
     Wp = batch.packed_words
     n_p = batch.num_games  # the first shard when the games are split
     bits = torch.empty((n_p, Wp), dtype=torch.int32, device=dev)
@@ -673,67 +838,65 @@ def main():
       select(10**6 + t); step_packed()
     torch.cuda.synchronize()
     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    Kp = min(K, 500)
+    K_pk = min(K, 500)
     p0.record()
-    for t in range(Kp):
+    for t in range(K_pk):
       select(10**6 + W + t); step_packed()
     p1.record()
     torch.cuda.synchronize()
-    pms = p0.elapsed_time(p1) / Kp
+    pms = p0.elapsed_time(p1) / K_pk
     packed = {"value": world * n_p / (pms * 1e-3), "unit": "env-steps/s", "ms_per_step": pms,
               "games": n_p,
               "obs_bytes_per_game": 4 * Wp, "note": "device-resident, bit-packed observation rows"}
     if args.e2e_steps > 0:
       hb2 = ph.HanabiBatch(params, ne, seeds[:ne], device=local_rank)
+      hb2.set_game_index_base(rank * n)
       pinned = lambda *shape, dt: torch.empty(shape, dtype=dt).pin_memory()
       q_bits, q_mask = pinned(ne, Wp, dt=torch.int32), pinned(ne, A, dt=torch.uint8)
       q_cur, q_rew = pinned(ne, dt=torch.int32), pinned(ne, dt=torch.int32)
       q_done, q_act = pinned(ne, dt=torch.uint8), pinned(ne, dt=torch.int32)
-      q_obs = pinned(ne, D, dt=torch.uint8)
-      hb2.reset_host(q_obs, q_mask, q_cur)
-      def packed_host_step(t):
-        ph.host_random_legal_actions(q_mask, seed=7, step=t, out=q_act)
-        hb2.step_encode_host_packed(q_act, q_rew, q_done, q_bits, q_mask, q_cur)
-      for t in range(3):
-        packed_host_step(t)
-      t0 = time.perf_counter()
-      for t in range(args.e2e_steps):
-        packed_host_step(3 + t)
-      dtp = time.perf_counter() - t0
-      single_p = world * ne * args.e2e_steps / dtp
+      hb2.reset_host(None, q_mask, q_cur)
       # pipelined (BatchStepEncodeHostRangePacked + BatchHostWait), as the byte-row e2e above
       launch_p, wait_p = hb2.bind_step_encode_host_range(q_act, q_rew, q_done, None, q_mask, q_cur,
                                                          obs_bits=q_bits)
       rs_p = (ne // 8 + 127) // 128 * 128
       ranges_p = [(lo, min(lo + rs_p, ne) - lo) for lo in range(0, ne, rs_p)]
-      views_p = [(q_mask[lo:lo + cnt], q_act[lo:lo + cnt]) for lo, cnt in ranges_p]
+      pols_p = [ph.bind_host_random_legal_actions(q_mask[lo:lo + cnt], POLICY_SEED, q_act[lo:lo + cnt],
+                                                  first_game=rank * n + lo) for lo, cnt in ranges_p]
 
       def piped_packed(t):
-        for (lo, cnt), (m_v, a_v) in zip(ranges_p, views_p):
+        for (lo, cnt), pol in zip(ranges_p, pols_p):
           wait_p(lo)
-          ph.host_random_legal_actions(m_v, seed=7, step=t, out=a_v)
+          pol(t)
           launch_p(lo, cnt)
 
       for t in range(3):
         piped_packed(200 + t)
       wait_p(-1)
+      if dist:
+        dist.barrier()
       steps_p = 3 * args.e2e_steps
       t0 = time.perf_counter()
       for t in range(steps_p):
         piped_packed(203 + t)
       wait_p(-1)
       dtp = time.perf_counter() - t0
+      own_dtp = dtp
+      if dist:
+        tm = torch.tensor([dtp], dtype=torch.float64, device=dev)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dtp = float(tm.item())
+      d2h_p = ne * (4 * Wp + A + 9)
       packed["e2e"] = {"value": world * ne * steps_p / dtp, "unit": "env-steps/s",
-                       "d2h_bytes_per_step": ne * (4 * Wp + A + 9), "h2d_bytes_per_step": ne * 4,
+                       "d2h_bytes_per_step": d2h_p, "h2d_bytes_per_step": ne * 4,
                        "games_per_step": ne, "ms_per_step": dtp / steps_p * 1e3,
-                       "single_call": single_p,
-                       "note": "BatchStepEncodeHostRangePacked/BatchHostWait, %d ranges per step" % len(ranges_p)}
+                       "d2h_gbs_achieved": d2h_p * steps_p / own_dtp / 1e9,
+                       "note": "BatchStepEncodeHostRangePacked/BatchHostWait, %d ranges per step; the "
+                               "host-buffer form for consumers that unpack bits themselves" % len(ranges_p)}
       del hb2
 
   if rank != 0:
-    if dist:
-      dist.destroy_process_group()
-    return
+    return None
 
   peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
   if os.path.exists(peaks_path):
@@ -759,7 +922,6 @@ def main():
     tj = json.load(open(tpath))
     if tj.get("workload") == args.workload and tj.get("games") == n:
       traffic = tj.get("dram_bytes_per_launch")
-  st = stats.cpu().tolist()
   line = {
       "metric": "env_steps_per_sec", "value": value, "unit": "env-steps/s", "n_gpus": world,
       "steps": K, "warmup": W, "ms_per_step": elapsed_ms / K, "higher_is_better": True,
@@ -794,6 +956,11 @@ def main():
       "e2e": e2e,
       "gpu_launches": launches_per_step * K,
       "clocks": clocks,
+      "parity_checked": bool(parity and parity["ok"]),
+      "parity": parity,
+      "ranks": {"ms_per_step": [x / K for x in rank_ms], "own_window": "CUDA events on each rank's "
+                "stream around its K steps, opened in-stream behind a tiny all-reduce; value uses the max",
+                "stats_allreduce_us": stats_allreduce_us},
       "episodes": {"count": st[0], "mean_score": st[1] / max(st[0], 1),
                    "mean_length": st[2] / max(st[0], 1)},
   }
@@ -803,13 +970,13 @@ def main():
     line["actor_loop"] = {"transitions_in_replay": memory.add_count, "replay_capacity": args.replay_capacity,
                           "transitions_dropped": recorder.dropped,
                           "note": "DeviceRecorder + DeviceReplayMemory inside the timed region"}
-  if not args.no_cpu_baseline and world == 1:  # the CPU leg runs at N = 1 only
+  if not args.no_cpu_baseline and world == 1 and not extra:  # the CPU legs run at N = 1 only
     line["cpu_baseline"] = cpu_reference_rate(args.workload, args.cpu_seconds)
-    if args.python_baselines:
-      line["cpu_baseline"]["python_paths"] = python_baselines(args.workload)
-  print(json.dumps(line), flush=True)
-  if dist:
-    dist.destroy_process_group()
+    if args.python_seconds > 0:
+      # the Python paths a reference user runs today (north_star: "pyhanabi stepped from Python,
+      # single-process and one process per core")
+      line["cpu_baseline"]["python_paths"] = python_baselines(args.workload, args.python_seconds)
+  return line
 
 
 if __name__ == "__main__":

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpyhanabi.so")
 CUDA_SOURCES = ["hb_batch.cu", "hb_policy.cu", "hb_replay.cu"]
-HOST_SOURCES = ["hb_single.cc"]
+HOST_SOURCES = ["hb_single.cc", "hb_host.cc"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default",

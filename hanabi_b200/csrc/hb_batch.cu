@@ -88,6 +88,7 @@ struct KArgs {
   // `actions` (every thread reads its action before it writes the next one)
   int32_t* random_actions;
   uint64_t policy_seed, policy_step;
+  int64_t game_base;  // global index of this batch's game 0 (BatchSetGameIndexBase): the policy key's game
   unsigned long long* stats;
   uint4* hist;  // optional: the 4 non-deal moves before `last`, newest first (BatchEnableHistory)
   int auto_reset;
@@ -445,7 +446,7 @@ __global__ void __launch_bounds__(V::kBlock, kResidentThreads / V::kBlock) k_mai
     const uint64_t legal = legal_bits(v, G);
     if (a.random_actions && valid) {
       const int n_legal = __popcll(legal);
-      const uint64_t bits = hbp::policy_bits(a.policy_seed, a.policy_step, (uint64_t)g);
+      const uint64_t bits = hbp::policy_bits(a.policy_seed, a.policy_step, (uint64_t)(g + a.game_base));
       a.random_actions[g] = n_legal > 0 ? select64(legal, hbp::random_legal_rank(bits, n_legal)) : -1;
     }
     if (a.mask) pack_mask_stream(mask_stream, a.spec.max_moves, legal, valid, lane);
@@ -672,6 +673,7 @@ struct Batch {
   uint4* hist = nullptr;                    // move history ring, BatchEnableHistory
   int sampler_mode = 0;
   int force_generic = 0;
+  int64_t game_base = 0;  // global index of game 0 (sharded batches), keys the fused policy
   int warp_smem_words = 0;
   int packed_words = 0, obs_stream_words = 0;
   size_t smem_pad = 0;  // experiments: extra dynamic shared memory per CTA (fewer resident CTAs)
@@ -751,6 +753,7 @@ hb::KArgs BaseArgs(const Batch* b) {
   a.stats = b->stats;
   a.hist = b->hist;
   a.sampler_mode = b->sampler_mode;
+  a.game_base = b->game_base;
   a.observer = -1;
   a.warp_smem_words = b->warp_smem_words;
   a.packed_words = b->packed_words;
@@ -1059,6 +1062,31 @@ int BatchStepEncodeRandom(pyhanabi_batch_t* h, const int32_t* actions, int32_t* 
   return 0;
 }
 
+// A batch that is one shard of a larger set of games (one process per GPU, several
+// shards per GPU) tells the engine the global index of its game 0: the fused random
+// policy is keyed (seed, step, base + i), so a sharded rollout reproduces the
+// unsharded one game for game (the games themselves never interact:
+// hanabi_lib/hanabi_game.h:114, one RNG per game).
+int BatchSetGameIndexBase(pyhanabi_batch_t* h, int64_t first_game_index) {
+  HB_BATCH(h);
+  if (first_game_index < 0) return Fail("BatchSetGameIndexBase: negative index");
+  b->game_base = first_game_index;
+  return 0;
+}
+
+// A uniformly random legal move of every game's CURRENT state (no move applied):
+// the draw BatchStepEncodeRandom would leave behind, keyed (seed, step, base + i) --
+// the first actions of a fused random rollout.
+int BatchRandomLegalActions(pyhanabi_batch_t* h, uint64_t seed, uint64_t step, int32_t* actions,
+                            void* stream) {
+  HB_BATCH(h);
+  if (!actions) return Fail("BatchRandomLegalActions: actions is null");
+  hb::KArgs a = BaseArgs(b);
+  a.random_actions = actions; a.policy_seed = seed; a.policy_step = step;
+  HB_CUDA(Launch<hb::kModeObserve>(b, a, (cudaStream_t)stream));
+  return 0;
+}
+
 // The fused hot path with HOST buffers (pinned memory recommended): the games
 // are cut into chunks that flow through three internal streams so that the
 // action upload, the kernel and the result download of neighbouring chunks
@@ -1165,7 +1193,10 @@ static int StepHostRange(pyhanabi_batch_t* h, int64_t first_game, int64_t num_ga
     return Fail("BatchStepEncodeHostRange: range must lie in the batch and start at a multiple of 128");
   if (HostSetup(b)) return 1;
   const int slot = b->range_next++ % Batch::kRangeSlots;
-  cudaStream_t s = b->h_streams[slot % 3];
+  // a range always runs on the same internal stream (chosen by its first game), so consecutive
+  // steps of one range are ordered by that stream even if the caller skips BatchHostWait;
+  // ranges must not overlap other ranges that are still in flight
+  cudaStream_t s = b->h_streams[(first_game >> 7) % 3];
   if (EnqueueHostRange(b, (size_t)first_game, (size_t)(first_game + num_games), actions, rewards, dones,
                        scores, obs, row_pitch, obs_bits, mask, cur_player, auto_reset, s))
     return 1;

@@ -15,7 +15,6 @@
 
 #include <cstdlib>
 #include <string>
-#include <thread>
 #include <type_traits>
 #include <vector>
 
@@ -851,41 +850,6 @@ int BatchExpandPacked(const uint32_t* obs_bits, int packed_words, int obs_size, 
   }
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? 0 : PFail(std::string("BatchExpandPacked: ") + cudaGetErrorString(e));
-}
-
-// Host-side twin of BatchSelectAction for epsilon >= 1 (uniform random legal
-// move; the reference's agents/random_agent.py): same counter-based generator,
-// so for equal (seed, step, game) it returns exactly the device kernel's actions.
-// mask and actions are HOST arrays; `threads` <= 0 uses the hardware concurrency.
-int HostRandomLegalActions(const uint8_t* mask, int n, int num_actions, uint64_t seed,
-                           uint64_t step, int32_t* actions, int threads) {
-  if (!mask || !actions || n < 0 || num_actions <= 0 || num_actions > 64) return PFail("HostRandomLegalActions: bad argument");
-  if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
-  if (threads < 1) threads = 1;
-  if (threads > 64) threads = 64;
-  if ((int64_t)threads * 4096 > n) threads = n / 4096 > 0 ? n / 4096 : 1;
-  auto work = [=](int t) {
-    const int lo = (int)((int64_t)n * t / threads), hi = (int)((int64_t)n * (t + 1) / threads);
-    for (int g = lo; g < hi; ++g) {
-      const uint8_t* m = mask + (int64_t)g * num_actions;
-      uint64_t legal = 0;
-      for (int a = 0; a < num_actions; ++a) legal |= (uint64_t)(m[a] != 0) << a;
-      const int n_legal = __builtin_popcountll(legal);
-      int choice = -1;
-      if (n_legal > 0) {
-        const uint64_t bits = hbp::policy_bits(seed, step, (uint64_t)g);
-        int k = (int)(((bits & 0xffffffffull) * (uint64_t)n_legal) >> 32);
-        while (k-- > 0) legal &= legal - 1;
-        choice = __builtin_ctzll(legal);
-      }
-      actions[g] = choice;
-    }
-  };
-  std::vector<std::thread> pool;
-  for (int t = 1; t < threads; ++t) pool.emplace_back(work, t);
-  work(0);
-  for (auto& th : pool) th.join();
-  return 0;
 }
 
 // C51 q-values q[n, A] = sum_i support_i softmax(logits[n, a, :])_i (all actions).

@@ -67,6 +67,7 @@ struct View {
   const uint8_t* terminals;
   const float* legal;
   const double* tree;
+  unsigned long long* sample_failures;  // elements for which sample_index_batch found no valid transition
 };
 
 __host__ __device__ inline uint64_t mix64(uint64_t z) {
@@ -237,7 +238,9 @@ __global__ void k_rebuild_level(double* tree, int depth, int l, const int32_t* i
 
 __global__ void k_get_priority(View v, const int32_t* indices, int count, float* out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < count) out[i] = (float)v.tree[((int64_t)1 << v.depth) - 1 + indices[i]];
+  if (i >= count) return;
+  const int64_t idx = indices[i];  // -1 (failed draw) or any other out-of-range index reads nothing
+  out[i] = (idx >= 0 && idx < v.cap) ? (float)v.tree[((int64_t)1 << v.depth) - 1 + idx] : 0.f;
 }
 
 __global__ void k_is_valid(View v, const int32_t* indices, int count, uint8_t* out) {
@@ -274,7 +277,8 @@ __global__ void k_sample_indices(View v, int prioritized, int stratified, uint64
     }
     if (valid_transition(v, index)) pick = index;
   }
-  out[i] = (int32_t)pick;  // -1: no valid transition found (the reference raises)
+  out[i] = (int32_t)pick;  // -1: no valid transition found (the reference raises; see ReplaySampleFailures)
+  if (pick < 0) atomicAdd(v.sample_failures, 1ull);
 }
 
 // sample_transition_batch(indices=...), replay_memory.py:290-347.  One warp per element.
@@ -284,6 +288,14 @@ __global__ void k_gather(View v, const int32_t* indices, int count, uint8_t* sta
   const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (b >= count) return;
   const int64_t idx = indices[b];
+  if (idx < 0 || idx >= v.cap) {
+    // a failed draw (-1) or a foreign index: an all-zero, terminal row instead of an
+    // out-of-bounds read; the caller learns about failed draws from ReplaySampleFailures
+    for (int k = lane; k < v.D; k += 32) { states[b * v.D + k] = 0; next_states[b * v.D + k] = 0; }
+    for (int k = lane; k < v.A; k += 32) next_legal[b * v.A + k] = 0.f;
+    if (lane == 0) { actions[b] = 0; rewards[b] = 0.f; terminals[b] = 1; }
+    return;
+  }
   const int64_t boot = (idx + v.horizon) % v.cap;
   for (int k = lane; k < v.D; k += 32) {
     states[b * v.D + k] = v.obs[idx * v.D + k];
@@ -529,6 +541,7 @@ hbr::View MakeView(const Replay* r) {
   std::memcpy(v.disc, r->disc, sizeof(v.disc));
   v.obs = r->obs; v.actions = r->actions; v.rewards = r->rewards; v.terminals = r->terminals;
   v.legal = r->legal; v.tree = r->tree;
+  v.sample_failures = r->d_counts + 2;
   return v;
 }
 
@@ -597,9 +610,9 @@ int NewReplay(pyhanabi_replay_t* out, int num_actions, int observation_size, int
   // the tree buffer also hosts the int32 "last writer" scratch behind the nodes
   if ((e = cudaMalloc(&r->tree, nodes * sizeof(double) + ((size_t)1 << r->depth) * sizeof(int32_t))) != cudaSuccess)
     return fail("cudaMalloc tree", e);
-  if ((e = cudaMalloc(&r->d_counts, 2 * sizeof(unsigned long long))) != cudaSuccess) return fail("cudaMalloc counters", e);
+  if ((e = cudaMalloc(&r->d_counts, 4 * sizeof(unsigned long long))) != cudaSuccess) return fail("cudaMalloc counters", e);
   if ((e = cudaMallocHost(&r->h_counts, 2 * sizeof(unsigned long long))) != cudaSuccess) return fail("cudaMallocHost counters", e);
-  cudaMemset(r->d_counts, 0, 2 * sizeof(unsigned long long));
+  cudaMemset(r->d_counts, 0, 4 * sizeof(unsigned long long));
   cudaMemset(r->obs, 0, cap * (size_t)observation_size);
   cudaMemset(r->actions, 0, cap * sizeof(int32_t));
   cudaMemset(r->rewards, 0, cap * sizeof(float));
@@ -741,11 +754,32 @@ int ReplayTreeSample(pyhanabi_replay_t* h, const double* query_values, int count
 int ReplaySampleIndexBatch(pyhanabi_replay_t* h, int count, int stratified, uint64_t seed, uint64_t step,
                            int32_t* indices, void* stream) {
   HBR_REPLAY(h);
-  if (r->add_count == 0) return HbFail("ReplaySampleIndexBatch: the replay memory is empty");
+  // no transition can be valid before update_horizon + 1 adds (is_valid_transition,
+  // replay_memory.py:233-258); the reference raises there (replay_memory.py:268)
+  if (r->add_count <= r->horizon)
+    return HbFail("ReplaySampleIndexBatch: the replay memory holds no valid transition yet "
+                  "(needs more than update_horizon adds)");
+  if (count <= 0 || !indices) return HbFail("ReplaySampleIndexBatch: bad argument");
   hbr::k_sample_indices<<<(count + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
       MakeView(r), r->prioritized, stratified, seed, step, count, indices);
   HBR_CUDA(cudaGetLastError());
   return 0;
+}
+
+// Number of elements for which ReplaySampleIndexBatch found no valid transition in its
+// 1000 attempts (they hold -1) since the counter was last cleared; the reference raises a
+// RuntimeError in that case (replay_memory.py:268, prioritized_replay_memory.py:128).
+// Synchronises `stream`.
+int64_t ReplaySampleFailures(pyhanabi_replay_t* h, int clear, void* stream) {
+  if (!h || !h->replay) return -1;
+  Replay* r = static_cast<Replay*>(h->replay);
+  Guard guard(r->device);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cudaMemcpyAsync(r->h_counts + 1, r->d_counts + 2, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s) != cudaSuccess)
+    return -1;
+  if (clear && cudaMemsetAsync(r->d_counts + 2, 0, sizeof(unsigned long long), s) != cudaSuccess) return -1;
+  if (cudaStreamSynchronize(s) != cudaSuccess) return -1;
+  return (int64_t)r->h_counts[1];
 }
 
 int ReplaySampleTransitionBatch(pyhanabi_replay_t* h, const int32_t* indices, int count, uint8_t* states,

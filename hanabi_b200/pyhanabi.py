@@ -797,6 +797,20 @@ class HanabiBatch(object):
         self._p(out, torch.int32, n, "int32_t*"), int(seed) & (2**64 - 1), int(step) & (2**64 - 1),
         self._stream()), "BatchStepEncodeRandom")
 
+  def set_game_index_base(self, first_game_index):
+    """Global index of this batch's game 0 (shards of a larger set of games): the fused
+    random policy is keyed (seed, step, first_game_index + i)."""
+    _check(lib.BatchSetGameIndexBase(self._c, int(first_game_index)), "BatchSetGameIndexBase")
+    self.game_index_base = int(first_game_index)
+
+  def random_legal_actions(self, actions, seed, step):
+    """Uniformly random legal move of every game's current state (the draw the fused
+    policy of step_encode_random makes), written into `actions`."""
+    torch = self._torch
+    _check(lib.BatchRandomLegalActions(self._c, int(seed) & (2**64 - 1), int(step) & (2**64 - 1),
+                                       self._p(actions, torch.int32, self.num_games, "int32_t*"),
+                                       self._stream()), "BatchRandomLegalActions")
+
   def bind_step_encode_random(self, actions, seed, rewards=None, dones=None, obs=None, mask=None,
                               cur_player=None, scores=None, auto_reset=True, stream=None):
     """Pre-bound in-place variant of step_encode_random for tight loops: run(step)."""
@@ -1256,9 +1270,10 @@ def expand_packed(obs_bits, obs_size, out):
   return out
 
 
-def host_random_legal_actions(mask, seed, step, out=None, threads=0):
+def host_random_legal_actions(mask, seed, step, out=None, threads=0, first_game=0):
   """Uniform random legal move per game on the HOST (CPU uint8 mask [n, A] ->
-  CPU int32 actions [n]); bit-identical to select_action(None, mask, 1.0, seed, step)."""
+  CPU int32 actions [n]); bit-identical to select_action(None, mask, 1.0, seed, step).
+  Row i is game first_game + i of the (seed, step, game) key."""
   import torch
   _require_lib()
   n, A = int(mask.shape[0]), int(mask.shape[1])
@@ -1266,11 +1281,38 @@ def host_random_legal_actions(mask, seed, step, out=None, threads=0):
     raise ValueError("mask must be a contiguous CPU uint8 tensor")
   if out is None:
     out = torch.empty(n, dtype=torch.int32)
-  _check(lib.HostRandomLegalActions(ffi.cast("uint8_t*", mask.data_ptr()), n, A,
-                                    int(seed) & (2**64 - 1), int(step) & (2**64 - 1),
-                                    ffi.cast("int32_t*", out.data_ptr()), int(threads)),
+  _check(lib.HostRandomLegalActionsAt(ffi.cast("uint8_t*", mask.data_ptr()), n, A,
+                                      int(seed) & (2**64 - 1), int(step) & (2**64 - 1),
+                                      int(first_game), ffi.cast("int32_t*", out.data_ptr()),
+                                      int(threads)),
          "HostRandomLegalActions")
   return out
+
+
+def bind_host_random_legal_actions(mask, seed, out, first_game=0, threads=0):
+  """Pre-bound host_random_legal_actions for tight loops: run(step)."""
+  import torch
+  _require_lib()
+  n, A = int(mask.shape[0]), int(mask.shape[1])
+  if mask.is_cuda or mask.dtype != torch.uint8 or not mask.is_contiguous():
+    raise ValueError("mask must be a contiguous CPU uint8 tensor")
+  if out.is_cuda or out.dtype != torch.int32 or out.numel() < n:
+    raise ValueError("out must be a CPU int32 tensor with one element per game")
+  head = (ffi.cast("uint8_t*", mask.data_ptr()), n, A, int(seed) & (2**64 - 1))
+  tail = (int(first_game), ffi.cast("int32_t*", out.data_ptr()), int(threads))
+  fn = lib.HostRandomLegalActionsAt
+  keep = (mask, out)
+
+  def run(step, _head=head, _tail=tail, _fn=fn, _keep=keep):
+    if _fn(*(_head + (step,) + _tail)) != 0:
+      raise RuntimeError("HostRandomLegalActions failed: %s" % encode_ffi_string(lib.BatchLastError()))
+  return run
+
+
+def host_policy_threads():
+  """Size of the persistent host worker pool behind host_random_legal_actions."""
+  _require_lib()
+  return int(lib.HostPolicyThreads())
 
 
 def c51_q_values(logits, support, mask):

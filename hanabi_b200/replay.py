@@ -99,7 +99,11 @@ class DeviceReplayMemory(object):
                                            self._stream()), "ReplayTreeSample")
     return out
 
-  def sample_index_batch(self, batch_size, stratified=False):
+  def sample_index_batch(self, batch_size, stratified=False, check=True):
+    """Indices of valid transitions (replay_memory.py:260-288 / prioritized_replay_memory.py:
+    109-132).  Like the reference, raises RuntimeError when no valid transition is found for
+    some element (check=True reads a device counter back: one stream synchronisation; pass
+    check=False inside captured / fully asynchronous loops and poll sample_failures())."""
     torch = self._torch
     out = torch.empty(batch_size, dtype=torch.int32, device=self.device)
     self._draws += 1
@@ -107,7 +111,13 @@ class DeviceReplayMemory(object):
                                                  self._seed, self._draws,
                                                  self._p(out, torch.int32, "int32_t*", batch_size),
                                                  self._stream()), "ReplaySampleIndexBatch")
+    if check and self.sample_failures(clear=True):
+      raise RuntimeError("Max sample attempts: Tried 1000 times but only sampled fewer than "
+                         "batch_size=%d valid indices" % batch_size)
     return out
+
+  def sample_failures(self, clear=True):
+    return int(self._lib.ReplaySampleFailures(self._c, int(bool(clear)), self._stream()))
 
   def sample_transition_batch(self, batch_size=None, indices=None):
     """Returns (state, action, reward, next_state, terminal, indices, next_legal_actions) like

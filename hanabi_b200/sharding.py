@@ -19,6 +19,46 @@ def world_from_env():
           int(os.environ.get("WORLD_SIZE", "1")))
 
 
+def _parse_cpulist(text):
+  cpus = set()
+  for part in text.strip().split(","):
+    if not part:
+      continue
+    lo, _, hi = part.partition("-")
+    cpus.update(range(int(lo), int(hi or lo) + 1))
+  return cpus
+
+
+def bind_rank_to_local_cores(local_rank, local_world):
+  """Pins this process (and the host worker pool it creates later) to its share of the
+  cores next to its GPU: the GPU's NUMA-local CPU list from sysfs, split evenly among the
+  local ranks whose GPUs report the same list.  Pinned host buffers allocated afterwards
+  are first touched on that node.  Host-side policy only; returns the chosen CPU set, or
+  None when the topology cannot be read (nothing is changed then)."""
+  try:
+    import torch
+    def cpus_of(i):
+      pr = torch.cuda.get_device_properties(i)
+      name = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+      with open("/sys/bus/pci/devices/%s/local_cpulist" % name) as f:
+        return frozenset(_parse_cpulist(f.read()))
+    allowed = os.sched_getaffinity(0)
+    lists = [cpus_of(i) for i in range(local_world)]
+    mine = lists[local_rank] & allowed
+    if not mine:
+      return None
+    peers = [i for i in range(local_world) if lists[i] == lists[local_rank]]
+    per = len(mine) // len(peers)
+    if per < 1:
+      return None
+    k = peers.index(local_rank)
+    chosen = set(sorted(mine)[k * per:(k + 1) * per])
+    os.sched_setaffinity(0, chosen)
+    return chosen
+  except Exception:  # pylint: disable=broad-except
+    return None
+
+
 def shard_range(total_games, rank, world_size):
   """Contiguous, balanced slice [lo, hi) of the global game index range."""
   if not 0 <= rank < world_size:

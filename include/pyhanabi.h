@@ -247,6 +247,16 @@ int BatchStepEncodeRandom(pyhanabi_batch_t* batch, const int32_t* actions, int32
                           uint8_t* dones, int32_t* scores, uint8_t* obs, int64_t row_pitch,
                           uint8_t* mask, int32_t* cur_player, int auto_reset,
                           int32_t* random_actions, uint64_t seed, uint64_t step, void* stream);
+/* A batch that is one shard of a larger set of games (one process per GPU, several
+   shards per GPU) sets the global index of its game 0: the fused random policy is keyed
+   (seed, step, first_game_index + i), so a sharded rollout reproduces the unsharded one
+   game for game (one RNG per game, hanabi_lib/hanabi_game.h:114; games never interact). */
+int BatchSetGameIndexBase(pyhanabi_batch_t* batch, int64_t first_game_index);
+/* A uniformly random legal move of every game's CURRENT state (no move applied), the
+   draw BatchStepEncodeRandom would leave behind for (seed, step): the first actions of
+   a fused random rollout. */
+int BatchRandomLegalActions(pyhanabi_batch_t* batch, uint64_t seed, uint64_t step,
+                            int32_t* actions, void* stream);
 
 /* Bit-packed observations (optional, reported separately from the byte form): row i
  * = BatchPackedObservationWords() uint32 words (16-byte multiple), bit j of the row
@@ -287,7 +297,11 @@ int BatchStepEncodeHostPacked(pyhanabi_batch_t* batch, const int32_t* actions,
    work: games [first_game, first_game + num_games) only (first_game % 128 == 0), the
    pointers are the bases of the whole arrays.  Returns once the work is queued; the
    range's host buffers are complete after BatchHostWait(batch, first_game)
-   (first_game < 0: everything queued). */
+   (first_game < 0: everything queued).  Ordering: a range runs on an internal stream
+   chosen by its first game, so successive steps of the SAME range are ordered among
+   themselves; work queued on other streams (BatchReset, BatchObserve on the caller's
+   stream) must have completed before the first ranged call, and ranges in flight must
+   not overlap. */
 int BatchStepEncodeHostRange(pyhanabi_batch_t* batch, int64_t first_game, int64_t num_games,
                              const int32_t* actions, int32_t* rewards, uint8_t* dones,
                              int32_t* scores, uint8_t* obs, int64_t row_pitch, uint8_t* mask,
@@ -362,6 +376,13 @@ int BatchExpandPacked(const uint32_t* obs_bits, int packed_words, int obs_size, 
  * identical to the device kernel for equal (seed, step, game). */
 int HostRandomLegalActions(const uint8_t* mask, int n, int num_actions, uint64_t seed,
                            uint64_t step, int32_t* actions, int threads);
+/* Same for rows that are games first_game_index .. first_game_index + n - 1 of the key
+   (ranges of a batch, shards of a larger set).  Both run on a persistent worker pool of
+   HostPolicyThreads() threads: cores / LOCAL_WORLD_SIZE, or HANABI_B200_HOST_THREADS. */
+int HostRandomLegalActionsAt(const uint8_t* mask, int n, int num_actions, uint64_t seed,
+                             uint64_t step, int64_t first_game_index, int32_t* actions,
+                             int threads);
+int HostPolicyThreads(void);
 int BatchC51QValues(const float* logits, const float* support, const uint8_t* mask, int n,
                     int num_actions, int num_atoms, float* q_out, int32_t* greedy_actions,
                     void* stream);
@@ -430,6 +451,11 @@ int ReplaySampleIndexBatch(pyhanabi_replay_t* replay, int count, int stratified,
 /* sample_transition_batch(indices=...) (replay_memory.py:290-347): n-step rewards
  * truncated at the first terminal, next state / next legal actions update_horizon
  * slots later. */
+/* Elements of ReplaySampleIndexBatch calls that found no valid transition (index -1)
+   since the last clear; the reference raises there (replay_memory.py:268).  Gathering
+   such an index yields an all-zero terminal row, never an out-of-bounds read.
+   Synchronises `stream`. */
+int64_t ReplaySampleFailures(pyhanabi_replay_t* replay, int clear, void* stream);
 int ReplaySampleTransitionBatch(pyhanabi_replay_t* replay, const int32_t* indices, int count,
                                 uint8_t* states, int32_t* actions, float* rewards,
                                 uint8_t* next_states, uint8_t* terminals,

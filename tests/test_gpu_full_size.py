@@ -149,3 +149,81 @@ def test_full_size_shard_invariance():
       assert torch.equal(r, rew[lo:hi]) and torch.equal(d, dn[lo:hi])
   assert torch.equal(torch.cat(ho), bo) and torch.equal(torch.cat(hm), bm)
   assert hashlib.sha256(bo.cpu().numpy().tobytes() + bm.cpu().numpy().tobytes()).hexdigest() == whole
+
+
+def _fused_rollout(ph, torch, params, seeds, base, steps, seed=7, init_step=1 << 40, device=0):
+  """Fused random-policy rollout (BatchStepEncodeRandom) of one shard whose game 0 has the
+  global index `base`; returns the final output tensors and the pending actions."""
+  n = len(seeds)
+  dev = torch.device("cuda", device)
+  with torch.cuda.device(dev):
+    b = ph.HanabiBatch(params, n, seeds, device=device)
+    b.set_game_index_base(base)
+    obs = torch.empty((n, b.obs_size), dtype=torch.uint8, device=dev)
+    mask = torch.empty((n, b.max_moves), dtype=torch.uint8, device=dev)
+    cur = torch.empty(n, dtype=torch.int32, device=dev)
+    rew = torch.empty(n, dtype=torch.int32, device=dev)
+    done = torch.empty(n, dtype=torch.uint8, device=dev)
+    act = torch.empty(n, dtype=torch.int32, device=dev)
+    b.reset()
+    b.observe(obs, mask, cur)
+    b.random_legal_actions(act, seed, init_step)
+    for t in range(steps):
+      b.step_encode_random(act, seed, t, rew, done, obs, mask, cur)
+    torch.cuda.synchronize(dev)
+  return obs, mask, cur, rew, done, act
+
+
+@pytest.mark.parametrize("name", ["full2", "small4"])
+def test_sharded_fused_rollout_equals_unsharded(name):
+  """Shards with BatchSetGameIndexBase reproduce the unsharded fused rollout byte for
+  byte (the policy is keyed by the GLOBAL game index), and sampled games equal the CPU
+  reference driven by the numpy twin of the policy -- what bench.py checks on every rank."""
+  import torch
+  import bench
+  from hanabi_b200 import pyhanabi as ph
+  params = common.CONFIGS[name]
+  n, steps = 1 << 14, 40
+  seeds = common.seeds_for(n)
+  whole = _fused_rollout(ph, torch, params, seeds, 0, steps)
+  cuts = [0, 4096, 4096 + 32 * 101, n]
+  parts = [_fused_rollout(ph, torch, params, seeds[lo:hi], lo, steps) for lo, hi in zip(cuts, cuts[1:])]
+  for k in range(len(whole)):
+    assert torch.equal(torch.cat([p[k] for p in parts]), whole[k])
+  # the select kernel with epsilon >= 1 is the same draw for base 0
+  twin = ph.select_action(None, whole[1], 1.0, seed=7, step=steps - 1)
+  assert torch.equal(twin, whole[5])
+  # CPU reference on sampled games of the last shard (global indices)
+  lo = cuts[-2]
+  local = np.array([0, 1, 31, 32, 777, n - lo - 1])
+  kind = "ref" if O.have_ref() else "oracle"
+  cpu = O.CpuBatch(kind, params, len(local), seeds[lo + local])
+  cpu.reset()
+  g = (lo + local).astype(np.int64)
+  act = bench.policy_draw(cpu.legal_mask(), 7, 1 << 40, g)
+  for t in range(steps):
+    _, _, _, illegal = cpu.step(act)
+    assert not illegal.any()
+    act = bench.policy_draw(cpu.legal_mask(), 7, t, g)
+  last = parts[-1]
+  idx = torch.as_tensor(local, device="cuda:0")
+  assert (last[0][idx].cpu().numpy() == cpu.encode()).all()
+  assert (last[1][idx].cpu().numpy() == cpu.legal_mask()).all()
+  assert (last[2][idx].cpu().numpy() == cpu.cur_player()).all()
+  assert (last[5][idx].cpu().numpy() == act).all()
+
+
+def test_two_gpu_shards_equal_one_gpu_run():
+  """On a box with two GPUs: the halves stepped on cuda:0 and cuda:1 equal the one-GPU run."""
+  import torch
+  from hanabi_b200 import pyhanabi as ph
+  if torch.cuda.device_count() < 2:
+    pytest.skip("needs two GPUs")
+  params = common.CONFIGS["full2"]
+  n, steps = 1 << 15, 32
+  seeds = common.seeds_for(n)
+  whole = _fused_rollout(ph, torch, params, seeds, 0, steps, device=0)
+  a = _fused_rollout(ph, torch, params, seeds[:n // 2], 0, steps, device=0)
+  b = _fused_rollout(ph, torch, params, seeds[n // 2:], n // 2, steps, device=1)
+  for k in range(len(whole)):
+    assert torch.equal(torch.cat([a[k], b[k].to("cuda:0")]), whole[k])

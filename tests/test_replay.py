@@ -124,3 +124,44 @@ def test_device_replay_against_restatement_at_size():
   uni.add(t(obs), t(act), t(rew), t(term), t(legal))
   u = uni.sample_index_batch(5000).cpu().numpy()
   assert u.min() >= 0 and u.max() < 120 - 2
+
+
+@pytest.mark.gpu
+def test_device_replay_failed_draws_raise_and_never_read_out_of_bounds():
+  """sampling before any transition is valid, or from a tree whose total is
+  zero, must raise like the reference (replay_memory.py:268,
+  prioritized_replay_memory.py:128) -- and an index of -1 handed to the gather must not read
+  outside the ring."""
+  import torch
+  from hanabi_b200 import replay
+  dev = torch.device("cuda:0")
+  A, D, cap, n = 5, 12, 64, 3
+  mem = replay.DeviceReplayMemory(A, D, cap, update_horizon=n, gamma=0.99)
+  t = lambda a, dt: torch.as_tensor(np.asarray(a), dtype=dt, device=dev)
+  with pytest.raises(RuntimeError):
+    mem.sample_index_batch(4)  # empty
+  for k in range(n):  # still no valid transition: needs more than update_horizon adds
+    mem.add(t(np.full((1, D), k), torch.uint8), t([1], torch.int32), t([1.0], torch.float32),
+            t([0], torch.uint8), t(np.zeros((1, A)), torch.float32))
+  with pytest.raises(RuntimeError):
+    mem.sample_index_batch(4)
+  for k in range(20):
+    mem.add(t(np.full((1, D), 10 + k), torch.uint8), t([2], torch.int32), t([0.5], torch.float32),
+            t([0], torch.uint8), t(np.ones((1, A)), torch.float32))
+  idx = mem.sample_index_batch(16)
+  assert int(idx.min()) >= 0
+  # every priority zero: the tree cannot produce a valid index -> raises
+  every = torch.arange(cap, dtype=torch.int32, device=dev)
+  mem.set_priority(every, torch.zeros(cap, dtype=torch.float32, device=dev))
+  if mem.get_priority(every).sum().item() == 0:
+    idx0 = mem.sample_index_batch(8, check=False)
+    if int(idx0.min()) < 0:
+      assert mem.sample_failures(clear=False) > 0
+      with pytest.raises(RuntimeError):
+        mem.sample_index_batch(8)
+  # the gather with failed / foreign indices: zero rows flagged terminal, no fault
+  bad = torch.tensor([-1, 0, cap + 5, 3], dtype=torch.int32, device=dev)
+  state, action, reward, nxt, term, _, legal = mem.sample_transition_batch(indices=bad)
+  torch.cuda.synchronize()
+  assert int(state[0].sum()) == 0 and int(state[2].sum()) == 0 and int(term[0]) == 1 and int(term[2]) == 1
+  assert float(mem.get_priority(bad)[0]) == 0.0
