@@ -4,8 +4,10 @@ Restatement of the per-episode transition bookkeeping of the reference's DQN/Rai
 agent and episode loop for ONE game (agents/rainbow_copy/dqn_agent.py:286-385,
 agents/run_experiment.py:344-403): begin_episode/step record (reward, o, l, a);
 end_episode posts, per player, (o_t, a_t, r_{t+1}, terminal, l_t) consecutively.
-PARITY UNPINNED beyond reading: the reference agent builds a TensorFlow graph in its
-constructor and cannot be imported here; this follows the cited lines one to one.
+Pinned (tests/test_actor_golden.py) by tests/golden/actor_golden.npz: the stream the
+reference's own DQNAgent methods posted when the reference's run_one_episode drove them
+on seeded games (tests/golden/make_actor_golden.py; the agent object is created without
+its TF-graph-building constructor, its three network hooks are scripted).
 """
 import numpy as np
 

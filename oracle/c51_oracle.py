@@ -1,13 +1,14 @@
 """oracle/c51_oracle.py -- TEST INFRASTRUCTURE ONLY.
 
-fp32 restatement (numpy, and torch on the test's device) of the two Rainbow
-pieces on the hot path, following the reference op by op.  TensorFlow is not
-installed here, so the reference code itself cannot run; the restatement is
-pinned by the worked example in the reference docstring
-(agents/rainbow_copy/rainbow_agent.py:262-266,400-401, committed as
-tests/golden/c51_docstring.json) and cross-checked against an independent
-floor/ceil scatter formulation of the same projection.  Beyond that example:
-PARITY UNPINNED (no TF); tolerance 1e-5 relative in fp32 as north_star states.
+fp32 restatement (numpy) of the two Rainbow pieces on the hot path, following the
+reference op by op.  Pinned (tests/test_c51_golden.py) by tests/golden/c51_golden.npz:
+the outputs of the reference's own `project_distribution`, `_reshape_networks` and
+`_build_target_distribution` (agents/rainbow_copy/rainbow_agent.py:163-213, 252-404)
+executed unmodified on a numpy stand-in for the TensorFlow ops they call
+(tests/golden/make_c51_golden.py; TensorFlow itself is not installed), plus the worked
+example of the reference docstring (rainbow_agent.py:262-266,400-401,
+tests/golden/c51_docstring.json) and an independent floor/ceil scatter formulation.
+Tolerance 1e-5 relative in fp32 as north_star states.
 """
 import numpy as np
 
