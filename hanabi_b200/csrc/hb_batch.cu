@@ -21,48 +21,24 @@
 namespace hb {
 
 enum Mode { kModeStep = 0, kModeReset = 1, kModeObserve = 2 };
-// Re-deal of finished games: 2 = parallel Lehmer decode when an initial deal has
-// at least HB_LEHMER_MIN_PAIRS cards (measured: +23 % on Full 4p, -3 % on Full 2p,
-// -12 % on Small 2p against the serial draw chain), 1 = always, 0 = never.
-#ifndef HB_RESET_LEHMER
-#define HB_RESET_LEHMER 2
-#endif
-#ifndef HB_LEHMER_MIN_PAIRS
-#define HB_LEHMER_MIN_PAIRS 12
-#endif
-// Serial-path re-deal: 1 = one thread per game draws the cards one after the other,
-// 0 = one thread per (game, draw) decodes its card from the game's draw indices (two more
-// CTA barriers), 2 = the former for deals of 10+ cards, the latter below (measured: Full 2p
-// 1.6 % faster with the chain, Small 2p / 4p 1.2 % / 3 % faster with the decode).
-#ifndef HB_SERIAL_B2
-#define HB_SERIAL_B2 2
-#endif
 #ifndef HB_EARLY_OUT
 #define HB_EARLY_OUT 0  // measured: -1.2 % on Full 2p, +1.1 % on Full 4p
 #endif
 #ifndef HB_RESET_PREFETCH
 #define HB_RESET_PREFETCH 1
 #endif
-#ifndef HB_RESET_PREFETCH_ALL
-#define HB_RESET_PREFETCH_ALL 0
-#endif
 // Games per CTA come with the rule-set view (V::kBlock); 768 threads are resident per SM.
 #ifndef HB_RESIDENT
 #define HB_RESIDENT 768  // measured again on the final kernel: 640 (90 registers, no spills) 0.5-0.7 % slower
 #endif
 constexpr int kResidentThreads = HB_RESIDENT;
-constexpr bool lehmer_for(int cards) {
-  return HB_RESET_LEHMER == 1 || (HB_RESET_LEHMER == 2 && cards >= HB_LEHMER_MIN_PAIRS);
-}
-constexpr int queue_cap(int block, int cards) {
-  return lehmer_for(cards) ? block / 2 : (block / 2 < 640 / cards ? block / 2 : 640 / cards);
-}
 constexpr int kStreamPad = 2;    // readable pad words after each packed bit stream
 constexpr int kNumStats = 32;    // [0] episodes [1] sum score [2] sum length [3..28] score histogram
 
 struct KArgs {
   Spec spec;
   uint4* state;
+  uint2* queue;  // the games' deal queue words (hb_engine.cuh "deal queue"), 8 bytes per game
   uint32_t* mt;
   int64_t N;
   int64_t g_begin, g_end;  // range of games this launch covers (g_begin % 32 == 0)
@@ -100,27 +76,29 @@ struct KArgs {
 
 // One CTA = kBlock games = kBlock/32 warp tiles.  Phases separated by CTA barriers keep the
 // warps of an SM inside the same stretch of code (the kernel is ~100 KB of SASS,
-// far beyond the instruction caches) and let finished games be re-dealt by
-// compacted threads:
-//   A  load state (+ prefetch two RNG words) -> apply move -> deal -> terminal;
-//      finished games enqueue themselves in shared memory
-//   B  the first n threads of the CTA draw the initial deals of the n queued games
-//   C  install new games, store state, encode observation + legal mask into the
-//      warp's packed bit stream, expand to bytes with 128-bit stores
+// far beyond the instruction caches) and let the RNG work be done by compacted lanes:
+//   A  load state -> apply move -> deal the follow-up card FROM THE GAME'S QUEUE (no RNG
+//      memory access) -> terminal; finished games and games whose queue ran dry enqueue a
+//      job in shared memory
+//   B  the warps work the jobs off, one lane per RNG word pair: regenerate the consumed
+//      slots, draw the initial deal of a new game and pre-draw the next queue
+//   C  install the job results, store state + queue, encode observation + legal mask into
+//      the warp's packed bit stream, expand to bytes with 128-bit stores
 // NET: the instantiation that also writes network-input rows (BatchStepEncodeNet /
 // BatchObserveNet); kept out of the plain kernels so that their code stays as small as it was.
 template <class V, int MODE, bool NET = false>
 __global__ void __launch_bounds__(V::kBlock, kResidentThreads / V::kBlock) k_main(const __grid_constant__ KArgs a) {
   constexpr int kBlock = V::kBlock, kWarps = kBlock / 32;
-  // finished games a CTA re-deals through the shared-memory queue (the serial path keeps three
-  // words per queued draw: bounded so that its table stays within 640 draws)
-  constexpr int kQueueCap = hb::queue_cap(kBlock, V::kP * V::kH);
+  constexpr int kQueueCap = kBlock / 2;  // jobs a CTA works off per launch; the rest take the per-thread path
   extern __shared__ uint32_t smem[];
   __shared__ int s_stats[kNumStats];
   __shared__ int s_nq;
   __shared__ int s_q_tid[kQueueCap];
-  __shared__ int s_q_mti[kQueueCap];
-  __shared__ ResetResult s_res[kQueueCap];
+  __shared__ uint32_t s_q_meta[kQueueCap];  // r0 | npend << 10 | nfresh << 14 | npeek << 20 | s0 << 24 | slow << 31
+  __shared__ uint2 s_q_deck[kQueueCap];     // deck bitmap the job draws from
+  __shared__ JobResult s_res[kQueueCap];
+  constexpr int kItems = 4;  // RNG word pairs per thread in flight in phase B
+  __shared__ uint8_t s_qb[kItems * kBlock];  // draw indices of the jobs of one pass
   __shared__ uint32_t s_spread[32];
   // byte -> its eight 16-bit elements: 4 KB of dynamic shared memory that only the launches
   // writing network-input rows ask for
@@ -143,6 +121,8 @@ __global__ void __launch_bounds__(V::kBlock, kResidentThreads / V::kBlock) k_mai
   const int64_t tile0 = g - lane;  // first game of this warp's tile
   const bool valid = g < a.g_end;
   const bool tile_live = tile0 < a.g_end;
+  // length of the deal queue for this batch (compiled out where the shape cannot have one)
+  const int n_pre = V::kPrefill > 0 ? a.spec.prefill : 0;
   if (threadIdx.x < 32) s_spread[threadIdx.x] = spread_entry(threadIdx.x, a.spec.C, a.spec.R);
   if (MODE != kModeObserve) {
     if (threadIdx.x < kNumStats) s_stats[threadIdx.x] = 0;
@@ -150,9 +130,9 @@ __global__ void __launch_bounds__(V::kBlock, kResidentThreads / V::kBlock) k_mai
   }
   __syncthreads();
   Game G;
-  Prefetch pre;
-  pre.at = -1;
-  bool queued = false, moved_any = false, restarted = false;
+  uint64_t Q = 0;
+  bool moved_any = false, restarted = false;
+  int job = 0;  // 0 none, 1 reset job queued, 2 refill job queued
   int slot = -1;
   int reward = 0, done_out = 0, score_out = 0;
   uint32_t prev_last = 0;
@@ -160,12 +140,14 @@ __global__ void __launch_bounds__(V::kBlock, kResidentThreads / V::kBlock) k_mai
   // ---------------------------------------------------------------- phase A
   if (tile_live) {
     load_game(a.state, a.N, valid ? g : tile0, v, G);  // idle lanes mirror a live game; never stored
-    bool restart = false;
+    if (MODE != kModeObserve && V::kPrefill > 0 && n_pre > 0) {
+      const uint2 q2 = __ldcg(a.queue + (valid ? g : tile0));
+      Q = (uint64_t)q2.x | ((uint64_t)q2.y << 32);
+    }
+    uint32_t* const x = a.mt + (valid ? g : tile0) * (int64_t)kMtN;
+    bool restart = false, want_refill = false, direct = false;
     if (MODE == kModeStep) {
       const int uid = valid ? a.actions[g] : -1;
-      // a play/discard is followed by a deal: start fetching its RNG words now
-      if (valid && !G.done && uid >= 0 && uid < 2 * v.H() && G.deck_size > 0)
-        mt_load5(a.mt + g * (int64_t)kMtN, G.mti, pre);
       bool moved = false, term = false;
       int ep_len = 0;
       if (valid) {
@@ -192,11 +174,31 @@ __global__ void __launch_bounds__(V::kBlock, kResidentThreads / V::kBlock) k_mai
           }
         }
       }
+      restart = term && a.auto_reset;
       // the deal that follows a play/discard -- also for a game that just ended:
       // the reference deals before it looks at IsTerminal (rl_env.py:357-361)
-      if (moved) deal_loop(v, a.spec, G, false, g, a.mt, a.sampler_mode, pre);
+      if (moved) {
+        if (V::kPrefill > 0 && n_pre > 0) {
+          while (needs_deal(v, G)) {
+            if (q_count(Q) > 0) {
+              deal_card(v, G, queue_pop(v, G, Q), a.spec.obs_type);
+            } else if (restart && G.deck_size >= kSafeDraw && q_pend(Q) < 15) {
+              // the game restarts anyway: only the two RNG words of the draw matter
+              queue_skip(G, Q);
+              deal_card(v, G, __ffsll((long long)G.deck) - 1, a.spec.obs_type);
+            } else {
+              break;
+            }
+          }
+          if (needs_deal(v, G)) {  // the queue is empty
+            if (!restart && (q_pend(Q) > 0 || G.deck_size >= kSafeDraw)) want_refill = true;
+            else direct = true;
+          }
+        } else {
+          direct = needs_deal(v, G);
+        }
+      }
       if (term && !a.auto_reset) G.done = 1;
-      restart = term && a.auto_reset;
 #if HB_EARLY_OUT
       // the step's results are final here (a re-deal does not touch them): write them
       // now instead of carrying three registers through phases B and C
@@ -205,12 +207,6 @@ __global__ void __launch_bounds__(V::kBlock, kResidentThreads / V::kBlock) k_mai
         if (a.dones) a.dones[g] = (uint8_t)done_out;
         if (a.scores) a.scores[g] = score_out;
       }
-#endif
-#if HB_RESET_PREFETCH
-      // (only where the re-deal is the serial path: with the warp-parallel Lehmer decode the
-      // lines arrive by coalesced loads anyway and the prefetches only add traffic)
-      if (HB_RESET_PREFETCH_ALL || !hb::lehmer_for(V::kP * V::kH))
-        if (restart && a.spec.fast_reset) mt_prefetch_deal(a.mt + g * (int64_t)kMtN, G.mti, v.P() * v.H());
 #endif
       // episode statistics: warp aggregate -> CTA shared counters
       const unsigned tm = __ballot_sync(kFull, term);
@@ -230,24 +226,53 @@ __global__ void __launch_bounds__(V::kBlock, kResidentThreads / V::kBlock) k_mai
     }
     if (MODE != kModeObserve) {
       restarted = restart;
-      queued = restart && a.spec.fast_reset;
-      const unsigned qm = __ballot_sync(kFull, queued);
+      // ---- enqueue the RNG work
+      const bool want_job = (restart && a.spec.fast_reset && !direct) || want_refill;
+      const unsigned qm = __ballot_sync(kFull, want_job);
       if (qm) {
         int base = 0;
         if (lane == 0) base = atomicAdd(&s_nq, __popc(qm));
         base = __shfl_sync(kFull, base, 0);
         slot = base + __popc(qm & ((1u << lane) - 1u));
-        if (queued && slot >= kQueueCap) queued = false;  // queue full: general path below
-        if (queued) {
+        if (want_job && slot < kQueueCap) {
+          job = restart ? 1 : 2;
+          const int npend = q_pend(Q);
+          int r0 = G.mti - 2 * npend;
+          r0 += r0 < 0 ? kMtN : 0;
+          const int PH = v.P() * v.H();
+          int nfresh, npeek, s0;
+          uint64_t deck0;
+          if (restart) {
+            nfresh = PH; s0 = v.deck_max(); deck0 = a.spec.full_deck;
+            npeek = n_pre;  // PrefillFor keeps the last peeked draw of a fresh deck safe
+          } else {
+            nfresh = 0; s0 = G.deck_size; deck0 = G.deck;
+            npeek = G.deck_size >= kSafeDraw ? min(n_pre, G.deck_size - (kSafeDraw - 1)) : 0;
+          }
           s_q_tid[slot] = threadIdx.x;
-          s_q_mti[slot] = G.mti;
+          s_q_meta[slot] = (uint32_t)r0 | ((uint32_t)npend << 10) | ((uint32_t)nfresh << 14) |
+                           ((uint32_t)npeek << 20) | ((uint32_t)s0 << 24) |
+                           (a.sampler_mode == 1 ? 0x80000000u : 0u);
+          s_q_deck[slot] = make_uint2((uint32_t)deck0, (uint32_t)(deck0 >> 32));
+#if HB_RESET_PREFETCH
+          // the job's lines: [r0, r0 + 2T] and, for the regenerated part, 397 slots ahead
+          mt_prefetch_span(x, r0, 2 * (npend + nfresh + npeek) + 1);
+          mt_prefetch_span(x, mt_wrap(r0 + kMtM), 2 * (npend + nfresh));
+#endif
         }
       }
-      // random start player / tiny decks / queue overflow: general per-thread path
-      if (restart && !queued) {
+      // random start player / tiny decks / queue overflow / the last cards of a deck: the
+      // general per-thread path, straight on the game's mt19937 block
+      const bool general_restart = restart && job == 0;
+      if (want_refill && job == 0) direct = true;
+      if (general_restart || direct) {
+        if (V::kPrefill > 0 && n_pre > 0) {
+          flush_pending(x, G.mti, Q);
+          if (general_restart) Q = 0;  // a dropped queue's words were never consumed
+        }
         Prefetch none;
         none.at = -1;
-        deal_loop(v, a.spec, G, true, g, a.mt, a.sampler_mode, none);
+        deal_loop(v, a.spec, G, general_restart, g, a.mt, a.sampler_mode, none);
       }
     }
   }
@@ -256,154 +281,111 @@ __global__ void __launch_bounds__(V::kBlock, kResidentThreads / V::kBlock) k_mai
   if (MODE != kModeObserve) {
     __syncthreads();
     const int nq = s_nq < kQueueCap ? s_nq : kQueueCap;
-    constexpr bool kLehmer = HB_RESET_LEHMER == 1 ||
-                             (HB_RESET_LEHMER == 2 && V::kP * V::kH >= HB_LEHMER_MIN_PAIRS);
-    if (kLehmer && nq > 0) {  // CTA-uniform
-      // One lane per (queued game, draw): a warp re-deals floor(32 / (P*H)) games per
-      // round, everything warp-local.  Draw r of a fresh deck has the known size
-      // deck_max - r, so its index q_r = floor(u_r * size) does not depend on the
-      // earlier draws, and the card it denotes follows from q_0..q_r alone: walking
-      // back through the earlier draws, every q_j <= idx shifts idx up by one (the
-      // decoding of a Lehmer code).  The full deck is the contiguous bit range
-      // [0, deck_max), so idx is the deck position itself.  No serial chain is left.
-      const int pairs = v.P() * v.H();
-      const int gpw = 32 / pairs;
-      const int el = lane / pairs, r = lane - el * pairs;
-      const int H = v.H();
-      const int pl = r / H, slot_i = r - pl * H;
-      uint32_t* scratch = smem + (size_t)warp * a.warp_smem_words;  // the stream area is idle now
-      for (int e0 = warp * gpw; e0 < nq; e0 += kWarps * gpw) {  // warp-uniform
-        const int e = e0 + el;
-        const bool act = el < gpw && e < nq;
-        const unsigned gmask = act ? ((1u << pairs) - 1u) << (el * pairs) : 0u;
-        Prefetch f;
-        uint32_t* x = a.mt;
-        int at = 0, q = 0;
-        uint32_t lo = 0, hi = 0;
-        bool amb = false;
-        if (act) {
-          x = a.mt + (cta0 + s_q_tid[e]) * (int64_t)kMtN;
-          at = mt_wrap(s_q_mti[e] + 2 * r);
-          mt_load5(x, at, f);
-          lo = mt_temper(f.a);
-          hi = mt_temper(f.b);
-          q = draw_index(v.deck_max() - r, lo, hi, amb);
-        }
-        // a pair's x[k+2] is the next pair's slot: every load of the warp is done
-        // before any regenerated slot is stored (a game's pairs sit in one warp)
-        __syncwarp();
-        if (act) {
-          __stcg(x + at, mt_next_block_word(f.a, f.b, f.p));
-          __stcg(x + mt_wrap(at + 1), mt_next_block_word(f.b, f.c, f.q));
-        }
-        const bool slow = a.sampler_mode == 1 || (amb && a.sampler_mode != 2);
-        const unsigned slow_m = __ballot_sync(kFull, act && slow);
-        int idx = q;
-        for (int j = pairs - 2; j >= 0; --j) {
-          const int qj = __shfl_sync(kFull, q, el * pairs + j);
-          if (j < r && qj <= idx) ++idx;
-        }
-        int color, rank;
-        card_of_position(v, idx, color, rank);
-        const uint32_t card = (uint32_t)(color | (rank << 3)) << (6 * slot_i);
-        if (act) {
-          const uint32_t dl = __reduce_or_sync(gmask, idx < 32 ? 1u << idx : 0u);
-          const uint32_t dh = __reduce_or_sync(gmask, idx >= 32 ? 1u << (idx - 32) : 0u);
+    if (nq > 0) {  // CTA-uniform
+      // B1, one thread per (job, RNG word pair), kItems pairs per thread in flight at once:
+      //   pairs [0, npend)                     consumed earlier by queue cards: regenerate
+      //   pairs [npend, npend + nfresh)        the initial deal of a new game: draw + regenerate
+      //   pairs [npend + nfresh, T)            the next queue: draw only (words stay unconsumed)
+      // Draw d of a job has the known deck size s0 - d, so its index q_d = floor(u_d * size)
+      // does not depend on the earlier draws and is computed here, in parallel, for every draw
+      // of every job.  All loads come first, then a barrier, then the regenerated slots are
+      // stored (a pair's x[k+2] is the next pair's slot, so stores wait for every load).
+      // B2, one thread per job: the short serial chain deck -> q-th set bit -> deck over the
+      // job's indices in shared memory (jobs run side by side in the lanes of one warp).
+      const int PH = v.P() * v.H(), H = v.H();
+      const int tmax = PH + 2 * n_pre + 1;          // pair slots per job
+      const int chunk_jobs = (kItems * kBlock) / tmax;  // jobs per pass (>= 4 * 192 / 31)
+      for (int e_base = 0; e_base < nq; e_base += chunk_jobs) {  // CTA-uniform
+        const int n_jobs = min(chunk_jobs, nq - e_base);
+        const int n_slots = n_jobs * tmax;
+        uint32_t new0[kItems], new1[kItems];
+        bool store[kItems];
+        uint32_t* xs[kItems];
 #pragma unroll
-          for (int k = 0; k < kMaxPlayers; ++k) {
-            const uint32_t c = k < V::kP ? __reduce_or_sync(gmask, pl == k ? card : 0u) : 0u;
-            if (r == 0) s_res[e].cards[k] = c;
+        for (int u = 0; u < kItems; ++u) {
+          const int k = u * kBlock + threadIdx.x;
+          store[u] = false;
+          xs[u] = a.mt;
+          new0[u] = new1[u] = 0u;
+          if (k < n_slots) {
+            const int ej = k / tmax, it = k - ej * tmax;
+            const int e = e_base + ej;
+            const uint32_t meta = s_q_meta[e];
+            const int r0 = meta & 1023, npend = (meta >> 10) & 15, nfresh = (meta >> 14) & 63,
+                      npeek = (meta >> 20) & 15, s0 = (meta >> 24) & 127;
+            const int d = it - npend;
+            if (it < npend + nfresh + npeek) {
+              uint32_t* x = a.mt + (cta0 + s_q_tid[e]) * (int64_t)kMtN;
+              int at = r0 + 2 * it;
+              at -= at >= kMtN ? kMtN : 0;
+              const uint32_t wa = __ldcg(x + at), wb = __ldcg(x + mt_wrap(at + 1));
+              if (d < nfresh) {  // regenerated now
+                const uint32_t wc = __ldcg(x + mt_wrap(at + 2)), wp = __ldcg(x + mt_wrap(at + kMtM)),
+                               wq = __ldcg(x + mt_wrap(at + kMtM + 1));
+                new0[u] = mt_next_block_word(wa, wb, wp);
+                new1[u] = mt_next_block_word(wb, wc, wq);
+                store[u] = true;
+                xs[u] = x + at;
+              }
+              if (d >= 0) {
+                bool amb = false;
+                const int q = draw_index(s0 - d, mt_temper(wa), mt_temper(wb), amb);
+                s_qb[ej * tmax + d] = (uint8_t)q;
+                // a job with a draw that needs the exact fp64 sampler is left untouched here and
+                // redone by its own thread on the general path (phase C)
+                if (amb && a.sampler_mode != 2) atomicOr(&s_q_meta[e], 0x80000000u);
+              }
+            }
           }
-          if (r == 0) {
-            s_res[e].deck_lo = (uint32_t)a.spec.full_deck & ~dl;
-            s_res[e].deck_hi = (uint32_t)(a.spec.full_deck >> 32) & ~dh;
-          }
-        }
-        if (slow_m) {  // warp-uniform; fp64 restatement of the library sampler, serial per game
-          __syncwarp();
-          scratch[lane] = (uint32_t)q | ((uint32_t)amb << 8);
-          scratch[32 + lane] = lo;
-          scratch[64 + lane] = hi;
-          __syncwarp();
-          if (act && r == 0 && (slow_m & gmask))
-            reset_draw(v, a.spec, scratch + el * pairs, scratch + 32 + el * pairs,
-                       scratch + 64 + el * pairs, a.sampler_mode, s_res[e]);
-          __syncwarp();
-        }
-      }
-    }
-    if (!kLehmer && nq > 0) {  // CTA-uniform
-      // B1: one thread per (queued game, word pair) takes the pair from the game's
-      // stream: all loads first, barrier, then the regenerated slots are stored
-      // (a pair's x[k+2] is the next pair's slot, so stores wait for every load)
-      uint32_t* s_words = smem + (size_t)kWarps * a.warp_smem_words;
-      const int pairs = v.P() * v.H();
-      const int cap = kQueueCap * pairs;
-      for (int k0 = 0; k0 < nq * pairs; k0 += kBlock) {  // CTA-uniform trip count
-        const int k = k0 + threadIdx.x;
-        const bool act = k < nq * pairs;
-        Prefetch f;
-        uint32_t* x = a.mt;
-        int at = 0;
-        if (act) {
-          const int e = k / pairs, r = k - e * pairs;
-          x = a.mt + (cta0 + s_q_tid[e]) * (int64_t)kMtN;
-          at = mt_wrap(s_q_mti[e] + 2 * r);
-          mt_load5(x, at, f);
-          const uint32_t lo = mt_temper(f.a), hi = mt_temper(f.b);
-          bool amb = false;
-          const int q = draw_index(v.deck_max() - r, lo, hi, amb);  // deck size of draw r is known
-          s_words[k] = (uint32_t)q | ((uint32_t)amb << 8);
-          s_words[cap + k] = lo;
-          s_words[2 * cap + k] = hi;
         }
         __syncthreads();
-        if (act) {
-          __stcg(x + at, mt_next_block_word(f.a, f.b, f.p));
-          __stcg(x + mt_wrap(at + 1), mt_next_block_word(f.b, f.c, f.q));
-        }
-      }
-      __syncthreads();
-      constexpr bool kChain = HB_SERIAL_B2 == 1 || (HB_SERIAL_B2 == 2 && V::kP * V::kH >= 10);
-      if (kChain) {
-      // B2: one thread per queued game runs the select chain on the precomputed indices
-      for (int i = threadIdx.x; i < nq; i += kBlock)
-        reset_draw(v, a.spec, s_words + i * pairs, s_words + cap + i * pairs,
-                   s_words + 2 * cap + i * pairs, a.sampler_mode, s_res[i]);
-      } else {
-      // B2: the draw indices are all in shared memory, so the cards follow without a serial
-      // chain (Lehmer decode as above, through shared memory instead of shuffles): one thread
-      // per (game, draw) walks back through the game's earlier indices, then ORs its card into
-      // the game's hands and clears its deck bit.  A game with a draw that needs the exact
-      // fp64 sampler (or the exact-only test mode) is redone serially afterwards.
-      for (int i = threadIdx.x; i < nq; i += kBlock) {
 #pragma unroll
-        for (int p = 0; p < kMaxPlayers; ++p) s_res[i].cards[p] = 0;
-        s_res[i].deck_lo = (uint32_t)a.spec.full_deck;
-        s_res[i].deck_hi = (uint32_t)(a.spec.full_deck >> 32);
-      }
-      __syncthreads();
-      for (int k = threadIdx.x; k < nq * pairs; k += kBlock) {
-        const int e = k / pairs, r = k - e * pairs;
-        const uint32_t* qa = s_words + e * pairs;
-        int idx = (int)(qa[r] & 0xffu);
-        for (int j = r - 1; j >= 0; --j) idx += ((int)(qa[j] & 0xffu) <= idx) ? 1 : 0;
-        int color, rank;
-        card_of_position(v, idx, color, rank);
-        const int pl = r / v.H(), slot_i = r - pl * v.H();
-        atomicOr(&s_res[e].cards[pl], (uint32_t)(color | (rank << 3)) << (6 * slot_i));
-        if (idx < 32) atomicAnd(&s_res[e].deck_lo, ~(1u << idx));
-        else atomicAnd(&s_res[e].deck_hi, ~(1u << (idx - 32)));
-      }
-      __syncthreads();
-      for (int i = threadIdx.x; i < nq; i += kBlock) {
-        bool slow = a.sampler_mode == 1;
-        if (a.sampler_mode != 2)
-          for (int r = 0; r < pairs; ++r) slow |= (s_words[i * pairs + r] >> 8) != 0;
-        if (slow)
-          reset_draw(v, a.spec, s_words + i * pairs, s_words + cap + i * pairs,
-                     s_words + 2 * cap + i * pairs, a.sampler_mode, s_res[i]);
-      }
+        for (int u = 0; u < kItems; ++u) {
+          const int k = u * kBlock + threadIdx.x;
+          if (store[u]) {
+            const int e = e_base + k / tmax;
+            if (!(s_q_meta[e] >> 31)) {
+              const int at = (int)(xs[u] - (a.mt + (cta0 + s_q_tid[e]) * (int64_t)kMtN));
+              __stcg(xs[u], new0[u]);
+              __stcg(xs[u] + (at + 1 >= kMtN ? 1 - kMtN : 1), new1[u]);
+            }
+          }
+        }
+        if ((int)threadIdx.x < n_jobs) {
+          const int e = e_base + threadIdx.x;
+          const uint32_t meta = s_q_meta[e];
+          if (!(meta >> 31)) {
+            const int nfresh = (meta >> 14) & 63, npeek = (meta >> 20) & 15;
+            const uint2 dk = s_q_deck[e];
+            uint64_t deck = (uint64_t)dk.x | ((uint64_t)dk.y << 32), deck_fresh = deck, qacc = 0;
+            const uint8_t* qb = s_qb + threadIdx.x * tmax;
+            uint32_t hand = 0;
+            int pl = 0, slot_i = 0;
+#pragma unroll 1
+            for (int d = 0; d < nfresh + npeek; ++d) {
+              const int pos = select64(deck, (int)qb[d]);
+              deck &= ~(1ull << pos);
+              int color, rank;
+              card_of_position(v, pos, color, rank);
+              if (d < nfresh) {
+                hand |= (uint32_t)(color | (rank << 3)) << (6 * slot_i);
+                if (++slot_i == H) {  // player 0's hand first, then player 1's, ... (PlayerToDeal)
+                  s_res[e].cards[pl++] = hand;
+                  hand = 0;
+                  slot_i = 0;
+                }
+                deck_fresh = deck;
+              } else {
+                qacc |= (uint64_t)(color * v.R() + rank) << (5 * (d - nfresh));
+              }
+            }
+            s_res[e].deck_lo = (uint32_t)deck_fresh;
+            s_res[e].deck_hi = (uint32_t)(deck_fresh >> 32);
+            s_res[e].q_lo = (uint32_t)qacc;
+            s_res[e].q_hi = (uint32_t)(qacc >> 32) | ((uint32_t)npeek << 24);  // count at bit 56, nothing pending
+          }
+        }
+        if (e_base + chunk_jobs < nq) __syncthreads();  // s_qb is reused by the next pass
       }
     }
     __syncthreads();
@@ -413,7 +395,28 @@ __global__ void __launch_bounds__(V::kBlock, kResidentThreads / V::kBlock) k_mai
   if (!tile_live) return;
 
   // ---------------------------------------------------------------- phase C
-  if (queued) reset_apply(v, a.spec, G, s_res[slot]);
+  if (job != 0) {
+    const bool slow = (s_q_meta[slot] >> 31) != 0u;
+    bool general = slow;
+    if (!slow) {
+      Q = (uint64_t)s_res[slot].q_lo | ((uint64_t)s_res[slot].q_hi << 32);
+      if (job == 1) {
+        reset_apply(v, a.spec, G, s_res[slot]);
+      } else {
+        // the refilled queue serves the deal this game was waiting for
+        while (needs_deal(v, G) && q_count(Q) > 0) deal_card(v, G, queue_pop(v, G, Q), a.spec.obs_type);
+        general = needs_deal(v, G);  // the last cards of the deck: no queue any more
+      }
+    }
+    if (general) {
+      uint32_t* const x = a.mt + g * (int64_t)kMtN;
+      flush_pending(x, G.mti, Q);
+      if (job == 1) Q = 0;
+      Prefetch none;
+      none.at = -1;
+      deal_loop(v, a.spec, G, job == 1, g, a.mt, a.sampler_mode, none);
+    }
+  }
   if (valid) {
 #if !HB_EARLY_OUT
     if (MODE == kModeStep) {
@@ -423,7 +426,10 @@ __global__ void __launch_bounds__(V::kBlock, kResidentThreads / V::kBlock) k_mai
     }
 #endif
     if (a.cur_player) a.cur_player[g] = G.cur;
-    if (MODE != kModeObserve) store_game(a.state, a.N, g, v, G);
+    if (MODE != kModeObserve) {
+      store_game(a.state, a.N, g, v, G);
+      if (V::kPrefill > 0 && n_pre > 0) __stcg(a.queue + g, make_uint2((uint32_t)Q, (uint32_t)(Q >> 32)));
+    }
     if (MODE != kModeObserve && a.hist != nullptr) {
       // move history for the rule-based agents: a new game starts with none
       if (restarted) {
@@ -573,6 +579,14 @@ __global__ void k_pack(KArgs a, const int32_t* in, const int32_t* extra) {
   const DView v(a.spec);
   Game G;
   load_game(a.state, a.N, g, v, G);
+  if (a.spec.prefill > 0) {
+    // the injected deck invalidates the pre-drawn cards: their words were never consumed, the
+    // pending slots are regenerated, and the game goes on without a queue until its next refill
+    const uint2 q2 = a.queue[g];
+    uint64_t Q = (uint64_t)q2.x | ((uint64_t)q2.y << 32);
+    flush_pending(a.mt + g * (int64_t)kMtN, G.mti, Q);
+    a.queue[g] = make_uint2(0u, 0u);
+  }
   const int32_t* d = in + g * (int64_t)kDumpLen;
   const int C = a.spec.C, R = a.spec.R;
   G.cur = d[0] < 0 ? 0 : d[0]; G.info = d[1]; G.life = d[2]; G.deck_size = d[3];
@@ -667,6 +681,7 @@ struct Batch {
   int64_t N = 0;
   int ncols = 0;
   uint4* state = nullptr;
+  uint2* queue = nullptr;
   uint32_t* mt = nullptr;
   unsigned long long* stats = nullptr;      // active stats buffer
   unsigned long long* own_stats = nullptr;  // library-owned fallback
@@ -746,6 +761,7 @@ hb::KArgs BaseArgs(const Batch* b) {
   std::memset(&a, 0, sizeof(a));
   a.spec = b->spec;
   a.state = b->state;
+  a.queue = b->queue;
   a.mt = b->mt;
   a.N = b->N;
   a.g_begin = 0;
@@ -761,14 +777,11 @@ hb::KArgs BaseArgs(const Batch* b) {
   return a;
 }
 
-// Dynamic shared memory of k_main<V>: one packed-stream area per warp, the (index, lo, hi)
-// table of the serial re-deal path, and -- for the launches that write network-input rows
-// -- the 4 KB element table behind them.
+// Dynamic shared memory of k_main<V>: one packed-stream area per warp and -- for the
+// launches that write network-input rows -- the 4 KB element table behind them.
 template <class V>
 size_t ViewSmemWords(const Batch* b) {
-  const bool lehmer = hb::lehmer_for(V::kP * V::kH);
-  const size_t words = (size_t)(V::kBlock / 32) * b->warp_smem_words +
-                       (lehmer ? 0 : (size_t)hb::queue_cap(V::kBlock, V::kP * V::kH) * 3 * b->spec.P * b->spec.H);
+  const size_t words = (size_t)(V::kBlock / 32) * b->warp_smem_words;
   return (words + 3) & ~(size_t)3;
 }
 
@@ -883,7 +896,7 @@ int NewBatch(pyhanabi_batch_t* out, int list_length, const char** param_list, in
   if (!guard.ok) { delete b; return Fail("NewBatch: cudaSetDevice failed"); }
   int32_t* d_seeds = nullptr;
   auto cleanup = [&]() {
-    cudaFree(b->state); cudaFree(b->mt); cudaFree(b->own_stats); cudaFree(d_seeds);
+    cudaFree(b->state); cudaFree(b->queue); cudaFree(b->mt); cudaFree(b->own_stats); cudaFree(d_seeds);
     delete b;
   };
 #define HB_TRY(expr)                                                           \
@@ -892,6 +905,8 @@ int NewBatch(pyhanabi_batch_t* out, int list_length, const char** param_list, in
     if (e__ != cudaSuccess) { cleanup(); return CudaFail("NewBatch: " #expr, e__); } \
   } while (0)
   HB_TRY(cudaMalloc(&b->state, sizeof(uint4) * (size_t)b->ncols * (size_t)b->N));
+  HB_TRY(cudaMalloc(&b->queue, sizeof(uint2) * (size_t)b->N));
+  HB_TRY(cudaMemset(b->queue, 0, sizeof(uint2) * (size_t)b->N));
   HB_TRY(cudaMalloc(&b->mt, sizeof(uint32_t) * (size_t)hb::kMtN * (size_t)b->N));
   HB_TRY(cudaMalloc(&b->own_stats, sizeof(unsigned long long) * hb::kNumStats));
   HB_TRY(cudaMemset(b->own_stats, 0, sizeof(unsigned long long) * hb::kNumStats));
@@ -930,6 +945,7 @@ void DeleteBatch(pyhanabi_batch_t* h) {
   cudaFree(b->d_actions); cudaFree(b->d_rewards); cudaFree(b->d_scores); cudaFree(b->d_cur);
   cudaFree(b->d_dones); cudaFree(b->d_obs); cudaFree(b->d_mask);
   cudaFree(b->state);
+  cudaFree(b->queue);
   cudaFree(b->mt);
   cudaFree(b->own_stats);
   cudaFree(b->hist);
@@ -1363,38 +1379,67 @@ int BatchObservePacked(pyhanabi_batch_t* h, int observer, uint32_t* obs_bits, ui
   return 0;
 }
 
+// Checkpoint blob: a 128-byte header (magic, layout version, the complete rule set, the
+// number of games and state columns, whether the move-history ring is on), then the packed
+// state columns, the deal queue words, every game's mt19937 block, the history ring (if on)
+// and the 32 statistics counters.
+namespace {
+constexpr int64_t kBlobMagic = 0x4842323030ll, kBlobVersion = 2;
+constexpr int kBlobHeader = 16;  // int64 words
+void FillBlobHeader(const Batch* b, int64_t* hd) {
+  const hb::Spec& s = b->spec;
+  const int64_t v[kBlobHeader] = {kBlobMagic, kBlobVersion, b->N, b->ncols, s.P, s.C, s.R, s.H, s.IT, s.LT,
+                                  s.obs_type, s.random_start, s.prefill, b->hist ? 1 : 0, s.obs_size, s.max_moves};
+  std::memcpy(hd, v, sizeof(v));
+}
+}  // namespace
+
 int64_t BatchStateBytes(pyhanabi_batch_t* h) {
   if (!h || !h->batch) return -1;
   Batch* b = AsBatch(h->batch);
-  return 64 + (int64_t)sizeof(uint4) * b->ncols * b->N + (int64_t)sizeof(uint32_t) * hb::kMtN * b->N;
+  return (int64_t)sizeof(int64_t) * kBlobHeader + (int64_t)sizeof(uint4) * b->ncols * b->N +
+         (int64_t)sizeof(uint2) * b->N + (int64_t)sizeof(uint32_t) * hb::kMtN * b->N +
+         (b->hist ? (int64_t)sizeof(uint4) * b->N : 0) + (int64_t)sizeof(int64_t) * hb::kNumStats;
 }
 
 int BatchGetState(pyhanabi_batch_t* h, void* host_blob, int64_t nbytes) {
   HB_BATCH(h);
   if (nbytes < BatchStateBytes(h)) return Fail("BatchGetState: blob too small, see BatchStateBytes");
   HB_CUDA(cudaDeviceSynchronize());
-  int64_t header[8] = {0x4842323030ll, b->N, b->spec.P, b->ncols, b->spec.obs_size, b->spec.max_moves, 0, 0};
-  std::memcpy(host_blob, header, 64);
-  char* p = static_cast<char*>(host_blob) + 64;
-  const size_t sb = sizeof(uint4) * (size_t)b->ncols * (size_t)b->N;
+  int64_t header[kBlobHeader];
+  FillBlobHeader(b, header);
+  std::memcpy(host_blob, header, sizeof(header));
+  char* p = static_cast<char*>(host_blob) + sizeof(header);
+  const size_t N = (size_t)b->N;
+  const size_t sb = sizeof(uint4) * (size_t)b->ncols * N, qb = sizeof(uint2) * N,
+               mb = sizeof(uint32_t) * (size_t)hb::kMtN * N, hbytes = b->hist ? sizeof(uint4) * N : 0;
   HB_CUDA(cudaMemcpy(p, b->state, sb, cudaMemcpyDeviceToHost));
-  HB_CUDA(cudaMemcpy(p + sb, b->mt, sizeof(uint32_t) * (size_t)hb::kMtN * (size_t)b->N, cudaMemcpyDeviceToHost));
+  HB_CUDA(cudaMemcpy(p + sb, b->queue, qb, cudaMemcpyDeviceToHost));
+  HB_CUDA(cudaMemcpy(p + sb + qb, b->mt, mb, cudaMemcpyDeviceToHost));
+  if (hbytes) HB_CUDA(cudaMemcpy(p + sb + qb + mb, b->hist, hbytes, cudaMemcpyDeviceToHost));
+  HB_CUDA(cudaMemcpy(p + sb + qb + mb + hbytes, b->stats, sizeof(int64_t) * hb::kNumStats, cudaMemcpyDeviceToHost));
   return 0;
 }
 
 int BatchSetState(pyhanabi_batch_t* h, const void* host_blob, int64_t nbytes) {
   HB_BATCH(h);
   if (nbytes < BatchStateBytes(h)) return Fail("BatchSetState: blob too small, see BatchStateBytes");
-  int64_t header[8];
-  std::memcpy(header, host_blob, 64);
-  if (header[0] != 0x4842323030ll || header[1] != b->N || header[2] != b->spec.P ||
-      header[3] != b->ncols || header[4] != b->spec.obs_size || header[5] != b->spec.max_moves)
-    return Fail("BatchSetState: blob does not match this batch (games / rules / state layout differ)");
+  int64_t header[kBlobHeader], mine[kBlobHeader];
+  std::memcpy(header, host_blob, sizeof(header));
+  FillBlobHeader(b, mine);
+  if (std::memcmp(header, mine, sizeof(header)) != 0)
+    return Fail("BatchSetState: blob does not match this batch (layout version, games, rule set, "
+                "observation type or history setting differ)");
   HB_CUDA(cudaDeviceSynchronize());
-  const char* p = static_cast<const char*>(host_blob) + 64;
-  const size_t sb = sizeof(uint4) * (size_t)b->ncols * (size_t)b->N;
+  const char* p = static_cast<const char*>(host_blob) + sizeof(header);
+  const size_t N = (size_t)b->N;
+  const size_t sb = sizeof(uint4) * (size_t)b->ncols * N, qb = sizeof(uint2) * N,
+               mb = sizeof(uint32_t) * (size_t)hb::kMtN * N, hbytes = b->hist ? sizeof(uint4) * N : 0;
   HB_CUDA(cudaMemcpy(b->state, p, sb, cudaMemcpyHostToDevice));
-  HB_CUDA(cudaMemcpy(b->mt, p + sb, sizeof(uint32_t) * (size_t)hb::kMtN * (size_t)b->N, cudaMemcpyHostToDevice));
+  HB_CUDA(cudaMemcpy(b->queue, p + sb, qb, cudaMemcpyHostToDevice));
+  HB_CUDA(cudaMemcpy(b->mt, p + sb + qb, mb, cudaMemcpyHostToDevice));
+  if (hbytes) HB_CUDA(cudaMemcpy(b->hist, p + sb + qb + mb, hbytes, cudaMemcpyHostToDevice));
+  HB_CUDA(cudaMemcpy(b->stats, p + sb + qb + mb + hbytes, sizeof(int64_t) * hb::kNumStats, cudaMemcpyHostToDevice));
   return 0;
 }
 

@@ -44,6 +44,8 @@ struct SView {
   static constexpr bool kStatic = true;
   static constexpr int kP = P_, kH = H_, kC = C_, kR = R_;
   static constexpr int kBlock = block_for_deal(P_ * H_);
+  // longest deal queue this shape can have (0: the queue code is compiled out)
+  static constexpr int kPrefill = PrefillFor(P_, H_, (R_ == 1 ? 3 : 2 * R_) * C_, 0);
   HB_DEV explicit SView(const Spec&) {}
   HB_DEV constexpr int P() const { return P_; }
   HB_DEV constexpr int H() const { return H_; }
@@ -60,6 +62,7 @@ struct DView {
   static constexpr bool kStatic = false;
   static constexpr int kP = kMaxPlayers, kH = kMaxHand, kC = kMaxColors, kR = kMaxRanks;
   static constexpr int kBlock = block_for_deal(kMaxPlayers * kMaxHand);
+  static constexpr int kPrefill = kMaxPrefill;
   const Spec& s;
   HB_DEV explicit DView(const Spec& sp) : s(sp) {}
   HB_DEV int P() const { return s.P; }
@@ -346,12 +349,73 @@ HB_DEV void mt_prefetch_deal(const uint32_t* x, int k, int pairs) {
   if (me >= kMtN) prefetch_l2(x);
 }
 
+// L2 prefetch of `count` consecutive slots from `start` on (indices mod 624), one prefetch
+// per 128 bytes.
+HB_DEV void mt_prefetch_span(const uint32_t* x, int start, int count) {
+  if (count <= 0) return;
+  for (int o = 0; o < count; o += 32) prefetch_l2(x + mt_wrap(start + o));
+  prefetch_l2(x + mt_wrap(start + count - 1));
+}
+
 // Takes one output (random start player draw).
 HB_DEV uint32_t mt_take1(uint32_t* x, int& k) {
   const uint32_t a = __ldcg(x + k), b = __ldcg(x + mt_wrap(k + 1)), p = __ldcg(x + mt_wrap(k + kMtM));
   __stcg(x + k, mt_next_block_word(a, b, p));
   k = mt_wrap(k + 1);
   return mt_temper(a);
+}
+
+// ------------------------------------------------------------ deal queue
+// Per game one 64-bit queue word (its own column, 8 bytes per game):
+//   bits [0,55)   up to 11 pre-drawn cards, 5-bit type ids (colour * R + rank), next card lowest
+//   bits [56,60)  number of cards in the queue
+//   bits [60,64)  pending pairs: RNG word pairs already consumed by dealt cards whose slots
+//                 have not been regenerated yet (they sit right below the take index G.mti)
+// The queue's cards were drawn from the word pairs at G.mti, G.mti + 2, ... given the deck as
+// it is; those words count as consumed only when their card is dealt, so a game that ends
+// early leaves them to the next episode exactly as the reference's single stream does
+// (one std::mt19937 per HanabiGame, hanabi_game.h:114).  Deferred regeneration keeps the
+// in-place mt19937 scheme valid as long as fewer than 227 words are pending (slot k's
+// regeneration needs slot k - 227 already regenerated): at most 2 * 15 here.
+HB_DEV int q_count(uint64_t Q) { return (int)(Q >> 56) & 15; }
+HB_DEV int q_pend(uint64_t Q) { return (int)(Q >> 60) & 15; }
+HB_DEV uint64_t q_make(uint64_t cards, int count, int pend) {
+  return cards | ((uint64_t)count << 56) | ((uint64_t)pend << 60);
+}
+
+// Takes the next card off the queue: returns its deck bit position (an instance of that
+// type that is still in the deck) and accounts for the two RNG words it consumes.
+template <class V>
+HB_DEV int queue_pop(V v, Game& G, uint64_t& Q) {
+  const int t = (int)(Q & 31u);
+  Q = q_make((Q & ((1ull << 55) - 1ull)) >> 5, q_count(Q) - 1, q_pend(Q) + 1);
+  G.mti = mt_wrap(G.mti + 2);
+  const int color = t / v.R(), rank = t - color * v.R();
+  const int off = color * v.per_color() + DiscardRankOffset(rank);
+  const uint32_t block = (uint32_t)(G.deck >> off) & 7u & ((1u << InstancesOfRank(v.R(), rank)) - 1u);
+  return off + __ffs((int)block) - 1;
+}
+
+// One more consumed pair whose card does not matter (the game is about to restart).
+HB_DEV void queue_skip(Game& G, uint64_t& Q) {
+  Q += 1ull << 60;
+  G.mti = mt_wrap(G.mti + 2);
+}
+
+// Regenerates the pending slots one after the other (rare paths only: state injection,
+// the last cards of a deck, queue overflow); afterwards every slot below G.mti is regenerated.
+HB_DEV void flush_pending(uint32_t* x, int mti, uint64_t& Q) {
+  const int pend = q_pend(Q);
+  int at = mti - 2 * pend;
+  at += at < 0 ? kMtN : 0;
+  for (int i = 0; i < pend; ++i) {
+    Prefetch f;
+    mt_load5(x, at, f);
+    __stcg(x + at, mt_next_block_word(f.a, f.b, f.p));
+    __stcg(x + mt_wrap(at + 1), mt_next_block_word(f.b, f.c, f.q));
+    at = mt_wrap(at + 2);
+  }
+  Q &= ~(15ull << 60);
 }
 
 // ------------------------------------------------------------- deal sampling
@@ -720,49 +784,17 @@ HB_DEV void deal_loop(V v, const Spec& spec, Game& G, bool restart, int64_t g, u
   }
 }
 
-// ---- re-deal of finished games, compacted over the CTA ----------------------
-// Finished games that qualify (spec.fast_reset: no random start player and every
-// draw of the initial deal is a >= 2-type draw) are queued in shared memory; after a barrier the
-// first threads of the CTA each draw one queued game's P*H cards, so the draw
-// code runs on densely populated warps instead of the few finished lanes of
-// every warp.  A rolled loop keeps the code small.
-struct ResetResult {
-  uint32_t cards[kMaxPlayers];
-  uint32_t deck_lo, deck_hi;
+// ---- (re-)deal jobs, compacted over the CTA --------------------------------
+// A finished game that qualifies (spec.fast_reset: no random start player, every draw of the
+// initial deal is a >= 2-type draw) and a running game whose deal queue ran dry enqueue a JOB
+// in shared memory; after a CTA barrier the warps work the jobs off with one lane per RNG word
+// pair (k_main, phase B).  The result of a job:
+struct JobResult {
+  uint32_t cards[kMaxPlayers];  // the new hands (reset jobs)
+  uint32_t deck_lo, deck_hi;    // deck bitmap after the initial deal (reset jobs)
+  uint32_t q_lo, q_hi;          // the game's new queue word
 };
-
-// Draws the initial deal of one game.  Draw r (deck size deck_max - r) comes with
-// its precomputed index qa[r] = floor(u_r * size) | ambiguous << 8 and its tempered
-// RNG words lo[r], hi[r] (only read for the rare exact re-draw), all in shared
-// memory.  The only serial dependency left is deck -> select -> deck.  Player 0's
-// hand is filled first, then player 1's, ... (PlayerToDeal, hanabi_state.cc:157-164).
-template <class V>
-HB_DEV void reset_draw(V v, const Spec& spec, const uint32_t* qa, const uint32_t* lo,
-                       const uint32_t* hi, int sampler_mode, ResetResult& out) {
-  uint64_t deck = spec.full_deck;
-  int n = v.deck_max();
-  const int H = v.H(), total = v.P() * H;
-#pragma unroll
-  for (int p = 0; p < kMaxPlayers; ++p) out.cards[p] = 0;
-  int p = 0, i = 0;
-#pragma unroll 1
-  for (int r = 0; r < total; ++r) {
-    const uint32_t w = qa[r];
-    int pos = select64(deck, (int)(w & 0xffu));
-    if (sampler_mode == 1 || ((w >> 8) && sampler_mode != 2))
-      pos = pick_exact(v, deck, n, lo[r], hi[r]);
-    int color, rank;
-    card_of_position(v, pos, color, rank);
-    const uint32_t card = (uint32_t)(color | (rank << 3)) << (6 * i);
-#pragma unroll
-    for (int k = 0; k < V::kP; ++k) out.cards[k] |= (k == p) ? card : 0u;
-    deck &= ~(1ull << pos);
-    --n;
-    if (++i == H) { i = 0; ++p; }
-  }
-  out.deck_lo = (uint32_t)deck;
-  out.deck_hi = (uint32_t)(deck >> 32);
-}
+typedef JobResult ResetResult;
 
 // Installs a drawn initial deal as the lane's new game.
 template <class V>

@@ -26,6 +26,16 @@ constexpr int kMaxInfo = 31;     // 5-bit field
 constexpr int kMaxLife = 15;     // 4-bit field
 constexpr int kMtN = 624;
 constexpr int kMtM = 397;
+// Pre-drawn deal queue (DESIGN.md "deal queue"): when a game is (re-)dealt, the cards of its
+// next `prefill` in-game deals are drawn as well -- from RNG words that stay unconsumed until
+// the card is actually dealt -- so that a deal inside the episode touches no RNG memory.
+// A draw from a deck of >= kSafeDraw cards always sees >= 2 card types (at most 3 instances
+// per type), i.e. always consumes two RNG words (random.tcc:2660-2664).
+constexpr int kMaxPrefill = 10;  // 5-bit type ids in a 64-bit queue word: 11 would fit, 10 keeps a job within 32 lanes
+constexpr int kSafeDraw = 4;
+#ifndef HB_PREFILL
+#define HB_PREFILL -1  // >= 0: upper bound on the queue length (experiments); -1: as long as it fits
+#endif
 
 // Observation types, hanabi_lib/hanabi_game.h:39.
 enum ObsType { kMinimal = 0, kCardKnowledge = 1, kSeer = 2 };
@@ -53,6 +63,7 @@ struct Spec {
   int32_t obs_size, max_moves;
   int32_t hands_len, board_len, discard_len, last_len, know_len;
   int32_t fast_reset;  // the unrolled re-deal applies (no random start, >= 2 card types left throughout)
+  int32_t prefill;     // length of the pre-drawn deal queue (0 = off), PrefillFor()
   // Deck bitmap helpers (one bit per card instance, same layout as the discard
   // thermometers): first bit of every type block by block width.
   uint64_t full_deck, type_m23, type_m3, type_m1;
@@ -63,6 +74,21 @@ HB_HD int InstancesOfRank(int R, int rank) {  // hanabi_game.cc:126-136
 }
 // Bit offset of rank r inside one colour's discard thermometer block.
 HB_HD int DiscardRankOffset(int rank) { return rank == 0 ? 0 : 2 * rank + 1; }
+
+// Queue length n for a rule set: one job = (n + 1) pending + P*H fresh + n peeked word
+// pairs must fit the 32 lanes of a warp, and the last peeked draw must still be "safe".
+HB_HD constexpr int PrefillFor(int P, int H, int deck_max, int random_start) {
+  if (random_start || deck_max - P * H < 3 || P * H > 30) return 0;
+  int n = (31 - P * H) / 2;
+  if (n > kMaxPrefill) n = kMaxPrefill;
+  // episodes of small decks are short: a quarter of the in-game deck is plenty, and short
+  // jobs pack two or three to a warp
+  const int quarter = (deck_max - P * H) / 4 < 2 ? 2 : (deck_max - P * H) / 4;
+  if (n > quarter) n = quarter;
+  if (n > deck_max - P * H - 3) n = deck_max - P * H - 3;
+  if (HB_PREFILL >= 0 && n > HB_PREFILL) n = HB_PREFILL;
+  return n < 0 ? 0 : n;
+}
 
 // Fills the derived fields.  Returns 0 on success, else an error code whose
 // text hb::SpecError() returns.
@@ -97,7 +123,8 @@ inline int FinishSpec(Spec* s) {
       if (n == 1) s->type_m1 |= 1ull << off;
     }
   // A deck with more cards than the largest multiplicity (3) holds >= 2 types.
-  s->fast_reset = (!s->random_start && s->deck_max - s->P * s->H >= 3) ? 1 : 0;
+  s->fast_reset = (!s->random_start && s->deck_max - s->P * s->H >= 3 && s->P * s->H <= 30) ? 1 : 0;
+  s->prefill = PrefillFor(s->P, s->H, s->deck_max, s->random_start);
   return 0;
 }
 
