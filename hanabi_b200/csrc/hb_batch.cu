@@ -21,6 +21,16 @@
 namespace hb {
 
 enum Mode { kModeStep = 0, kModeReset = 1, kModeObserve = 2 };
+#ifndef HB_ITEMS
+#define HB_ITEMS 3
+#endif
+// Serial path (initial deals of up to 10 cards), phase B2: 1 = one thread per game draws the
+// cards one after the other, 0 = one thread per (game, draw) decodes its card from the game's
+// draw indices (two more CTA barriers), 2 = the former for deals of 10+ cards, the latter below
+// (measured: Full 2p 1.6 % faster with the chain, Small 2p / 4p 1.2 % / 3 % faster with the decode).
+#ifndef HB_SERIAL_B2
+#define HB_SERIAL_B2 2
+#endif
 #ifndef HB_EARLY_OUT
 #define HB_EARLY_OUT 0  // measured: -1.2 % on Full 2p, +1.1 % on Full 4p
 #endif
@@ -32,13 +42,16 @@ enum Mode { kModeStep = 0, kModeReset = 1, kModeObserve = 2 };
 #define HB_RESIDENT 768  // measured again on the final kernel: 640 (90 registers, no spills) 0.5-0.7 % slower
 #endif
 constexpr int kResidentThreads = HB_RESIDENT;
+// serial path: three words per queued draw, bounded so that the table stays within 640 draws
+constexpr int serial_queue_cap(int block, int cards) {
+  return block / 2 < 640 / cards ? block / 2 : 640 / cards;
+}
 constexpr int kStreamPad = 2;    // readable pad words after each packed bit stream
 constexpr int kNumStats = 32;    // [0] episodes [1] sum score [2] sum length [3..28] score histogram
 
 struct KArgs {
   Spec spec;
   uint4* state;
-  uint2* queue;  // the games' deal queue words (hb_engine.cuh "deal queue"), 8 bytes per game
   uint32_t* mt;
   int64_t N;
   int64_t g_begin, g_end;  // range of games this launch covers (g_begin % 32 == 0)
@@ -77,28 +90,30 @@ struct KArgs {
 // One CTA = kBlock games = kBlock/32 warp tiles.  Phases separated by CTA barriers keep the
 // warps of an SM inside the same stretch of code (the kernel is ~100 KB of SASS,
 // far beyond the instruction caches) and let the RNG work be done by compacted lanes:
-//   A  load state -> apply move -> deal the follow-up card FROM THE GAME'S QUEUE (no RNG
-//      memory access) -> terminal; finished games and games whose queue ran dry enqueue a
-//      job in shared memory
-//   B  the warps work the jobs off, one lane per RNG word pair: regenerate the consumed
-//      slots, draw the initial deal of a new game and pre-draw the next queue
-//   C  install the job results, store state + queue, encode observation + legal mask into
-//      the warp's packed bit stream, expand to bytes with 128-bit stores
+//   A  load state (+ prefetch two RNG words) -> apply move -> deal (the deal only READS its
+//      two words: lazy regeneration) -> terminal; finished games and games with many pending
+//      pairs enqueue a job in shared memory
+//   B  all threads work the jobs off, one thread per RNG word pair: regenerate the pending
+//      slots and draw the initial deals of the new games
+//   C  install new games, store state, encode observation + legal mask into the
+//      warp's packed bit stream, expand to bytes with 128-bit stores
 // NET: the instantiation that also writes network-input rows (BatchStepEncodeNet /
 // BatchObserveNet); kept out of the plain kernels so that their code stays as small as it was.
 template <class V, int MODE, bool NET = false>
 __global__ void __launch_bounds__(V::kBlock, kResidentThreads / V::kBlock) k_main(const __grid_constant__ KArgs a) {
   constexpr int kBlock = V::kBlock, kWarps = kBlock / 32;
-  constexpr int kQueueCap = kBlock / 2;  // jobs a CTA works off per launch; the rest take the per-thread path
+  constexpr bool kJobs = V::kJobs;  // which re-deal machinery this rule set uses (hb_engine.cuh)
+  // finished games (and flushes) a CTA works off through shared memory per launch; the rest
+  // take the per-thread path
+  constexpr int kQueueCap = kJobs ? kBlock / 2 : hb::serial_queue_cap(kBlock, V::kP * V::kH);
   extern __shared__ uint32_t smem[];
   __shared__ int s_stats[kNumStats];
   __shared__ int s_nq;
   __shared__ int s_q_tid[kQueueCap];
-  __shared__ uint32_t s_q_meta[kQueueCap];  // r0 | npend << 10 | nfresh << 14 | npeek << 20 | s0 << 24 | slow << 31
-  __shared__ uint2 s_q_deck[kQueueCap];     // deck bitmap the job draws from
+  __shared__ uint32_t s_q_meta[kQueueCap];  // jobs: r0 | npend << 10 | nfresh << 14 | slow << 31; serial: mt index
   __shared__ JobResult s_res[kQueueCap];
-  constexpr int kItems = 4;  // RNG word pairs per thread in flight in phase B
-  __shared__ uint8_t s_qb[kItems * kBlock];  // draw indices of the jobs of one pass
+  constexpr int kItems = HB_ITEMS;  // job path: RNG word pairs per thread in flight in phase B
+  __shared__ uint8_t s_qb[kJobs ? kItems * kBlock : 4];  // job path: draw indices of one pass
   __shared__ uint32_t s_spread[32];
   // byte -> its eight 16-bit elements: 4 KB of dynamic shared memory that only the launches
   // writing network-input rows ask for
@@ -121,8 +136,10 @@ __global__ void __launch_bounds__(V::kBlock, kResidentThreads / V::kBlock) k_mai
   const int64_t tile0 = g - lane;  // first game of this warp's tile
   const bool valid = g < a.g_end;
   const bool tile_live = tile0 < a.g_end;
-  // length of the deal queue for this batch (compiled out where the shape cannot have one)
-  const int n_pre = V::kPrefill > 0 ? a.spec.prefill : 0;
+  // lazy regeneration: pending pairs a game of this batch may carry (0 = off; compiled out
+  // where the shape cannot use it)
+  const int pend_cap = V::kPendCap > 0 ? a.spec.pend_cap : 0;
+  const bool lazy = pend_cap > 0;
   if (threadIdx.x < 32) s_spread[threadIdx.x] = spread_entry(threadIdx.x, a.spec.C, a.spec.R);
   if (MODE != kModeObserve) {
     if (threadIdx.x < kNumStats) s_stats[threadIdx.x] = 0;
@@ -130,9 +147,10 @@ __global__ void __launch_bounds__(V::kBlock, kResidentThreads / V::kBlock) k_mai
   }
   __syncthreads();
   Game G;
-  uint64_t Q = 0;
+  Prefetch pre;
+  pre.at = -1;
   bool moved_any = false, restarted = false;
-  int job = 0;  // 0 none, 1 reset job queued, 2 refill job queued
+  int job = 0;  // 0 none, 1 re-deal job queued, 2 flush job queued
   int slot = -1;
   int reward = 0, done_out = 0, score_out = 0;
   uint32_t prev_last = 0;
@@ -140,14 +158,14 @@ __global__ void __launch_bounds__(V::kBlock, kResidentThreads / V::kBlock) k_mai
   // ---------------------------------------------------------------- phase A
   if (tile_live) {
     load_game(a.state, a.N, valid ? g : tile0, v, G);  // idle lanes mirror a live game; never stored
-    if (MODE != kModeObserve && V::kPrefill > 0 && n_pre > 0) {
-      const uint2 q2 = __ldcg(a.queue + (valid ? g : tile0));
-      Q = (uint64_t)q2.x | ((uint64_t)q2.y << 32);
-    }
-    uint32_t* const x = a.mt + (valid ? g : tile0) * (int64_t)kMtN;
-    bool restart = false, want_refill = false, direct = false;
+    bool restart = false, want_flush = false;
     if (MODE == kModeStep) {
       const int uid = valid ? a.actions[g] : -1;
+      // a play/discard is followed by a deal: start fetching its RNG words now
+      if (valid && !G.done && uid >= 0 && uid < 2 * v.H() && G.deck_size > 0) {
+        if (lazy) mt_load2(a.mt + g * (int64_t)kMtN, G.mti, pre);
+        else mt_load5(a.mt + g * (int64_t)kMtN, G.mti, pre);
+      }
       bool moved = false, term = false;
       int ep_len = 0;
       if (valid) {
@@ -174,31 +192,16 @@ __global__ void __launch_bounds__(V::kBlock, kResidentThreads / V::kBlock) k_mai
           }
         }
       }
-      restart = term && a.auto_reset;
       // the deal that follows a play/discard -- also for a game that just ended:
       // the reference deals before it looks at IsTerminal (rl_env.py:357-361)
-      if (moved) {
-        if (V::kPrefill > 0 && n_pre > 0) {
-          while (needs_deal(v, G)) {
-            if (q_count(Q) > 0) {
-              deal_card(v, G, queue_pop(v, G, Q), a.spec.obs_type);
-            } else if (restart && G.deck_size >= kSafeDraw && q_pend(Q) < 15) {
-              // the game restarts anyway: only the two RNG words of the draw matter
-              queue_skip(G, Q);
-              deal_card(v, G, __ffsll((long long)G.deck) - 1, a.spec.obs_type);
-            } else {
-              break;
-            }
-          }
-          if (needs_deal(v, G)) {  // the queue is empty
-            if (!restart && (q_pend(Q) > 0 || G.deck_size >= kSafeDraw)) want_refill = true;
-            else direct = true;
-          }
-        } else {
-          direct = needs_deal(v, G);
-        }
-      }
+      if (moved) deal_loop(v, a.spec, G, false, g, a.mt, a.sampler_mode, pre, pend_cap);
       if (term && !a.auto_reset) G.done = 1;
+      restart = term && a.auto_reset;
+      want_flush = lazy && !restart && G.pend >= pend_cap - 1;
+#if HB_RESET_PREFETCH
+      if constexpr (!kJobs)
+        if (restart && a.spec.fast_reset) mt_prefetch_deal(a.mt + g * (int64_t)kMtN, G.mti, v.P() * v.H());
+#endif
 #if HB_EARLY_OUT
       // the step's results are final here (a re-deal does not touch them): write them
       // now instead of carrying three registers through phases B and C
@@ -226,53 +229,62 @@ __global__ void __launch_bounds__(V::kBlock, kResidentThreads / V::kBlock) k_mai
     }
     if (MODE != kModeObserve) {
       restarted = restart;
-      // ---- enqueue the RNG work
-      const bool want_job = (restart && a.spec.fast_reset && !direct) || want_refill;
-      const unsigned qm = __ballot_sync(kFull, want_job);
-      if (qm) {
-        int base = 0;
-        if (lane == 0) base = atomicAdd(&s_nq, __popc(qm));
-        base = __shfl_sync(kFull, base, 0);
-        slot = base + __popc(qm & ((1u << lane) - 1u));
-        if (want_job && slot < kQueueCap) {
-          job = restart ? 1 : 2;
-          const int npend = q_pend(Q);
-          int r0 = G.mti - 2 * npend;
-          r0 += r0 < 0 ? kMtN : 0;
-          const int PH = v.P() * v.H();
-          int nfresh, npeek, s0;
-          uint64_t deck0;
-          if (restart) {
-            nfresh = PH; s0 = v.deck_max(); deck0 = a.spec.full_deck;
-            npeek = n_pre;  // PrefillFor keeps the last peeked draw of a fresh deck safe
-          } else {
-            nfresh = 0; s0 = G.deck_size; deck0 = G.deck;
-            npeek = G.deck_size >= kSafeDraw ? min(n_pre, G.deck_size - (kSafeDraw - 1)) : 0;
-          }
-          s_q_tid[slot] = threadIdx.x;
-          s_q_meta[slot] = (uint32_t)r0 | ((uint32_t)npend << 10) | ((uint32_t)nfresh << 14) |
-                           ((uint32_t)npeek << 20) | ((uint32_t)s0 << 24) |
-                           (a.sampler_mode == 1 ? 0x80000000u : 0u);
-          s_q_deck[slot] = make_uint2((uint32_t)deck0, (uint32_t)(deck0 >> 32));
+      if constexpr (kJobs) {
+        // ---- enqueue the RNG work: re-deals of finished games, flushes of pending pairs
+        const bool want_job = (restart && a.spec.fast_reset) || want_flush;
+        const unsigned qm = __ballot_sync(kFull, want_job);
+        if (qm) {
+          int base = 0;
+          if (lane == 0) base = atomicAdd(&s_nq, __popc(qm));
+          base = __shfl_sync(kFull, base, 0);
+          slot = base + __popc(qm & ((1u << lane) - 1u));
+          if (want_job && slot < kQueueCap) {
+            job = restart ? 1 : 2;
+            int r0 = G.mti - 2 * G.pend;
+            r0 += r0 < 0 ? kMtN : 0;
+            const int nfresh = restart ? v.P() * v.H() : 0;
+            s_q_tid[slot] = threadIdx.x;
+            s_q_meta[slot] = (uint32_t)r0 | ((uint32_t)G.pend << 10) | ((uint32_t)nfresh << 14) |
+                             (a.sampler_mode == 1 ? 0x80000000u : 0u);
 #if HB_RESET_PREFETCH
-          // the job's lines: [r0, r0 + 2T] and, for the regenerated part, 397 slots ahead
-          mt_prefetch_span(x, r0, 2 * (npend + nfresh + npeek) + 1);
-          mt_prefetch_span(x, mt_wrap(r0 + kMtM), 2 * (npend + nfresh));
+            // the job's lines: [r0, r0 + 2T] and 397 slots ahead
+            mt_prefetch_span(a.mt + g * (int64_t)kMtN, r0, 2 * (G.pend + nfresh) + 1);
+            mt_prefetch_span(a.mt + g * (int64_t)kMtN, mt_wrap(r0 + kMtM), 2 * (G.pend + nfresh));
 #endif
+          }
         }
-      }
-      // random start player / tiny decks / queue overflow / the last cards of a deck: the
-      // general per-thread path, straight on the game's mt19937 block
-      const bool general_restart = restart && job == 0;
-      if (want_refill && job == 0) direct = true;
-      if (general_restart || direct) {
-        if (V::kPrefill > 0 && n_pre > 0) {
-          flush_pending(x, G.mti, Q);
-          if (general_restart) Q = 0;  // a dropped queue's words were never consumed
+        // random start player / tiny decks / job-queue overflow: the per-thread path,
+        // straight on the game's mt19937 block
+        if ((want_job || restart) && job == 0) {
+          if (lazy) flush_pending(a.mt + g * (int64_t)kMtN, G.mti, G.pend);
+          if (restart) {
+            Prefetch none;
+            none.at = -1;
+            deal_loop(v, a.spec, G, true, g, a.mt, a.sampler_mode, none);
+          }
         }
-        Prefetch none;
-        none.at = -1;
-        deal_loop(v, a.spec, G, general_restart, g, a.mt, a.sampler_mode, none);
+      } else {
+        // ---- serial path: finished games enqueue themselves
+        bool queued = restart && a.spec.fast_reset;
+        const unsigned qm = __ballot_sync(kFull, queued);
+        if (qm) {
+          int base = 0;
+          if (lane == 0) base = atomicAdd(&s_nq, __popc(qm));
+          base = __shfl_sync(kFull, base, 0);
+          slot = base + __popc(qm & ((1u << lane) - 1u));
+          if (queued && slot >= kQueueCap) queued = false;  // queue full: general path below
+          if (queued) {
+            job = 1;
+            s_q_tid[slot] = threadIdx.x;
+            s_q_meta[slot] = (uint32_t)G.mti;
+          }
+        }
+        // random start player / tiny decks / queue overflow: general per-thread path
+        if (restart && !queued) {
+          Prefetch none;
+          none.at = -1;
+          deal_loop(v, a.spec, G, true, g, a.mt, a.sampler_mode, none);
+        }
       }
     }
   }
@@ -281,55 +293,49 @@ __global__ void __launch_bounds__(V::kBlock, kResidentThreads / V::kBlock) k_mai
   if (MODE != kModeObserve) {
     __syncthreads();
     const int nq = s_nq < kQueueCap ? s_nq : kQueueCap;
+    if constexpr (kJobs) {
     if (nq > 0) {  // CTA-uniform
       // B1, one thread per (job, RNG word pair), kItems pairs per thread in flight at once:
-      //   pairs [0, npend)                     consumed earlier by queue cards: regenerate
-      //   pairs [npend, npend + nfresh)        the initial deal of a new game: draw + regenerate
-      //   pairs [npend + nfresh, T)            the next queue: draw only (words stay unconsumed)
-      // Draw d of a job has the known deck size s0 - d, so its index q_d = floor(u_d * size)
-      // does not depend on the earlier draws and is computed here, in parallel, for every draw
-      // of every job.  All loads come first, then a barrier, then the regenerated slots are
-      // stored (a pair's x[k+2] is the next pair's slot, so stores wait for every load).
-      // B2, one thread per job: the short serial chain deck -> q-th set bit -> deck over the
-      // job's indices in shared memory (jobs run side by side in the lanes of one warp).
+      //   pairs [0, npend)               taken earlier by in-game deals: regenerate
+      //   pairs [npend, npend + nfresh)  the initial deal of a new game: draw + regenerate
+      // Draw d of a fresh deck has the known size deck_max - d, so its index q_d =
+      // floor(u_d * size) does not depend on the earlier draws and is computed here, in
+      // parallel, for every draw of every job.  All loads come first, then a barrier, then
+      // the regenerated slots are stored (a pair's x[k+2] is the next pair's slot, so stores
+      // wait for every load).
+      // B2, one thread per re-deal job: the short serial chain deck -> q-th set bit -> deck
+      // over the job's indices in shared memory (jobs side by side in the lanes of a warp).
       const int PH = v.P() * v.H(), H = v.H();
-      const int tmax = PH + 2 * n_pre + 1;          // pair slots per job
-      const int chunk_jobs = (kItems * kBlock) / tmax;  // jobs per pass (>= 4 * 192 / 31)
+      const int tmax = PH + pend_cap;                   // pair slots per job (pend <= pend_cap)
+      const int chunk_jobs = (kItems * kBlock) / tmax;  // jobs per pass
       for (int e_base = 0; e_base < nq; e_base += chunk_jobs) {  // CTA-uniform
         const int n_jobs = min(chunk_jobs, nq - e_base);
         const int n_slots = n_jobs * tmax;
         uint32_t new0[kItems], new1[kItems];
-        bool store[kItems];
         uint32_t* xs[kItems];
 #pragma unroll
         for (int u = 0; u < kItems; ++u) {
           const int k = u * kBlock + threadIdx.x;
-          store[u] = false;
-          xs[u] = a.mt;
+          xs[u] = nullptr;
           new0[u] = new1[u] = 0u;
           if (k < n_slots) {
             const int ej = k / tmax, it = k - ej * tmax;
             const int e = e_base + ej;
             const uint32_t meta = s_q_meta[e];
-            const int r0 = meta & 1023, npend = (meta >> 10) & 15, nfresh = (meta >> 14) & 63,
-                      npeek = (meta >> 20) & 15, s0 = (meta >> 24) & 127;
-            const int d = it - npend;
-            if (it < npend + nfresh + npeek) {
+            const int r0 = meta & 1023, npend = (meta >> 10) & 15, nfresh = (meta >> 14) & 63;
+            if (it < npend + nfresh) {
               uint32_t* x = a.mt + (cta0 + s_q_tid[e]) * (int64_t)kMtN;
               int at = r0 + 2 * it;
               at -= at >= kMtN ? kMtN : 0;
-              const uint32_t wa = __ldcg(x + at), wb = __ldcg(x + mt_wrap(at + 1));
-              if (d < nfresh) {  // regenerated now
-                const uint32_t wc = __ldcg(x + mt_wrap(at + 2)), wp = __ldcg(x + mt_wrap(at + kMtM)),
-                               wq = __ldcg(x + mt_wrap(at + kMtM + 1));
-                new0[u] = mt_next_block_word(wa, wb, wp);
-                new1[u] = mt_next_block_word(wb, wc, wq);
-                store[u] = true;
-                xs[u] = x + at;
-              }
+              Prefetch f;
+              mt_load5(x, at, f);
+              new0[u] = mt_next_block_word(f.a, f.b, f.p);
+              new1[u] = mt_next_block_word(f.b, f.c, f.q);
+              xs[u] = x + at;
+              const int d = it - npend;
               if (d >= 0) {
                 bool amb = false;
-                const int q = draw_index(s0 - d, mt_temper(wa), mt_temper(wb), amb);
+                const int q = draw_index(v.deck_max() - d, mt_temper(f.a), mt_temper(f.b), amb);
                 s_qb[ej * tmax + d] = (uint8_t)q;
                 // a job with a draw that needs the exact fp64 sampler is left untouched here and
                 // redone by its own thread on the general path (phase C)
@@ -341,52 +347,120 @@ __global__ void __launch_bounds__(V::kBlock, kResidentThreads / V::kBlock) k_mai
         __syncthreads();
 #pragma unroll
         for (int u = 0; u < kItems; ++u) {
-          const int k = u * kBlock + threadIdx.x;
-          if (store[u]) {
+          if (xs[u] != nullptr) {
+            const int k = u * kBlock + threadIdx.x;
             const int e = e_base + k / tmax;
             if (!(s_q_meta[e] >> 31)) {
-              const int at = (int)(xs[u] - (a.mt + (cta0 + s_q_tid[e]) * (int64_t)kMtN));
+              // (without a random start player the take index is even: a pair never wraps)
               __stcg(xs[u], new0[u]);
-              __stcg(xs[u] + (at + 1 >= kMtN ? 1 - kMtN : 1), new1[u]);
+              __stcg(xs[u] + 1, new1[u]);
             }
           }
         }
         if ((int)threadIdx.x < n_jobs) {
           const int e = e_base + threadIdx.x;
           const uint32_t meta = s_q_meta[e];
-          if (!(meta >> 31)) {
-            const int nfresh = (meta >> 14) & 63, npeek = (meta >> 20) & 15;
-            const uint2 dk = s_q_deck[e];
-            uint64_t deck = (uint64_t)dk.x | ((uint64_t)dk.y << 32), deck_fresh = deck, qacc = 0;
+          const int nfresh = (meta >> 14) & 63;
+          if (!(meta >> 31) && nfresh > 0) {
+            uint64_t deck = a.spec.full_deck;
             const uint8_t* qb = s_qb + threadIdx.x * tmax;
             uint32_t hand = 0;
             int pl = 0, slot_i = 0;
 #pragma unroll 1
-            for (int d = 0; d < nfresh + npeek; ++d) {
+            for (int d = 0; d < nfresh; ++d) {
               const int pos = select64(deck, (int)qb[d]);
               deck &= ~(1ull << pos);
               int color, rank;
               card_of_position(v, pos, color, rank);
-              if (d < nfresh) {
-                hand |= (uint32_t)(color | (rank << 3)) << (6 * slot_i);
-                if (++slot_i == H) {  // player 0's hand first, then player 1's, ... (PlayerToDeal)
-                  s_res[e].cards[pl++] = hand;
-                  hand = 0;
-                  slot_i = 0;
-                }
-                deck_fresh = deck;
-              } else {
-                qacc |= (uint64_t)(color * v.R() + rank) << (5 * (d - nfresh));
+              hand |= (uint32_t)(color | (rank << 3)) << (6 * slot_i);
+              if (++slot_i == H) {  // player 0's hand first, then player 1's, ... (PlayerToDeal)
+                s_res[e].cards[pl++] = hand;
+                hand = 0;
+                slot_i = 0;
               }
             }
-            s_res[e].deck_lo = (uint32_t)deck_fresh;
-            s_res[e].deck_hi = (uint32_t)(deck_fresh >> 32);
-            s_res[e].q_lo = (uint32_t)qacc;
-            s_res[e].q_hi = (uint32_t)(qacc >> 32) | ((uint32_t)npeek << 24);  // count at bit 56, nothing pending
+            s_res[e].deck_lo = (uint32_t)deck;
+            s_res[e].deck_hi = (uint32_t)(deck >> 32);
           }
         }
         if (e_base + chunk_jobs < nq) __syncthreads();  // s_qb is reused by the next pass
       }
+    }
+    } else {
+    if (nq > 0) {  // CTA-uniform
+      // B1: one thread per (queued game, word pair) takes the pair from the game's
+      // stream: all loads first, barrier, then the regenerated slots are stored
+      // (a pair's x[k+2] is the next pair's slot, so stores wait for every load)
+      uint32_t* s_words = smem + (size_t)kWarps * a.warp_smem_words;
+      const int pairs = v.P() * v.H();
+      const int cap = kQueueCap * pairs;
+      for (int k0 = 0; k0 < nq * pairs; k0 += kBlock) {  // CTA-uniform trip count
+        const int k = k0 + threadIdx.x;
+        const bool act = k < nq * pairs;
+        Prefetch f;
+        uint32_t* x = a.mt;
+        int at = 0;
+        if (act) {
+          const int e = k / pairs, r = k - e * pairs;
+          x = a.mt + (cta0 + s_q_tid[e]) * (int64_t)kMtN;
+          at = mt_wrap((int)s_q_meta[e] + 2 * r);
+          mt_load5(x, at, f);
+          const uint32_t lo = mt_temper(f.a), hi = mt_temper(f.b);
+          bool amb = false;
+          const int q = draw_index(v.deck_max() - r, lo, hi, amb);  // deck size of draw r is known
+          s_words[k] = (uint32_t)q | ((uint32_t)amb << 8);
+          s_words[cap + k] = lo;
+          s_words[2 * cap + k] = hi;
+        }
+        __syncthreads();
+        if (act) {
+          __stcg(x + at, mt_next_block_word(f.a, f.b, f.p));
+          __stcg(x + mt_wrap(at + 1), mt_next_block_word(f.b, f.c, f.q));
+        }
+      }
+      __syncthreads();
+      constexpr bool kChain = HB_SERIAL_B2 == 1 || (HB_SERIAL_B2 == 2 && V::kP * V::kH >= 10);
+      if (kChain) {
+      // B2: one thread per queued game runs the select chain on the precomputed indices
+      for (int i = threadIdx.x; i < nq; i += kBlock)
+        reset_draw(v, a.spec, s_words + i * pairs, s_words + cap + i * pairs,
+                   s_words + 2 * cap + i * pairs, a.sampler_mode, s_res[i]);
+      } else {
+      // B2: the draw indices are all in shared memory, so the cards follow without a serial
+      // chain (Lehmer decode as above, through shared memory instead of shuffles): one thread
+      // per (game, draw) walks back through the game's earlier indices, then ORs its card into
+      // the game's hands and clears its deck bit.  A game with a draw that needs the exact
+      // fp64 sampler (or the exact-only test mode) is redone serially afterwards.
+      for (int i = threadIdx.x; i < nq; i += kBlock) {
+#pragma unroll
+        for (int p = 0; p < kMaxPlayers; ++p) s_res[i].cards[p] = 0;
+        s_res[i].deck_lo = (uint32_t)a.spec.full_deck;
+        s_res[i].deck_hi = (uint32_t)(a.spec.full_deck >> 32);
+      }
+      __syncthreads();
+      for (int k = threadIdx.x; k < nq * pairs; k += kBlock) {
+        const int e = k / pairs, r = k - e * pairs;
+        const uint32_t* qa = s_words + e * pairs;
+        int idx = (int)(qa[r] & 0xffu);
+        for (int j = r - 1; j >= 0; --j) idx += ((int)(qa[j] & 0xffu) <= idx) ? 1 : 0;
+        int color, rank;
+        card_of_position(v, idx, color, rank);
+        const int pl = r / v.H(), slot_i = r - pl * v.H();
+        atomicOr(&s_res[e].cards[pl], (uint32_t)(color | (rank << 3)) << (6 * slot_i));
+        if (idx < 32) atomicAnd(&s_res[e].deck_lo, ~(1u << idx));
+        else atomicAnd(&s_res[e].deck_hi, ~(1u << (idx - 32)));
+      }
+      __syncthreads();
+      for (int i = threadIdx.x; i < nq; i += kBlock) {
+        bool slow = a.sampler_mode == 1;
+        if (a.sampler_mode != 2)
+          for (int r = 0; r < pairs; ++r) slow |= (s_words[i * pairs + r] >> 8) != 0;
+        if (slow)
+          reset_draw(v, a.spec, s_words + i * pairs, s_words + cap + i * pairs,
+                     s_words + 2 * cap + i * pairs, a.sampler_mode, s_res[i]);
+      }
+      }
+    }
     }
     __syncthreads();
     if (MODE == kModeStep && a.stats && threadIdx.x < kNumStats && s_stats[threadIdx.x] != 0)
@@ -395,27 +469,24 @@ __global__ void __launch_bounds__(V::kBlock, kResidentThreads / V::kBlock) k_mai
   if (!tile_live) return;
 
   // ---------------------------------------------------------------- phase C
-  if (job != 0) {
-    const bool slow = (s_q_meta[slot] >> 31) != 0u;
-    bool general = slow;
-    if (!slow) {
-      Q = (uint64_t)s_res[slot].q_lo | ((uint64_t)s_res[slot].q_hi << 32);
-      if (job == 1) {
-        reset_apply(v, a.spec, G, s_res[slot]);
+  if constexpr (kJobs) {
+    if (job != 0) {
+      if (!(s_q_meta[slot] >> 31)) {
+        G.pend = 0;  // the job regenerated the pending slots
+        if (job == 1) reset_apply(v, a.spec, G, s_res[slot]);
       } else {
-        // the refilled queue serves the deal this game was waiting for
-        while (needs_deal(v, G) && q_count(Q) > 0) deal_card(v, G, queue_pop(v, G, Q), a.spec.obs_type);
-        general = needs_deal(v, G);  // the last cards of the deck: no queue any more
+        // a draw of this job needs the exact sampler (or the exact-only test mode): nothing was
+        // stored for it; redo it on the per-thread path
+        flush_pending(a.mt + g * (int64_t)kMtN, G.mti, G.pend);
+        if (job == 1) {
+          Prefetch none;
+          none.at = -1;
+          deal_loop(v, a.spec, G, true, g, a.mt, a.sampler_mode, none);
+        }
       }
     }
-    if (general) {
-      uint32_t* const x = a.mt + g * (int64_t)kMtN;
-      flush_pending(x, G.mti, Q);
-      if (job == 1) Q = 0;
-      Prefetch none;
-      none.at = -1;
-      deal_loop(v, a.spec, G, job == 1, g, a.mt, a.sampler_mode, none);
-    }
+  } else {
+    if (job != 0) reset_apply(v, a.spec, G, s_res[slot]);
   }
   if (valid) {
 #if !HB_EARLY_OUT
@@ -428,7 +499,6 @@ __global__ void __launch_bounds__(V::kBlock, kResidentThreads / V::kBlock) k_mai
     if (a.cur_player) a.cur_player[g] = G.cur;
     if (MODE != kModeObserve) {
       store_game(a.state, a.N, g, v, G);
-      if (V::kPrefill > 0 && n_pre > 0) __stcg(a.queue + g, make_uint2((uint32_t)Q, (uint32_t)(Q >> 32)));
     }
     if (MODE != kModeObserve && a.hist != nullptr) {
       // move history for the rule-based agents: a new game starts with none
@@ -579,14 +649,6 @@ __global__ void k_pack(KArgs a, const int32_t* in, const int32_t* extra) {
   const DView v(a.spec);
   Game G;
   load_game(a.state, a.N, g, v, G);
-  if (a.spec.prefill > 0) {
-    // the injected deck invalidates the pre-drawn cards: their words were never consumed, the
-    // pending slots are regenerated, and the game goes on without a queue until its next refill
-    const uint2 q2 = a.queue[g];
-    uint64_t Q = (uint64_t)q2.x | ((uint64_t)q2.y << 32);
-    flush_pending(a.mt + g * (int64_t)kMtN, G.mti, Q);
-    a.queue[g] = make_uint2(0u, 0u);
-  }
   const int32_t* d = in + g * (int64_t)kDumpLen;
   const int C = a.spec.C, R = a.spec.R;
   G.cur = d[0] < 0 ? 0 : d[0]; G.info = d[1]; G.life = d[2]; G.deck_size = d[3];
@@ -681,7 +743,6 @@ struct Batch {
   int64_t N = 0;
   int ncols = 0;
   uint4* state = nullptr;
-  uint2* queue = nullptr;
   uint32_t* mt = nullptr;
   unsigned long long* stats = nullptr;      // active stats buffer
   unsigned long long* own_stats = nullptr;  // library-owned fallback
@@ -761,7 +822,6 @@ hb::KArgs BaseArgs(const Batch* b) {
   std::memset(&a, 0, sizeof(a));
   a.spec = b->spec;
   a.state = b->state;
-  a.queue = b->queue;
   a.mt = b->mt;
   a.N = b->N;
   a.g_begin = 0;
@@ -777,11 +837,13 @@ hb::KArgs BaseArgs(const Batch* b) {
   return a;
 }
 
-// Dynamic shared memory of k_main<V>: one packed-stream area per warp and -- for the
-// launches that write network-input rows -- the 4 KB element table behind them.
+// Dynamic shared memory of k_main<V>: one packed-stream area per warp, the (index, lo, hi)
+// table of the serial re-deal path, and -- for the launches that write network-input rows
+// -- the 4 KB element table behind them.
 template <class V>
 size_t ViewSmemWords(const Batch* b) {
-  const size_t words = (size_t)(V::kBlock / 32) * b->warp_smem_words;
+  const size_t words = (size_t)(V::kBlock / 32) * b->warp_smem_words +
+                       (V::kJobs ? 0 : (size_t)hb::serial_queue_cap(V::kBlock, V::kP * V::kH) * 3 * b->spec.P * b->spec.H);
   return (words + 3) & ~(size_t)3;
 }
 
@@ -896,7 +958,7 @@ int NewBatch(pyhanabi_batch_t* out, int list_length, const char** param_list, in
   if (!guard.ok) { delete b; return Fail("NewBatch: cudaSetDevice failed"); }
   int32_t* d_seeds = nullptr;
   auto cleanup = [&]() {
-    cudaFree(b->state); cudaFree(b->queue); cudaFree(b->mt); cudaFree(b->own_stats); cudaFree(d_seeds);
+    cudaFree(b->state); cudaFree(b->mt); cudaFree(b->own_stats); cudaFree(d_seeds);
     delete b;
   };
 #define HB_TRY(expr)                                                           \
@@ -905,8 +967,6 @@ int NewBatch(pyhanabi_batch_t* out, int list_length, const char** param_list, in
     if (e__ != cudaSuccess) { cleanup(); return CudaFail("NewBatch: " #expr, e__); } \
   } while (0)
   HB_TRY(cudaMalloc(&b->state, sizeof(uint4) * (size_t)b->ncols * (size_t)b->N));
-  HB_TRY(cudaMalloc(&b->queue, sizeof(uint2) * (size_t)b->N));
-  HB_TRY(cudaMemset(b->queue, 0, sizeof(uint2) * (size_t)b->N));
   HB_TRY(cudaMalloc(&b->mt, sizeof(uint32_t) * (size_t)hb::kMtN * (size_t)b->N));
   HB_TRY(cudaMalloc(&b->own_stats, sizeof(unsigned long long) * hb::kNumStats));
   HB_TRY(cudaMemset(b->own_stats, 0, sizeof(unsigned long long) * hb::kNumStats));
@@ -945,7 +1005,6 @@ void DeleteBatch(pyhanabi_batch_t* h) {
   cudaFree(b->d_actions); cudaFree(b->d_rewards); cudaFree(b->d_scores); cudaFree(b->d_cur);
   cudaFree(b->d_dones); cudaFree(b->d_obs); cudaFree(b->d_mask);
   cudaFree(b->state);
-  cudaFree(b->queue);
   cudaFree(b->mt);
   cudaFree(b->own_stats);
   cudaFree(b->hist);
@@ -1381,7 +1440,7 @@ int BatchObservePacked(pyhanabi_batch_t* h, int observer, uint32_t* obs_bits, ui
 
 // Checkpoint blob: a 128-byte header (magic, layout version, the complete rule set, the
 // number of games and state columns, whether the move-history ring is on), then the packed
-// state columns, the deal queue words, every game's mt19937 block, the history ring (if on)
+// state columns, every game's mt19937 block, the history ring (if on)
 // and the 32 statistics counters.
 namespace {
 constexpr int64_t kBlobMagic = 0x4842323030ll, kBlobVersion = 2;
@@ -1389,7 +1448,7 @@ constexpr int kBlobHeader = 16;  // int64 words
 void FillBlobHeader(const Batch* b, int64_t* hd) {
   const hb::Spec& s = b->spec;
   const int64_t v[kBlobHeader] = {kBlobMagic, kBlobVersion, b->N, b->ncols, s.P, s.C, s.R, s.H, s.IT, s.LT,
-                                  s.obs_type, s.random_start, s.prefill, b->hist ? 1 : 0, s.obs_size, s.max_moves};
+                                  s.obs_type, s.random_start, s.pend_cap, b->hist ? 1 : 0, s.obs_size, s.max_moves};
   std::memcpy(hd, v, sizeof(v));
 }
 }  // namespace
@@ -1398,7 +1457,7 @@ int64_t BatchStateBytes(pyhanabi_batch_t* h) {
   if (!h || !h->batch) return -1;
   Batch* b = AsBatch(h->batch);
   return (int64_t)sizeof(int64_t) * kBlobHeader + (int64_t)sizeof(uint4) * b->ncols * b->N +
-         (int64_t)sizeof(uint2) * b->N + (int64_t)sizeof(uint32_t) * hb::kMtN * b->N +
+         (int64_t)sizeof(uint32_t) * hb::kMtN * b->N +
          (b->hist ? (int64_t)sizeof(uint4) * b->N : 0) + (int64_t)sizeof(int64_t) * hb::kNumStats;
 }
 
@@ -1411,10 +1470,9 @@ int BatchGetState(pyhanabi_batch_t* h, void* host_blob, int64_t nbytes) {
   std::memcpy(host_blob, header, sizeof(header));
   char* p = static_cast<char*>(host_blob) + sizeof(header);
   const size_t N = (size_t)b->N;
-  const size_t sb = sizeof(uint4) * (size_t)b->ncols * N, qb = sizeof(uint2) * N,
+  const size_t sb = sizeof(uint4) * (size_t)b->ncols * N, qb = 0,
                mb = sizeof(uint32_t) * (size_t)hb::kMtN * N, hbytes = b->hist ? sizeof(uint4) * N : 0;
   HB_CUDA(cudaMemcpy(p, b->state, sb, cudaMemcpyDeviceToHost));
-  HB_CUDA(cudaMemcpy(p + sb, b->queue, qb, cudaMemcpyDeviceToHost));
   HB_CUDA(cudaMemcpy(p + sb + qb, b->mt, mb, cudaMemcpyDeviceToHost));
   if (hbytes) HB_CUDA(cudaMemcpy(p + sb + qb + mb, b->hist, hbytes, cudaMemcpyDeviceToHost));
   HB_CUDA(cudaMemcpy(p + sb + qb + mb + hbytes, b->stats, sizeof(int64_t) * hb::kNumStats, cudaMemcpyDeviceToHost));
@@ -1433,10 +1491,9 @@ int BatchSetState(pyhanabi_batch_t* h, const void* host_blob, int64_t nbytes) {
   HB_CUDA(cudaDeviceSynchronize());
   const char* p = static_cast<const char*>(host_blob) + sizeof(header);
   const size_t N = (size_t)b->N;
-  const size_t sb = sizeof(uint4) * (size_t)b->ncols * N, qb = sizeof(uint2) * N,
+  const size_t sb = sizeof(uint4) * (size_t)b->ncols * N, qb = 0,
                mb = sizeof(uint32_t) * (size_t)hb::kMtN * N, hbytes = b->hist ? sizeof(uint4) * N : 0;
   HB_CUDA(cudaMemcpy(b->state, p, sb, cudaMemcpyHostToDevice));
-  HB_CUDA(cudaMemcpy(b->queue, p + sb, qb, cudaMemcpyHostToDevice));
   HB_CUDA(cudaMemcpy(b->mt, p + sb + qb, mb, cudaMemcpyHostToDevice));
   if (hbytes) HB_CUDA(cudaMemcpy(b->hist, p + sb + qb + mb, hbytes, cudaMemcpyHostToDevice));
   HB_CUDA(cudaMemcpy(b->stats, p + sb + qb + mb + hbytes, sizeof(int64_t) * hb::kNumStats, cudaMemcpyHostToDevice));

@@ -33,6 +33,9 @@ constexpr unsigned kFull = 0xffffffffu;
 // Threads (= games) per CTA, measured per rule set with two launches in flight per GPU
 // (768 resident threads per SM in every case): 256 where the re-deal is the parallel
 // Lehmer decode (initial deals of 12+ cards), 192 for the short serial re-deals.
+#ifndef HB_JOBS_MIN_CARDS
+#define HB_JOBS_MIN_CARDS 12
+#endif
 #ifdef HB_BLOCK
 constexpr int block_for_deal(int) { return HB_BLOCK; }
 #else
@@ -44,8 +47,12 @@ struct SView {
   static constexpr bool kStatic = true;
   static constexpr int kP = P_, kH = H_, kC = C_, kR = R_;
   static constexpr int kBlock = block_for_deal(P_ * H_);
-  // longest deal queue this shape can have (0: the queue code is compiled out)
-  static constexpr int kPrefill = PrefillFor(P_, H_, (R_ == 1 ? 3 : 2 * R_) * C_, 0);
+  // Re-deal machinery, measured per rule set (profiles/r02i_ab.log): initial deals of 12+ cards
+  // go through the job path (one thread per RNG word pair over all jobs of the CTA, serial
+  // chain per job, lazy slot regeneration); deals of up to 10 cards keep round 1's serial path.
+  static constexpr bool kJobs = P_ * H_ >= HB_JOBS_MIN_CARDS;
+  // pending-pair cap of this shape without a random start player (0: lazy regeneration off)
+  static constexpr int kPendCap = kJobs ? PendCapFor(P_, H_, (R_ == 1 ? 3 : 2 * R_) * C_, 0) : 0;
   HB_DEV explicit SView(const Spec&) {}
   HB_DEV constexpr int P() const { return P_; }
   HB_DEV constexpr int H() const { return H_; }
@@ -62,7 +69,8 @@ struct DView {
   static constexpr bool kStatic = false;
   static constexpr int kP = kMaxPlayers, kH = kMaxHand, kC = kMaxColors, kR = kMaxRanks;
   static constexpr int kBlock = block_for_deal(kMaxPlayers * kMaxHand);
-  static constexpr int kPrefill = kMaxPrefill;
+  static constexpr bool kJobs = true;
+  static constexpr int kPendCap = HB_LAZY_REGEN ? kMaxPend : 0;
   const Spec& s;
   HB_DEV explicit DView(const Spec& sp) : s(sp) {}
   HB_DEV int P() const { return s.P; }
@@ -100,6 +108,7 @@ struct Game {
   uint32_t fw;    // 3 bits per colour
   int info, life, cur, turns, done, err;
   int deck_size, mti, eplen;
+  int pend;  // RNG word pairs taken but not yet regenerated (they sit right below mti)
   uint32_t last;
   uint32_t spare;
 };
@@ -151,7 +160,8 @@ HB_DEV void st_state(uint4* p, uint4 v) {
 //   column P   : x = deck lo   y = deck hi (18 bits) | X[24,32) << 18 | L[22,28) << 26
 //                z = discard lo   w = discard hi (18 bits) | L[0,14) << 18
 // with X = the general layout's word x (fireworks ... done, error: the error flag is bit 25 of
-// column P's y), m = mt19937 index | episode length << 10, L = last-action record.
+// column P's y), m = mt19937 index | episode length (8 bits, saturating) << 10 | pending pairs << 18,
+// L = last-action record.
 #ifndef HB_COMPACT_STATE
 #define HB_COMPACT_STATE 1
 #endif
@@ -186,7 +196,8 @@ HB_DEV void load_game(const uint4* __restrict__ st, int64_t N, int64_t g, V v, G
     const uint32_t m = (c0.y >> 25) | ((c0.z >> 25) << 7) | ((c1.y >> 25) << 14) | (((c0.x >> 30) & 1u) << 21);
     G.deck_size = __popcll(G.deck);
     G.mti = (int)(m & 1023u);
-    G.eplen = (int)(m >> 10);
+    G.eplen = (int)((m >> 10) & 255u);
+    G.pend = V::kPendCap > 0 ? (int)(m >> 18) : 0;  // (views without lazy regeneration never have pending pairs)
     G.last = (c2.w >> 18) | ((c1.z >> 25) << 14) | (((c1.x >> 30) & 1u) << 21) | ((c2.y >> 26) << 22);
     G.spare = 0;
     return;
@@ -213,7 +224,8 @@ HB_DEV void load_game(const uint4* __restrict__ st, int64_t N, int64_t g, V v, G
   G.err = (b.x >> 31) & 1;
   G.deck_size = b.y & 63;
   G.mti = (b.y >> 6) & 1023;
-  G.eplen = (b.y >> 16) & 4095;
+  G.eplen = (b.y >> 16) & 255;
+  G.pend = (b.y >> 28) & 15;
   G.last = b.z;
   G.spare = b.w;
 }
@@ -224,7 +236,8 @@ HB_DEV void store_game(uint4* __restrict__ st, int64_t N, int64_t g, V v, const 
     const uint32_t X = G.fw | ((uint32_t)G.info << 15) | ((uint32_t)G.life << 20) |
                        ((uint32_t)G.cur << 24) | ((uint32_t)G.turns << 27) | ((uint32_t)G.done << 30) |
                        ((uint32_t)G.err << 31);
-    const uint32_t m = (uint32_t)G.mti | ((uint32_t)(G.eplen > 4095 ? 4095 : G.eplen) << 10);
+    const uint32_t m = (uint32_t)G.mti | ((uint32_t)(G.eplen > 255 ? 255 : G.eplen) << 10) |
+                       (V::kPendCap > 0 ? (uint32_t)G.pend << 18 : 0u);
     const uint32_t L = G.last & 0xfffffffu;
 #pragma unroll
     for (int p = 0; p < V::kP; ++p) {
@@ -255,7 +268,7 @@ HB_DEV void store_game(uint4* __restrict__ st, int64_t N, int64_t g, V v, const 
                ((uint32_t)G.cur << 24) | ((uint32_t)G.turns << 27) | ((uint32_t)G.done << 30) |
                ((uint32_t)G.err << 31);
   uint32_t y = (uint32_t)G.deck_size | ((uint32_t)G.mti << 6) |
-               ((uint32_t)(G.eplen > 4095 ? 4095 : G.eplen) << 16);
+               ((uint32_t)(G.eplen > 255 ? 255 : G.eplen) << 16) | ((uint32_t)G.pend << 28);
   st_state(st + (int64_t)(v.P() + 1) * N + g, make_uint4(x, y, G.last, G.spare));
 }
 
@@ -365,47 +378,27 @@ HB_DEV uint32_t mt_take1(uint32_t* x, int& k) {
   return mt_temper(a);
 }
 
-// ------------------------------------------------------------ deal queue
-// Per game one 64-bit queue word (its own column, 8 bytes per game):
-//   bits [0,55)   up to 11 pre-drawn cards, 5-bit type ids (colour * R + rank), next card lowest
-//   bits [56,60)  number of cards in the queue
-//   bits [60,64)  pending pairs: RNG word pairs already consumed by dealt cards whose slots
-//                 have not been regenerated yet (they sit right below the take index G.mti)
-// The queue's cards were drawn from the word pairs at G.mti, G.mti + 2, ... given the deck as
-// it is; those words count as consumed only when their card is dealt, so a game that ends
-// early leaves them to the next episode exactly as the reference's single stream does
-// (one std::mt19937 per HanabiGame, hanabi_game.h:114).  Deferred regeneration keeps the
-// in-place mt19937 scheme valid as long as fewer than 227 words are pending (slot k's
-// regeneration needs slot k - 227 already regenerated): at most 2 * 15 here.
-HB_DEV int q_count(uint64_t Q) { return (int)(Q >> 56) & 15; }
-HB_DEV int q_pend(uint64_t Q) { return (int)(Q >> 60) & 15; }
-HB_DEV uint64_t q_make(uint64_t cards, int count, int pend) {
-  return cards | ((uint64_t)count << 56) | ((uint64_t)pend << 60);
+// ------------------------------------------------------- lazy regeneration
+// A take that only reads: outputs k and k+1 (tempered), the two slots stay as they are and
+// count as pending (G.pend) until a job or flush_pending regenerates them, in stream order.
+HB_DEV void mt_load2(const uint32_t* x, int k, Prefetch& f) {
+  f.a = __ldcg(x + k);
+  f.b = __ldcg(x + mt_wrap(k + 1));
+  f.at = k;
 }
-
-// Takes the next card off the queue: returns its deck bit position (an instance of that
-// type that is still in the deck) and accounts for the two RNG words it consumes.
-template <class V>
-HB_DEV int queue_pop(V v, Game& G, uint64_t& Q) {
-  const int t = (int)(Q & 31u);
-  Q = q_make((Q & ((1ull << 55) - 1ull)) >> 5, q_count(Q) - 1, q_pend(Q) + 1);
-  G.mti = mt_wrap(G.mti + 2);
-  const int color = t / v.R(), rank = t - color * v.R();
-  const int off = color * v.per_color() + DiscardRankOffset(rank);
-  const uint32_t block = (uint32_t)(G.deck >> off) & 7u & ((1u << InstancesOfRank(v.R(), rank)) - 1u);
-  return off + __ffs((int)block) - 1;
-}
-
-// One more consumed pair whose card does not matter (the game is about to restart).
-HB_DEV void queue_skip(Game& G, uint64_t& Q) {
-  Q += 1ull << 60;
-  G.mti = mt_wrap(G.mti + 2);
+HB_DEV void mt_take2_lazy(const uint32_t* x, int& k, uint32_t& w0, uint32_t& w1, Prefetch& pre) {
+  Prefetch f;
+  if (pre.at == k) { f = pre; pre.at = -1; }
+  else mt_load2(x, k, f);
+  w0 = mt_temper(f.a);
+  w1 = mt_temper(f.b);
+  k = mt_wrap(k + 2);
 }
 
 // Regenerates the pending slots one after the other (rare paths only: state injection,
-// the last cards of a deck, queue overflow); afterwards every slot below G.mti is regenerated.
-HB_DEV void flush_pending(uint32_t* x, int mti, uint64_t& Q) {
-  const int pend = q_pend(Q);
+// job-queue overflow, draws that need the exact sampler); afterwards every slot below mti
+// is regenerated.
+HB_DEV void flush_pending(uint32_t* x, int mti, int& pend) {
   int at = mti - 2 * pend;
   at += at < 0 ? kMtN : 0;
   for (int i = 0; i < pend; ++i) {
@@ -415,7 +408,7 @@ HB_DEV void flush_pending(uint32_t* x, int mti, uint64_t& Q) {
     __stcg(x + mt_wrap(at + 1), mt_next_block_word(f.b, f.c, f.q));
     at = mt_wrap(at + 2);
   }
-  Q &= ~(15ull << 60);
+  pend = 0;
 }
 
 // ------------------------------------------------------------- deal sampling
@@ -750,9 +743,12 @@ HB_DEV void init_fresh(V v, const Spec& spec, Game& G, int start_player) {
 // at IsTerminal, rl_env.py:357-361), then a new game starts on the same RNG
 // stream (one std::mt19937 per HanabiGame, hanabi_game.h:114) and gets its P*H
 // cards.  Purely per-thread.
+// `lazy_cap` > 0: takes only read their words (pending regeneration, see above) while the
+// game carries fewer than lazy_cap pending pairs; a restart always regenerates at once
+// (callers flush first).
 template <class V>
 HB_DEV void deal_loop(V v, const Spec& spec, Game& G, bool restart, int64_t g, uint32_t* mt_all,
-                      int sampler_mode, Prefetch& pre) {
+                      int sampler_mode, Prefetch& pre, int lazy_cap = 0) {
   uint32_t* x = mt_all + g * (int64_t)kMtN;
   for (;;) {
     bool need = needs_deal(v, G);
@@ -772,7 +768,13 @@ HB_DEV void deal_loop(V v, const Spec& spec, Game& G, bool restart, int64_t g, u
     int pos;
     if (deck_types(spec, G.deck) >= 2) {
       uint32_t lo, hi;
-      mt_take2(x, G.mti, lo, hi, pre);
+      if (V::kPendCap > 0 && G.pend < lazy_cap) {
+        mt_take2_lazy(x, G.mti, lo, hi, pre);
+        G.pend += 1;
+      } else {
+        if (V::kPendCap > 0 && G.pend > 0) flush_pending(x, G.mti, G.pend);  // slots regenerate in stream order
+        mt_take2(x, G.mti, lo, hi, pre);
+      }
       bool amb = false;
       pos = pick_fast(G.deck, G.deck_size, lo, hi, amb);
       if (sampler_mode == 1 || (amb && sampler_mode != 2))
@@ -784,17 +786,49 @@ HB_DEV void deal_loop(V v, const Spec& spec, Game& G, bool restart, int64_t g, u
   }
 }
 
-// ---- (re-)deal jobs, compacted over the CTA --------------------------------
+// ---- re-deal / flush jobs, compacted over the CTA ----------------------------
 // A finished game that qualifies (spec.fast_reset: no random start player, every draw of the
-// initial deal is a >= 2-type draw) and a running game whose deal queue ran dry enqueue a JOB
-// in shared memory; after a CTA barrier the warps work the jobs off with one lane per RNG word
-// pair (k_main, phase B).  The result of a job:
+// initial deal is a >= 2-type draw) and a running game whose pending pairs reach the cap
+// enqueue a JOB in shared memory; after a CTA barrier all threads work the jobs off, one
+// thread per RNG word pair (k_main, phase B).  The result of a re-deal job:
 struct JobResult {
-  uint32_t cards[kMaxPlayers];  // the new hands (reset jobs)
-  uint32_t deck_lo, deck_hi;    // deck bitmap after the initial deal (reset jobs)
-  uint32_t q_lo, q_hi;          // the game's new queue word
+  uint32_t cards[kMaxPlayers];  // the new hands
+  uint32_t deck_lo, deck_hi;    // deck bitmap after the initial deal
 };
 typedef JobResult ResetResult;
+
+// Draws the initial deal of one game.  Draw r (deck size deck_max - r) comes with
+// its precomputed index qa[r] = floor(u_r * size) | ambiguous << 8 and its tempered
+// RNG words lo[r], hi[r] (only read for the rare exact re-draw), all in shared
+// memory.  The only serial dependency left is deck -> select -> deck.  Player 0's
+// hand is filled first, then player 1's, ... (PlayerToDeal, hanabi_state.cc:157-164).
+template <class V>
+HB_DEV void reset_draw(V v, const Spec& spec, const uint32_t* qa, const uint32_t* lo,
+                       const uint32_t* hi, int sampler_mode, ResetResult& out) {
+  uint64_t deck = spec.full_deck;
+  int n = v.deck_max();
+  const int H = v.H(), total = v.P() * H;
+#pragma unroll
+  for (int p = 0; p < kMaxPlayers; ++p) out.cards[p] = 0;
+  int p = 0, i = 0;
+#pragma unroll 1
+  for (int r = 0; r < total; ++r) {
+    const uint32_t w = qa[r];
+    int pos = select64(deck, (int)(w & 0xffu));
+    if (sampler_mode == 1 || ((w >> 8) && sampler_mode != 2))
+      pos = pick_exact(v, deck, n, lo[r], hi[r]);
+    int color, rank;
+    card_of_position(v, pos, color, rank);
+    const uint32_t card = (uint32_t)(color | (rank << 3)) << (6 * i);
+#pragma unroll
+    for (int k = 0; k < V::kP; ++k) out.cards[k] |= (k == p) ? card : 0u;
+    deck &= ~(1ull << pos);
+    --n;
+    if (++i == H) { i = 0; ++p; }
+  }
+  out.deck_lo = (uint32_t)deck;
+  out.deck_hi = (uint32_t)(deck >> 32);
+}
 
 // Installs a drawn initial deal as the lane's new game.
 template <class V>

@@ -26,15 +26,16 @@ constexpr int kMaxInfo = 31;     // 5-bit field
 constexpr int kMaxLife = 15;     // 4-bit field
 constexpr int kMtN = 624;
 constexpr int kMtM = 397;
-// Pre-drawn deal queue (DESIGN.md "deal queue"): when a game is (re-)dealt, the cards of its
-// next `prefill` in-game deals are drawn as well -- from RNG words that stay unconsumed until
-// the card is actually dealt -- so that a deal inside the episode touches no RNG memory.
-// A draw from a deck of >= kSafeDraw cards always sees >= 2 card types (at most 3 instances
-// per type), i.e. always consumes two RNG words (random.tcc:2660-2664).
-constexpr int kMaxPrefill = 10;  // 5-bit type ids in a 64-bit queue word: 11 would fit, 10 keeps a job within 32 lanes
-constexpr int kSafeDraw = 4;
-#ifndef HB_PREFILL
-#define HB_PREFILL -1  // >= 0: upper bound on the queue length (experiments); -1: as long as it fits
+// Lazy slot regeneration (DESIGN.md "mt19937"): a deal inside an episode only READS its two
+// RNG words; the slots are regenerated later, together and coalesced, by the job that
+// re-deals the game (or by a flush job once `pend_cap - 1` pairs are pending).  The in-place
+// scheme stays valid while fewer than 227 words are pending: at most 2 * 15 here.
+constexpr int kMaxPend = 15;  // 4-bit field
+#ifndef HB_LAZY_REGEN
+#define HB_LAZY_REGEN 1
+#endif
+#ifndef HB_JOBS_MIN_CARDS
+#define HB_JOBS_MIN_CARDS 12  // initial deals of this many cards or more use the job path (hb_engine.cuh)
 #endif
 
 // Observation types, hanabi_lib/hanabi_game.h:39.
@@ -63,7 +64,7 @@ struct Spec {
   int32_t obs_size, max_moves;
   int32_t hands_len, board_len, discard_len, last_len, know_len;
   int32_t fast_reset;  // the unrolled re-deal applies (no random start, >= 2 card types left throughout)
-  int32_t prefill;     // length of the pre-drawn deal queue (0 = off), PrefillFor()
+  int32_t pend_cap;    // lazy regeneration: pending pairs a game may carry (0 = regenerate at once), PendCapFor()
   // Deck bitmap helpers (one bit per card instance, same layout as the discard
   // thermometers): first bit of every type block by block width.
   uint64_t full_deck, type_m23, type_m3, type_m1;
@@ -75,19 +76,13 @@ HB_HD int InstancesOfRank(int R, int rank) {  // hanabi_game.cc:126-136
 // Bit offset of rank r inside one colour's discard thermometer block.
 HB_HD int DiscardRankOffset(int rank) { return rank == 0 ? 0 : 2 * rank + 1; }
 
-// Queue length n for a rule set: one job = (n + 1) pending + P*H fresh + n peeked word
-// pairs must fit the 32 lanes of a warp, and the last peeked draw must still be "safe".
-HB_HD constexpr int PrefillFor(int P, int H, int deck_max, int random_start) {
-  if (random_start || deck_max - P * H < 3 || P * H > 30) return 0;
-  int n = (31 - P * H) / 2;
-  if (n > kMaxPrefill) n = kMaxPrefill;
-  // episodes of small decks are short: a quarter of the in-game deck is plenty, and short
-  // jobs pack two or three to a warp
-  const int quarter = (deck_max - P * H) / 4 < 2 ? 2 : (deck_max - P * H) / 4;
-  if (n > quarter) n = quarter;
-  if (n > deck_max - P * H - 3) n = deck_max - P * H - 3;
-  if (HB_PREFILL >= 0 && n > HB_PREFILL) n = HB_PREFILL;
-  return n < 0 ? 0 : n;
+// Pending pairs a game of this rule set may carry.  Games of small decks deal few cards per
+// episode; a small cap keeps their re-deal jobs narrow (a job has P*H + pend_cap pair slots).
+HB_HD constexpr int PendCapFor(int P, int H, int deck_max, int random_start) {
+  if (!HB_LAZY_REGEN || P * H < HB_JOBS_MIN_CARDS || random_start || deck_max - P * H < 3 || P * H > 30) return 0;
+  int n = (deck_max - P * H) / 3;
+  n = n < 4 ? 4 : n;
+  return n > kMaxPend ? kMaxPend : n;
 }
 
 // Fills the derived fields.  Returns 0 on success, else an error code whose
@@ -124,7 +119,7 @@ inline int FinishSpec(Spec* s) {
     }
   // A deck with more cards than the largest multiplicity (3) holds >= 2 types.
   s->fast_reset = (!s->random_start && s->deck_max - s->P * s->H >= 3 && s->P * s->H <= 30) ? 1 : 0;
-  s->prefill = PrefillFor(s->P, s->H, s->deck_max, s->random_start);
+  s->pend_cap = PendCapFor(s->P, s->H, s->deck_max, s->random_start);
   return 0;
 }
 
