@@ -13,6 +13,7 @@
 #include <math_constants.h>
 #include <stdint.h>
 
+#include <climits>
 #include <cstdlib>
 #include <string>
 #include <type_traits>
@@ -708,6 +709,161 @@ __global__ void k_c51_target(const float* __restrict__ rewards, const uint8_t* _
   project_row(s_sup, s_w, z, N, out + (int64_t)b * N, lane);
 }
 
+// C51 head with 51 atoms and 16-bit logits, the shape the Rainbow actor runs
+// (agents/rainbow_copy/rainbow_agent.py:36-68,163-172): a streaming kernel, HBM-bound by design
+// (one 2 KB row in, 4 bytes out per game).
+//   * persistent warps, one game per warp and iteration; rows travel global -> shared memory
+//     with cp.async (16 bytes per lane and copy, four copies per row), kStages rows in flight
+//     per warp, no registers and no store instructions spent on staging;
+//   * an action's 51 atoms are three UNITS of 17; a lane owns two consecutive units =
+//     34 elements = 17 consecutive 32-bit words of the row, which it picks out of the staged
+//     row with 17 conflict-free LDS.32 (17 is odd); unit boundaries are therefore compile-time
+//     positions inside the lane's registers and everything below unrolls;
+//   * per unit: maximum, sum of 2^((x - max) * log2e), and the same sum weighted with the
+//     support (the lane's 34 support values stay in registers across games);
+//   * the three units of an action meet through shared memory (rescaled to their common
+//     maximum, as in any split softmax), q = weighted / plain sum, then the masked arg-max
+//     with the first maximal index (tf.argmax) by one warp reduction on an order-preserving
+//     integer image of q; epsilon-greedy as in k_select_c51.
+// Needs 3 * A <= 64, rows 16-byte aligned.  T = __nv_bfloat16 or __half.
+#ifndef HB_U17_WARPS
+#define HB_U17_WARPS 8
+#endif
+#ifndef HB_U17_STAGES
+#define HB_U17_STAGES 4
+#endif
+// Element-wise maximum of two packed 16-bit pairs.
+template <class T> __device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b);
+template <> __device__ __forceinline__ uint32_t max2<__nv_bfloat16>(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+template <> __device__ __forceinline__ uint32_t max2<__half>(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("max.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory");
+}
+constexpr int kU17RowQuads = 128 + 8;  // 2 KB row + pad (the last lane reads words 527..543)
+constexpr size_t kU17SmemBytes = (size_t)HB_U17_WARPS * HB_U17_STAGES * kU17RowQuads * sizeof(uint4) +
+                                 (size_t)HB_U17_WARPS * 64 * 3 * sizeof(float);
+
+template <class T>
+__global__ void __launch_bounds__(32 * HB_U17_WARPS) k_select_c51_u17(const T* __restrict__ logits, int64_t row_pitch,
+                                                                     const float* __restrict__ support,
+                                                                     const uint8_t* __restrict__ mask, int n, int A,
+                                                                     float epsilon, uint64_t seed, uint64_t step,
+                                                                     int32_t* __restrict__ actions) {
+  constexpr int kAtoms = 51, kUnit = 17, kWarps = HB_U17_WARPS, kStages = HB_U17_STAGES;
+  constexpr float kL2e = 1.4426950408889634f;
+  extern __shared__ uint4 s_dyn[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint4* rows = s_dyn + (size_t)warp * kStages * kU17RowQuads;          // this warp's stages
+  float* part = reinterpret_cast<float*>(s_dyn + (size_t)kWarps * kStages * kU17RowQuads) + warp * 64 * 3;
+  const int units = 3 * A, len_row = A * kAtoms;
+  const int quads = (len_row + 7) >> 3;        // 16-byte groups of a row that hold logits
+  // the lane's two units and their support values (loop invariant)
+  const int u0 = 2 * lane, u1 = 2 * lane + 1;
+  float z0[kUnit], z1[kUnit];
+#pragma unroll
+  for (int j = 0; j < kUnit; ++j) {
+    z0[j] = support[(u0 % 3) * kUnit + j];
+    z1[j] = support[(u1 % 3) * kUnit + j];
+  }
+  // the pad words are read (by lanes whose units do not exist) but never used: keep them finite
+  for (int st = 0; st < kStages; ++st)
+    if (lane < 8) rows[st * kU17RowQuads + 128 + lane] = make_uint4(0, 0, 0, 0);
+  const int wstride = gridDim.x * kWarps;
+  const int g0 = blockIdx.x * kWarps + warp;
+  auto fetch = [&](int g, int st) {
+    if (g < n) {
+      const uint4* src = reinterpret_cast<const uint4*>(logits + (int64_t)g * row_pitch);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (lane + 32 * k < quads) cp_async16(rows + st * kU17RowQuads + lane + 32 * k, src + lane + 32 * k);
+    }
+    cp_async_commit();  // (an empty group keeps the group count in step)
+  };
+#pragma unroll
+  for (int st = 0; st < kStages - 1; ++st) fetch(g0 + st * wstride, st);
+  int stage = 0;
+  // the legal-move byte of the lane's action, fetched one game ahead like the rows
+  uint32_t mask_next = (g0 < n && lane < A) ? mask[(int64_t)g0 * A + lane] : 0u;
+  for (int g = g0; g < n; g += wstride) {
+    // the row kStages - 1 iterations ahead goes into the stage consumed in the previous iteration
+    __syncwarp();
+    fetch(g + (kStages - 1) * wstride, stage == 0 ? kStages - 1 : stage - 1);
+    const bool legal = mask_next != 0u;
+    mask_next = (g + wstride < n && lane < A) ? mask[(int64_t)(g + wstride) * A + lane] : 0u;
+    cp_async_wait<kStages - 1>();  // this iteration's row has landed (this thread's copies) ...
+    __syncwarp();                  // ... and everybody else's
+    const uint32_t* words = reinterpret_cast<const uint32_t*>(rows + stage * kU17RowQuads);
+    // the lane's 34 elements: words 17*lane .. 17*lane + 16; unit 0 = x[0..16], unit 1 = x[17..33]
+    uint32_t wd[kUnit];
+#pragma unroll
+    for (int w = 0; w < kUnit; ++w) wd[w] = words[kUnit * lane + w];
+    // unit maxima on the packed 16-bit pairs (one instruction per two elements): words 0..7 are
+    // unit 0, words 9..16 unit 1, word 8 holds the last element of unit 0 and the first of unit 1
+    uint32_t p0 = wd[0], p1 = wd[9];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) { p0 = max2<T>(p0, wd[w]); p1 = max2<T>(p1, wd[9 + w]); }
+    const float2 f0 = unpack2<T>(p0), f1 = unpack2<T>(p1), mid = unpack2<T>(wd[8]);
+    const float m0 = fmaxf(fmaxf(f0.x, f0.y), mid.x), m1 = fmaxf(fmaxf(f1.x, f1.y), mid.y);
+    float x[2 * kUnit];
+#pragma unroll
+    for (int w = 0; w < kUnit; ++w) {
+      const float2 v = unpack2<T>(wd[w]);
+      x[2 * w] = v.x;
+      x[2 * w + 1] = v.y;
+    }
+    const float n0 = -m0 * kL2e, n1 = -m1 * kL2e;
+    float s0 = 0.f, w0 = 0.f, s1 = 0.f, w1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < kUnit; ++j) {
+      const float e0 = ex2_fast(fmaf(x[j], kL2e, n0));
+      const float e1 = ex2_fast(fmaf(x[kUnit + j], kL2e, n1));
+      s0 += e0; w0 = fmaf(e0, z0[j], w0);
+      s1 += e1; w1 = fmaf(e1, z1[j], w1);
+    }
+    if (u0 < units) { part[3 * u0] = m0; part[3 * u0 + 1] = s0; part[3 * u0 + 2] = w0; }
+    if (u1 < units) { part[3 * u1] = m1; part[3 * u1 + 1] = s1; part[3 * u1 + 2] = w1; }
+    __syncwarp();
+    int key = INT_MIN;  // order-preserving integer image of q (illegal actions: below everything)
+    if (legal) {
+      const float* p = part + 9 * lane;  // units 3a, 3a+1, 3a+2 of action a = lane
+      const float mm = fmaxf(p[0], fmaxf(p[3], p[6]));
+      const float c0 = ex2_fast((p[0] - mm) * kL2e), c1 = ex2_fast((p[3] - mm) * kL2e),
+                  c2 = ex2_fast((p[6] - mm) * kL2e);
+      const float se = fmaf(p[1], c0, fmaf(p[4], c1, p[7] * c2));
+      const float sw = fmaf(p[2], c0, fmaf(p[5], c1, p[8] * c2));
+      const int qi = __float_as_int(sw / se);
+      key = qi ^ ((qi >> 31) & 0x7fffffff);
+      key = key == INT_MIN ? INT_MIN + 1 : key;
+    }
+    const unsigned legal_m = __ballot_sync(kFull, legal);
+    const int best = __reduce_max_sync(kFull, key);
+    int choice = __ffs((int)__ballot_sync(kFull, legal && key == best)) - 1;  // first maximal index
+    if (legal_m == 0u) {
+      choice = -1;
+    } else if (epsilon > 0.0f) {
+      const uint64_t bits = policy_bits(seed, step, (uint64_t)g);
+      const float u01 = (float)(bits >> 40) * (1.0f / 16777216.0f);
+      if (u01 <= epsilon) choice = kth_set_bit((uint64_t)legal_m, random_legal_rank(bits, __popc(legal_m)));
+    }
+    if (lane == 0) actions[g] = choice;
+    stage = stage + 1 == kStages ? 0 : stage + 1;
+  }
+  cp_async_wait<0>();
+}
+
 }  // namespace hbp
 
 int HbFail(const std::string& msg);  // hb_batch.cu
@@ -728,7 +884,27 @@ cudaError_t LaunchSelectC51(const T* logits, int64_t row_pitch, const float* sup
   const size_t thirds_bytes = 512 + 8 * row_bytes + 8 * (size_t)3 * A * sizeof(float2);
   static const bool use_thirds = std::getenv("HANABI_B200_SELECT_THIRDS") == nullptr ||
                                  std::atoi(std::getenv("HANABI_B200_SELECT_THIRDS")) != 0;
-  if (use_thirds && aligned && atoms <= 63 && thirds_bytes <= 48 * 1024) {
+  static const bool use_u17 = std::getenv("HANABI_B200_SELECT_U17") == nullptr ||
+                              std::atoi(std::getenv("HANABI_B200_SELECT_U17")) != 0;
+  if (use_u17 && sizeof(T) == 2 && aligned && atoms == 51 && 3 * A <= 64 && A <= 32) {
+    // the Rainbow actor's shape: streaming kernel, persistent warps (a few CTAs per SM)
+    typedef typename std::conditional<sizeof(T) == 2, T, __half>::type T16;
+    static int resident_ctas = 0;  // CTAs of this kernel the device holds at once
+    if (resident_ctas == 0) {
+      int dev = 0, sms = 148, per_sm = 2;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      cudaFuncSetAttribute(hbp::k_select_c51_u17<T16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                           (int)hbp::kU17SmemBytes);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hbp::k_select_c51_u17<T16>, 32 * HB_U17_WARPS,
+                                                    hbp::kU17SmemBytes);
+      resident_ctas = sms * (per_sm > 0 ? per_sm : 1);
+    }
+    const int64_t want = ((int64_t)n + HB_U17_WARPS - 1) / HB_U17_WARPS;
+    const unsigned pgrid = (unsigned)(want < resident_ctas ? want : resident_ctas);
+    hbp::k_select_c51_u17<T16><<<pgrid, 32 * HB_U17_WARPS, hbp::kU17SmemBytes, s>>>(reinterpret_cast<const T16*>(logits), row_pitch, support, mask,
+                                                     n, A, epsilon, seed, step, actions);
+  } else if (use_thirds && aligned && atoms <= 63 && thirds_bytes <= 48 * 1024) {
     if (atoms == 51)
       hbp::k_select_c51_thirds<T, 17><<<grid, 256, thirds_bytes, s>>>(logits, row_pitch, support, mask, n, A, atoms,
                                                                      epsilon, seed, step, actions, nullptr,
