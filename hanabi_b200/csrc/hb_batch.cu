@@ -80,6 +80,7 @@ struct KArgs {
   int64_t game_base;  // global index of this batch's game 0 (BatchSetGameIndexBase): the policy key's game
   unsigned long long* stats;
   uint4* hist;  // optional: the 4 non-deal moves before `last`, newest first (BatchEnableHistory)
+  uint32_t* disc_log;  // optional, with hist: the discard pile in order, kDiscardLogWords words per game
   int auto_reset;
   int sampler_mode;
   int observer;
@@ -115,6 +116,12 @@ __global__ void __launch_bounds__(V::kBlock, kResidentThreads / V::kBlock) k_mai
   constexpr int kItems = HB_ITEMS;  // job path: RNG word pairs per thread in flight in phase B
   __shared__ uint8_t s_qb[kJobs ? kItems * kBlock : 4];  // job path: draw indices of one pass
   __shared__ uint32_t s_spread[32];
+#if HB_EXPAND_LUT16
+  __shared__ uint32_t s_nib[16];
+  if (threadIdx.x < 16) s_nib[threadIdx.x] = nibble_to_bytes(threadIdx.x);
+#else
+  const uint32_t* const s_nib = nullptr;
+#endif
   // byte -> its eight 16-bit elements: 4 KB of dynamic shared memory that only the launches
   // writing network-input rows ask for
   uint4* s_net_lut = reinterpret_cast<uint4*>(smem + a.net_lut_offset_words);  // behind this view's areas
@@ -502,11 +509,27 @@ __global__ void __launch_bounds__(V::kBlock, kResidentThreads / V::kBlock) k_mai
     }
     if (MODE != kModeObserve && a.hist != nullptr) {
       // move history for the rule-based agents: a new game starts with none
+      uint32_t* log = a.disc_log + g * (int64_t)kDiscardLogWords;
       if (restarted) {
         a.hist[g] = make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int w = 0; w < kDiscardLogWords; ++w) log[w] = 0u;
       } else if (moved_any) {
         const uint4 h = a.hist[g];
         a.hist[g] = make_uint4(prev_last, h.x, h.y, h.z);
+        // a discarded or misplayed card goes on the pile: append its type to the ordered log
+        // (the pile itself is kept as order-free thermometers; rl_env.py:416-418 wants the order)
+        const uint32_t la = G.last;
+        const int type = (la >> kLaTypeSh) & 3;
+        if (type == kLaDiscard || (type == kLaPlay && !((la >> kLaScoredSh) & 1u))) {
+          const int idx = __popcll(G.disc) - 1;  // its position on the pile
+          const uint32_t card = ((la >> kLaColSh) & 7u) * (uint32_t)v.R() + ((la >> kLaRankSh) & 7u);
+          const int bit = 5 * idx, w = bit >> 5, sh = bit & 31;
+          if (w < kDiscardLogWords) {
+            log[w] |= card << sh;
+            if (sh > 27 && w + 1 < kDiscardLogWords) log[w + 1] |= card >> (32 - sh);
+          }
+        }
       }
     }
   }
@@ -530,7 +553,7 @@ __global__ void __launch_bounds__(V::kBlock, kResidentThreads / V::kBlock) k_mai
   __syncwarp();
   if (a.obs)
     expand_stream(obs_stream, a.spec.obs_size, a.obs + tile0 * a.obs_pitch, a.obs_pitch, n_valid,
-                  lane);
+                  lane, s_nib);
   if (a.obs_bits)
     store_packed_rows(obs_stream, a.packed_words, a.obs_bits + tile0 * a.packed_words, n_valid, lane);
   if (NET) {
@@ -540,24 +563,61 @@ __global__ void __launch_bounds__(V::kBlock, kResidentThreads / V::kBlock) k_mai
   }
   if (a.mask)
     expand_stream(mask_stream, a.spec.max_moves, a.mask + tile0 * a.spec.max_moves,
-                  a.spec.max_moves, n_valid, lane);
+                  a.spec.max_moves, n_valid, lane, s_nib);
 }
 
 // std::mt19937::seed(value) per game followed by the first block regeneration
 // (libstdc++ does it lazily on the first draw), so that the block holds outputs
-// 0..623 (untempered) and the index starts at 0.
-__global__ void k_seed(uint32_t* mt, const int32_t* seeds, int64_t N) {
-  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// 0..623 (untempered) and the index starts at 0.  Two kernels, both with coalesced
+// traffic on the 2.5 KB blocks:
+//   k_seed_init   init_genrand: a serial recurrence per game, one thread per game; a warp's
+//                 32 games go through a transposed shared-memory tile, 32 words at a time, so
+//                 that every store instruction writes 128 contiguous bytes of one game's block
+//   k_seed_twist  the first block regeneration, one warp per game in shared memory: slot k
+//                 needs the old slots k, k+1 and slot k+397 (old for k < 227, new beyond), so
+//                 the warp walks k upwards 32 slots at a time
+__global__ void __launch_bounds__(128) k_seed_init(uint32_t* mt, const int32_t* seeds, int64_t N) {
+  __shared__ uint32_t tile[4][32][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t g0 = ((int64_t)blockIdx.x * 4 + warp) * 32;  // first game of this warp
+  if (g0 >= N) return;
+  const int64_t g = g0 + lane;
+  const int n_games = (int)(N - g0 < 32 ? N - g0 : 32);
+  uint32_t x = g < N ? (uint32_t)seeds[g] : 0u;
+  for (int c = 0; c < kMtN; c += 32) {  // 19 chunks of 32 words and one of 16
+    const int len = kMtN - c < 32 ? kMtN - c : 32;
+    for (int j = 0; j < len; ++j) {
+      const int i = c + j;
+      if (i > 0) x = 1812433253u * (x ^ (x >> 30)) + (uint32_t)i;
+      tile[warp][lane][j] = x;
+    }
+    __syncwarp();
+    for (int r = 0; r < n_games; ++r)
+      if (lane < len) mt[(g0 + r) * (int64_t)kMtN + c + lane] = tile[warp][r][lane];
+    __syncwarp();
+  }
+}
+
+__global__ void __launch_bounds__(128) k_seed_twist(uint32_t* mt, int64_t N) {
+  __shared__ uint32_t blk[4][kMtN + 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t g = (int64_t)blockIdx.x * 4 + warp;
   if (g >= N) return;
   uint32_t* my = mt + g * (int64_t)kMtN;
-  uint32_t x = (uint32_t)seeds[g];
-  my[0] = x;
-  for (int i = 1; i < kMtN; ++i) {
-    x = 1812433253u * (x ^ (x >> 30)) + (uint32_t)i;
-    my[i] = x;
+  uint32_t* s = blk[warp];
+  for (int k = lane; k < kMtN; k += 32) s[k] = my[k];
+  __syncwarp();
+  for (int k0 = 0; k0 < kMtN; k0 += 32) {
+    const int k = k0 + lane;
+    uint32_t v = 0;
+    if (k < kMtN) v = mt_next_block_word(s[k], s[mt_wrap(k + 1)], s[mt_wrap(k + kMtM)]);
+    // slot 623 reads the NEW slot 0 as its successor (written in the first round); every other
+    // successor and every slot k + 397 < 624 is still old, every wrapped k + 397 already new
+    __syncwarp();
+    if (k < kMtN) s[k] = v;
+    __syncwarp();
   }
-  for (int k = 0; k < kMtN; ++k)
-    my[k] = mt_next_block_word(my[k], my[mt_wrap(k + 1)], my[mt_wrap(k + kMtM)]);
+  for (int k = lane; k < kMtN; k += 32) my[k] = s[k];
 }
 
 __global__ void k_blank(uint4* state, int64_t N, int ncols) {
@@ -620,6 +680,10 @@ __global__ void k_export(KArgs a, int64_t g, int32_t* out) {
   out[kDumpLen + 4] = (int32_t)h.z; out[kDumpLen + 5] = (int32_t)h.w;
   out[kDumpLen + 6] = G.done;
   out[kDumpLen + 7] = G.eplen;
+  for (int w = 0; w < kDiscardLogWords; ++w)
+    out[kDumpLen + 8 + w] = a.disc_log ? (int32_t)a.disc_log[g * (int64_t)kDiscardLogWords + w] : 0;
+  out[kDumpLen + 8 + kDiscardLogWords] = a.disc_log ? 1 : 0;
+  out[kDumpLen + 9 + kDiscardLogWords] = 0;
 }
 
 // Per-game error flags (an illegal action was submitted since the last clear).
@@ -682,6 +746,10 @@ __global__ void k_pack(KArgs a, const int32_t* in, const int32_t* extra) {
   G.done = is_terminal(v, G) ? 1 : 0;
   store_game(a.state, a.N, g, v, G);
   if (a.hist) a.hist[g] = make_uint4(0, 0, 0, 0);
+  // (an injected pile has no order: the log restarts empty and stays marked valid only for
+  //  cards discarded from here on -- BatchExportGame reports it invalid when the counts disagree)
+  if (a.disc_log)
+    for (int w = 0; w < kDiscardLogWords; ++w) a.disc_log[g * (int64_t)kDiscardLogWords + w] = 0u;
 }
 
 // Test hook: the deal sampler alone on caller-provided decks (2-bit counts per
@@ -747,6 +815,7 @@ struct Batch {
   unsigned long long* stats = nullptr;      // active stats buffer
   unsigned long long* own_stats = nullptr;  // library-owned fallback
   uint4* hist = nullptr;                    // move history ring, BatchEnableHistory
+  uint32_t* disc_log = nullptr;             // ordered discard pile, allocated with hist
   int sampler_mode = 0;
   int force_generic = 0;
   int64_t game_base = 0;  // global index of game 0 (sharded batches), keys the fused policy
@@ -828,6 +897,7 @@ hb::KArgs BaseArgs(const Batch* b) {
   a.g_end = b->N;
   a.stats = b->stats;
   a.hist = b->hist;
+  a.disc_log = b->disc_log;
   a.sampler_mode = b->sampler_mode;
   a.game_base = b->game_base;
   a.observer = -1;
@@ -974,7 +1044,8 @@ int NewBatch(pyhanabi_batch_t* out, int list_length, const char** param_list, in
   HB_TRY(cudaMalloc(&d_seeds, sizeof(int32_t) * (size_t)b->N));
   HB_TRY(cudaMemcpy(d_seeds, seeds, sizeof(int32_t) * (size_t)b->N, cudaMemcpyHostToDevice));
   const unsigned grid = (unsigned)((b->N + 127) / 128);
-  hb::k_seed<<<grid, 128>>>(b->mt, d_seeds, b->N);
+  hb::k_seed_init<<<grid, 128>>>(b->mt, d_seeds, b->N);
+  hb::k_seed_twist<<<(unsigned)((b->N + 3) / 4), 128>>>(b->mt, b->N);
   hb::k_blank<<<grid, 128>>>(b->state, b->N, b->ncols);
   HB_TRY(cudaGetLastError());
   HB_TRY(cudaDeviceSynchronize());
@@ -1008,6 +1079,7 @@ void DeleteBatch(pyhanabi_batch_t* h) {
   cudaFree(b->mt);
   cudaFree(b->own_stats);
   cudaFree(b->hist);
+  cudaFree(b->disc_log);
   delete b;
   h->batch = nullptr;
 }
@@ -1458,7 +1530,8 @@ int64_t BatchStateBytes(pyhanabi_batch_t* h) {
   Batch* b = AsBatch(h->batch);
   return (int64_t)sizeof(int64_t) * kBlobHeader + (int64_t)sizeof(uint4) * b->ncols * b->N +
          (int64_t)sizeof(uint32_t) * hb::kMtN * b->N +
-         (b->hist ? (int64_t)sizeof(uint4) * b->N : 0) + (int64_t)sizeof(int64_t) * hb::kNumStats;
+         (b->hist ? (int64_t)(sizeof(uint4) + sizeof(uint32_t) * hb::kDiscardLogWords) * b->N : 0) +
+         (int64_t)sizeof(int64_t) * hb::kNumStats;
 }
 
 int BatchGetState(pyhanabi_batch_t* h, void* host_blob, int64_t nbytes) {
@@ -1474,8 +1547,10 @@ int BatchGetState(pyhanabi_batch_t* h, void* host_blob, int64_t nbytes) {
                mb = sizeof(uint32_t) * (size_t)hb::kMtN * N, hbytes = b->hist ? sizeof(uint4) * N : 0;
   HB_CUDA(cudaMemcpy(p, b->state, sb, cudaMemcpyDeviceToHost));
   HB_CUDA(cudaMemcpy(p + sb + qb, b->mt, mb, cudaMemcpyDeviceToHost));
+  const size_t lbytes = b->hist ? sizeof(uint32_t) * hb::kDiscardLogWords * N : 0;
   if (hbytes) HB_CUDA(cudaMemcpy(p + sb + qb + mb, b->hist, hbytes, cudaMemcpyDeviceToHost));
-  HB_CUDA(cudaMemcpy(p + sb + qb + mb + hbytes, b->stats, sizeof(int64_t) * hb::kNumStats, cudaMemcpyDeviceToHost));
+  if (lbytes) HB_CUDA(cudaMemcpy(p + sb + qb + mb + hbytes, b->disc_log, lbytes, cudaMemcpyDeviceToHost));
+  HB_CUDA(cudaMemcpy(p + sb + qb + mb + hbytes + lbytes, b->stats, sizeof(int64_t) * hb::kNumStats, cudaMemcpyDeviceToHost));
   return 0;
 }
 
@@ -1495,8 +1570,10 @@ int BatchSetState(pyhanabi_batch_t* h, const void* host_blob, int64_t nbytes) {
                mb = sizeof(uint32_t) * (size_t)hb::kMtN * N, hbytes = b->hist ? sizeof(uint4) * N : 0;
   HB_CUDA(cudaMemcpy(b->state, p, sb, cudaMemcpyHostToDevice));
   HB_CUDA(cudaMemcpy(b->mt, p + sb + qb, mb, cudaMemcpyHostToDevice));
+  const size_t lbytes = b->hist ? sizeof(uint32_t) * hb::kDiscardLogWords * N : 0;
   if (hbytes) HB_CUDA(cudaMemcpy(b->hist, p + sb + qb + mb, hbytes, cudaMemcpyHostToDevice));
-  HB_CUDA(cudaMemcpy(b->stats, p + sb + qb + mb + hbytes, sizeof(int64_t) * hb::kNumStats, cudaMemcpyHostToDevice));
+  if (lbytes) HB_CUDA(cudaMemcpy(b->disc_log, p + sb + qb + mb + hbytes, lbytes, cudaMemcpyHostToDevice));
+  HB_CUDA(cudaMemcpy(b->stats, p + sb + qb + mb + hbytes + lbytes, sizeof(int64_t) * hb::kNumStats, cudaMemcpyHostToDevice));
   return 0;
 }
 
@@ -1565,6 +1642,8 @@ int BatchEnableHistory(pyhanabi_batch_t* h) {
   if (b->hist) return 0;
   HB_CUDA(cudaMalloc(&b->hist, sizeof(uint4) * (size_t)b->N));
   HB_CUDA(cudaMemset(b->hist, 0, sizeof(uint4) * (size_t)b->N));
+  HB_CUDA(cudaMalloc(&b->disc_log, sizeof(uint32_t) * hb::kDiscardLogWords * (size_t)b->N));
+  HB_CUDA(cudaMemset(b->disc_log, 0, sizeof(uint32_t) * hb::kDiscardLogWords * (size_t)b->N));
   return 0;
 }
 

@@ -1120,8 +1120,11 @@ HB_DEV uint4 bits16_to_bytes(uint32_t bits) {
 // is fed by one halfword of the stream, a warp covering 512 contiguous bytes per
 // instruction.  The stream must have one readable pad word after its last word.
 // (A 256-entry shared-memory table instead of the multiplies was measured 3 % slower.)
+#ifndef HB_EXPAND_LUT16
+#define HB_EXPAND_LUT16 0  // 1: nibble -> four bytes through a 16-word shared-memory table (experiment)
+#endif
 HB_DEV void expand_stream(const uint32_t* stream, int dim, uint8_t* out, int64_t pitch,
-                          int n_valid, int lane) {
+                          int n_valid, int lane, const uint32_t* nib = nullptr) {
   const bool aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
   if (pitch == dim && aligned) {
     const int total = n_valid * dim;
@@ -1134,8 +1137,16 @@ HB_DEV void expand_stream(const uint32_t* stream, int dim, uint8_t* out, int64_t
 #define HB_EXPAND_UNROLL 2
 #endif
     constexpr int kUnroll = HB_EXPAND_UNROLL;
+#if HB_EXPAND_LUT16
+#pragma unroll kUnroll
+    for (int k = lane; k < full_chunks; k += 32) {
+      const uint32_t b = half[k];
+      store_out(dst + k, make_uint4(nib[b & 15u], nib[(b >> 4) & 15u], nib[(b >> 8) & 15u], nib[b >> 12]));
+    }
+#else
 #pragma unroll kUnroll
     for (int k = lane; k < full_chunks; k += 32) store_out(dst + k, bits16_to_bytes(half[k]));
+#endif
     for (int b = (full_chunks << 4) + lane; b < total; b += 32)  // ragged tail of a partial tile
       out[b] = (uint8_t)((stream[b >> 5] >> (b & 31)) & 1u);
   } else if ((pitch & 15) == 0 && aligned) {

@@ -732,10 +732,11 @@ void DeleteState(pyhanabi_state_t* state) {
 // Rebuilds `state` (an existing state of `game`) from one game of a batch as
 // BatchExportGame returns it, so that the reference's per-object API -- observations,
 // encoders, the rule-based agents, the GUI layer -- can look at a batched game.
-// The batch keeps neither the order of the discard pile (the pile comes back sorted
-// by card type) nor deal moves nor more than the last 1 (5 with BatchEnableHistory)
-// player moves; newly_revealed_bitmask is not recorded and returns as the reveal
-// bitmask.  Everything the canonical encoder and LegalMoves look at is exact.
+// With BatchEnableHistory the discard pile comes back in the order the cards were discarded
+// and the move history holds what any observer can see: the newest P player moves with the
+// deals that followed them (without it: the pile sorted by card type, the last player move
+// only).  newly_revealed_bitmask is not recorded and returns as the reveal bitmask.
+// Everything the canonical encoder and LegalMoves look at is exact either way.
 void StateFromBatchGame(pyhanabi_game_t* game, const int32_t* rec, pyhanabi_state_t* state) {
   HBS_REQUIRE(game != nullptr && game->game != nullptr && rec != nullptr && state != nullptr);
   const Game* g = CAS(Game, game->game);
@@ -766,20 +767,54 @@ void StateFromBatchGame(pyhanabi_game_t* game, const int32_t* rec, pyhanabi_stat
     }
   }
   st->discard_pile.clear();
+  int total_discards = 0;
   for (int k = 0; k < C * R; ++k) {
     st->deck[k] = rec[216 + k];
-    for (int j = 0; j < rec[241 + k]; ++j) {
+    total_discards += rec[241 + k];
+  }
+  // the pile in the order the cards were discarded (rl_env.py:416-418), when the batch logged
+  // it (BatchEnableHistory) and the log agrees with the per-type counts; else sorted by type
+  bool ordered = rec[hb::kDumpLen + 8 + hb::kDiscardLogWords] != 0 && total_discards * 5 <= 32 * hb::kDiscardLogWords;
+  if (ordered) {
+    std::vector<int> seen(C * R, 0);
+    std::vector<Card> pile;
+    for (int i = 0; i < total_discards && ordered; ++i) {
+      const int bit = 5 * i, w = bit >> 5, sh = bit & 31;
+      uint32_t v = (uint32_t)rec[hb::kDumpLen + 8 + w] >> sh;
+      if (sh > 27 && w + 1 < hb::kDiscardLogWords) v |= (uint32_t)rec[hb::kDumpLen + 9 + w] << (32 - sh);
+      const int k = (int)(v & 31u);
+      if (k >= C * R) { ordered = false; break; }
+      seen[k] += 1;
       Card card;
       card.color = k / R;
       card.rank = k % R;
-      st->discard_pile.push_back(card);
+      pile.push_back(card);
     }
+    for (int k = 0; k < C * R && ordered; ++k) ordered = seen[k] == rec[241 + k];
+    if (ordered) st->discard_pile = pile;
+  }
+  if (!ordered) {
+    for (int k = 0; k < C * R; ++k)
+      for (int j = 0; j < rec[241 + k]; ++j) {
+        Card card;
+        card.color = k / R;
+        card.rank = k % R;
+        st->discard_pile.push_back(card);
+      }
   }
   st->turns_to_play = rec[hb::kDumpLen];
   st->history.clear();
-  for (int j = 4; j >= 0; --j) {  // oldest first; [1] is the newest
+  // Nobody sees further back than his own previous move (HanabiObservation,
+  // hanabi_observation.cc:77-92), i.e. at most the newest P player moves -- each by a different
+  // player, none of whom has moved since.  That is why the deal that followed a play/discard
+  // can be restored: the actor's hand is full again exactly when a card was dealt, and the
+  // card is the last one in his hand.
+  int kept = 0;
+  for (int j = 0; j <= 4; ++j)
+    if ((uint32_t)rec[hb::kDumpLen + 1 + j] & 1u) ++kept; else break;
+  if (kept > P) kept = P;
+  for (int j = kept - 1; j >= 0; --j) {  // oldest first; [1] is the newest
     const uint32_t la = (uint32_t)rec[hb::kDumpLen + 1 + j];
-    if (!(la & 1u)) continue;
     HistoryItem h;
     const int type = (la >> hb::kLaTypeSh) & 3;
     h.player = (int8_t)((la >> hb::kLaActorSh) & 7);
@@ -797,6 +832,17 @@ void StateFromBatchGame(pyhanabi_game_t* game, const int32_t* rec, pyhanabi_stat
       h.newly_revealed_bitmask = h.reveal_bitmask;
     }
     st->history.push_back(h);
+    if ((type == hb::kLaPlay || type == hb::kLaDiscard) && h.player >= 0 && h.player < P) {
+      const Hand& hand = st->hands[h.player];
+      if ((int)hand.cards.size() == g->hand_size && !hand.cards.empty()) {
+        HistoryItem d;
+        const Card& c = hand.cards.back();
+        d.move = Move(kDeal, -1, -1, c.color, c.rank);
+        d.player = -1;  // the chance player
+        d.deal_to_player = h.player;
+        st->history.push_back(d);
+      }
+    }
   }
   delete AS(State, state->state);
   state->state = st;

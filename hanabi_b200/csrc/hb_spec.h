@@ -54,8 +54,12 @@ constexpr int kLaValid = 0, kLaTypeSh = 1, kLaActorSh = 3, kLaOffSh = 6, kLaValS
 // BatchExportGame: canonical dump (272 ints, oracle/oracle_api.h layout) followed by
 // [272] turns_to_play [273] last-move record [274..277] the four records before it, newest
 // first (0 unless BatchEnableHistory) [278] done flag [279] episode length
+// [280..287] the discard pile in the order the cards were discarded, 5-bit card types
+// (colour * R + rank) packed from bit 0 on [288] 1 when that log is valid (BatchEnableHistory
+// was on for the whole episode), else 0 [289] spare
 constexpr int kDumpLen = 272;
-constexpr int kExportLen = 280;
+constexpr int kExportLen = 290;
+constexpr int kDiscardLogWords = 8;  // 50 cards x 5 bits
 
 struct Spec {
   int32_t P, C, R, H, IT, LT;

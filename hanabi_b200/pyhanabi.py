@@ -1077,11 +1077,13 @@ class HanabiBatch(object):
   def export_state(self, game_index):
     """Game `game_index` as a single-game HanabiState (BatchExportGame +
     StateFromBatchGame): observations, encoders, rule-based agents and the GUI layer
-    of the per-object API work on it.  The discard pile comes back sorted by card type
-    and the move history holds the last player move only (five with enable_history())."""
+    of the per-object API work on it.  With enable_history() the discard pile keeps its
+    order and the move history holds everything an observer can see (the newest P player
+    moves and the deals after them); without it the pile comes back sorted by card type and
+    the history holds the last player move only."""
     if getattr(self, "_host_game", None) is None:
       self._host_game = HanabiGame(dict(self._params))
-    rec = ffi.new("int32_t[280]")
+    rec = ffi.new("int32_t[290]")
     _check(lib.BatchExportGame(self._c, int(game_index), rec, self._stream()), "BatchExportGame")
     state = HanabiState(self._host_game)
     lib.StateFromBatchGame(self._host_game.c_game, rec, state._state)

@@ -245,9 +245,10 @@ class BatchedHanabiEnv(object):
   def game_observations(self, game_index):
     """What the reference's HanabiEnv returns for one game -- {'player_observations':
     [14-key dict per player], 'current_player'} (rl_env.py:368-438) -- built on demand
-    from game `game_index` of the batch, for debugging, logging and the GUI layer.  The
-    discard pile is sorted by card type and `pyhanabi.last_moves()` holds the last player
-    move only (five with batch.enable_history()); everything else is exact."""
+    from game `game_index` of the batch, for debugging, logging and the GUI layer.  After
+    batch.enable_history() every key is exact, including the order of the discard pile and
+    `pyhanabi.last_moves()`; without it the pile is sorted by card type and last_moves()
+    holds the last player move only."""
     state = self.batch.export_state(game_index)
     game = self.batch.host_game
     if getattr(self, "_host_encoder", None) is None:

@@ -472,13 +472,16 @@ int BatchErrorFlags(pyhanabi_batch_t* batch, uint8_t* flags, uint64_t* count, in
                     void* stream);
 
 /* One game of a batch for the per-object API above (debugging, the GUI layer, the
-   rule-based agents): BatchExportGame copies game `game` into host_record (280
+   rule-based agents): BatchExportGame copies game `game` into host_record (290
    int32: the canonical state dump, turns_to_play, the last player move and -- with
-   BatchEnableHistory -- the four before it); StateFromBatchGame rebuilds `state`
-   (any existing state of a HanabiGame with the batch's parameters) from it.  Exact
-   for everything LegalMoves, Score, the observations' hands/knowledge/tokens and the
-   canonical encoding read; the discard pile comes back sorted by card type and deal
-   moves are not part of the history. */
+   BatchEnableHistory -- the four before it and the discard pile in order);
+   StateFromBatchGame rebuilds `state` (any existing state of a HanabiGame with the
+   batch's parameters) from it.  Exact for everything LegalMoves, Score, the
+   observations' hands/knowledge/tokens and the canonical encoding read.  With
+   BatchEnableHistory also the discard pile's order (rl_env.py:416-418) and the moves an
+   observer sees (HanabiObservation::LastMoves, hanabi_observation.cc:77-92: the newest
+   P player moves and the deals after them); without it the pile comes back sorted by
+   card type and only the last player move is kept. */
 int BatchExportGame(pyhanabi_batch_t* batch, int64_t game, int32_t* host_record, void* stream);
 void StateFromBatchGame(pyhanabi_game_t* game, const int32_t* host_record,
                         pyhanabi_state_t* state);

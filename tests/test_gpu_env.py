@@ -212,6 +212,60 @@ def test_self_play_recorder_posts_the_reference_trajectories():
     assert abs(float(reward3[i]) - float(acc)) < 1e-5 and int(terminal[i]) == term
 
 
+def _move_item_tuple(m):
+  mv = m.move()
+  return (str(mv), m.player(), m.scored(), m.information_token(), m.color(), m.rank(),
+          tuple(m.card_info_revealed()), m.deal_to_player())
+
+
+@pytest.mark.parametrize("players", [2, 3, 5])
+def test_exported_game_with_history_keeps_discard_order_and_last_moves(players):
+  """With BatchEnableHistory the single-game view of a batched game has the discard pile in the
+  order the cards were discarded (rl_env.py:416-418) and, for EVERY observer, exactly the
+  last_moves the reference observation holds (hanabi_observation.cc:77-92: player moves and
+  deals back to the observer's own previous move) -- against the single-game HanabiEnv."""
+  import torch
+  from hanabi_b200 import rl_env
+  n, probe = 70, [0, 33, 69]
+  env = rl_env.make_batched("Hanabi-Full", num_players=players, num_games=n, seed=300)
+  env.batch.enable_history()
+  singles = {}
+  for i in probe:
+    cfg = dict(colors=5, ranks=5, players=players, max_information_tokens=8, max_life_tokens=3,
+               observation_type=1, seed=300 + i)
+    singles[i] = rl_env.HanabiEnv(cfg)
+    singles[i].reset()
+  obs = env.reset()
+  rng = np.random.default_rng(11)
+  alive = set(probe)
+  saw_discards = 0
+  for t in range(60):
+    mask = obs["legal_moves_mask"].cpu().numpy()
+    for i in sorted(alive):
+      got = env.game_observations(i)
+      want = singles[i]._make_observation_all_players()
+      for pg, pw in zip(got["player_observations"], want["player_observations"]):
+        assert pg["discard_pile"] == pw["discard_pile"], (i, t)   # order included
+        saw_discards = max(saw_discards, len(pw["discard_pile"]))
+        mine = [_move_item_tuple(m) for m in pg["pyhanabi"].last_moves()]
+        ref = [_move_item_tuple(m) for m in pw["pyhanabi"].last_moves()]
+        assert mine == ref, (i, t)
+    # a policy that discards and plays a lot, so that piles grow and deals follow
+    a = common.choose_actions(None, mask, rng, False, 5, 5)
+    low = (mask[:, :2 * (5 if players < 4 else 4)] * rng.random((n, 2 * (5 if players < 4 else 4)))).argmax(axis=1)
+    use_low = (mask[:, :2 * (5 if players < 4 else 4)].sum(axis=1) > 0) & (rng.random(n) < 0.6)
+    a = np.where(use_low, low, a).astype(np.int32)
+    obs, reward, done, _ = env.step(torch.as_tensor(a, device=env.device))
+    for i in sorted(alive):
+      _, r, d, _ = singles[i].step(int(a[i]))
+      assert r == int(reward[i]) and d == bool(done[i])
+      if d:
+        alive.discard(i)
+    if not alive:
+      break
+  assert saw_discards >= 4
+
+
 @pytest.mark.parametrize("players", [2, 4])
 def test_exported_game_gives_the_reference_observation_dict(players):
   """BatchedHanabiEnv.game_observations(i) against the single-game HanabiEnv (same seed,
@@ -246,10 +300,11 @@ def test_exported_game_gives_the_reference_observation_dict(players):
             assert pg[key] == pw[key], (i, t, key)
       cur = got["current_player"]
       assert got["player_observations"][cur]["vectorized"] == obs["vectorized"][i].cpu().tolist()
-      # the newest entry of last_moves is the last player move (deals are not kept)
+      # without the history ring the newest player move (and the deal after it) is kept
       moves = [m for m in want["player_observations"][cur]["pyhanabi"].last_moves()
                if m.move().type() != 5]
-      mine = got["player_observations"][cur]["pyhanabi"].last_moves()
+      mine = [m for m in got["player_observations"][cur]["pyhanabi"].last_moves()
+              if m.move().type() != 5]
       if moves:
         assert str(mine[0].move()) == str(moves[0].move()) and mine[0].player() == moves[0].player()
         assert mine[0].scored() == moves[0].scored()
