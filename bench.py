@@ -75,6 +75,9 @@ def parse_args():
                   help="rainbow policy: run the whole actor loop -- the device recorder keeps every "
                        "seat's episode and appends finished episodes to a device replay memory")
   ap.add_argument("--replay-capacity", type=int, default=1 << 22)
+  ap.add_argument("--graph-steps", type=int, default=0,
+                  help="rainbow / adhoc (all rows) policies: env steps captured per CUDA graph "
+                       "(0 = 1, or 8 below 32768 games per GPU where the step is launch-bound)")
   ap.add_argument("--no-graph", action="store_true",
                   help="rainbow / adhoc (all rows) policies: launch every kernel of a step from the "
                        "host instead of replaying one captured CUDA graph per step")
@@ -614,6 +617,16 @@ def gpu_arm(args, ctx, extra):
     step_graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(step_graph, stream=torch.cuda.current_stream()):
       one_step(0)
+    # several steps per graph where the step is launch-bound (nothing in a captured step depends
+    # on the step number: greedy select, stateless agents)
+    graph_steps = args.graph_steps if args.graph_steps > 0 else (8 if n < 32768 else 1)
+    multi_graph = None
+    if graph_steps > 1:
+      multi_graph = torch.cuda.CUDAGraph()
+      with torch.cuda.graph(multi_graph, stream=torch.cuda.current_stream()):
+        for _ in range(graph_steps):
+          one_step(0)
+      multi_graph.replay()
     for _ in range(3):
       step_graph.replay()
     stats.zero_()
@@ -656,8 +669,14 @@ def gpu_arm(args, ctx, extra):
       for st in streams:
         main_stream.wait_stream(st)
   elif use_graph:
-    for g_i in range(K):
-      step_graph.replay()
+    if multi_graph is not None:
+      for g_i in range(K // graph_steps):
+        multi_graph.replay()
+      for g_i in range(K % graph_steps):
+        step_graph.replay()
+    else:
+      for g_i in range(K):
+        step_graph.replay()
   else:
     for t in range(K):
       select(W + t)
@@ -943,6 +962,7 @@ def gpu_arm(args, ctx, extra):
                                 "the games whose player to act is seat 0 (gathered rows)")
                              if args.policy == "adhoc" else "")),
                  "cuda_graph": bool(use_graph),
+                 "graph_steps": (graph_steps if use_graph else None),
                  "auto_reset": True, "seeds": "1 + global game index",
                  "l2": "outputs per step (%.0f MB) exceed the 126 MB L2" % (n * (D + A) / 1e6),
                  "parallelism": "games sharded over %d GPU(s), no step-path collective" % world +
