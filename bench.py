@@ -787,8 +787,11 @@ def gpu_arm(args, ctx, extra):
                    "note": "one synchronous BatchStepEncodeHost call per step, host policy before it"}
     # pipelined form of the same step (BatchStepEncodeHostRange + BatchHostWait): the games go
     # through in ranges; the host policy of range c runs while the transfers of range c-1 are
-    # on the link.  Every step still uploads every action and downloads every observation,
-    # mask, reward, done flag and player index into the host buffers.
+    # on the link.  Every step still uploads every action and delivers every observation,
+    # mask, reward, done flag and player index into the host buffers.  Measured with both
+    # forms of the link (BatchSetHostLink): packed = the library's default, the observation
+    # rows cross PCIe bit-packed and the host worker pool expands them into h_obs inside
+    # BatchHostWait; bytes = the kernel's uint8 rows cross the link as they are.
     launch, wait = hb.bind_step_encode_host_range(h_act, h_rew, h_done, h_obs, h_mask, h_cur)
     n_ranges = 16 if ne >= (1 << 19) else 8
     rs = (ne // n_ranges + 127) // 128 * 128
@@ -802,23 +805,32 @@ def gpu_arm(args, ctx, extra):
         pol(t)
         launch(lo, cnt)
 
+    def timed_piped(packed_link, steps, t_base):
+      wait(-1)
+      hb.set_host_link(packed_link)
+      for t in range(3):
+        piped_step(t_base + t)
+      wait(-1)
+      if dist:
+        dist.barrier()
+      t0 = time.perf_counter()
+      for t in range(steps):
+        piped_step(t_base + 3 + t)
+      wait(-1)
+      own = time.perf_counter() - t0
+      worst = own
+      if dist:
+        tm = torch.tensor([own], dtype=torch.float64, device=dev)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        worst = float(tm.item())
+      return own, worst
+
     e2e_steps = 3 * args.e2e_steps
-    for t in range(3):
-      piped_step(100 + t)
-    wait(-1)
-    if dist:
-      dist.barrier()
-    t0 = time.perf_counter()
-    for t in range(e2e_steps):
-      piped_step(103 + t)
-    wait(-1)
-    dt = time.perf_counter() - t0
-    own_dt = dt
-    if dist:
-      tm = torch.tensor([dt], dtype=torch.float64, device=dev)
-      dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-      dt = float(tm.item())
-    d2h = ne * (D + A + 4 + 1 + 4)
+    own_b, dt_b = timed_piped(False, e2e_steps, 100)
+    own_dt, dt = timed_piped(True, e2e_steps, 1000)
+    Wp = hb.packed_words
+    d2h_bytes = ne * (D + A + 4 + 1 + 4)          # bytes delivered to the host buffers / on the link as bytes
+    d2h_packed = ne * (4 * Wp + A + 4 + 1 + 4)    # on the link with packed rows
     # what one large pinned copy reaches on this box, for comparison
     probe_d = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     probe_h = torch.empty(256 << 20, dtype=torch.uint8).pin_memory()
@@ -829,17 +841,32 @@ def gpu_arm(args, ctx, extra):
       torch.cuda.synchronize()
       best = max(best, probe_d.numel() / (c0.elapsed_time(c1) * 1e-3) / 1e9)
     del probe_d, probe_h
+    bytes_link = {"value": world * ne * e2e_steps / dt_b, "unit": "env-steps/s",
+                  "ms_per_step": dt_b / e2e_steps * 1e3, "d2h_bytes_per_step": d2h_bytes,
+                  "d2h_gbs_achieved": d2h_bytes * e2e_steps / own_b / 1e9,
+                  "note": "BatchSetHostLink(0): the kernel's uint8 rows cross the link; bound by the "
+                          "observation download"}
     e2e = {"value": world * ne * e2e_steps / dt, "unit": "env-steps/s",
-           "h2d_bytes_per_step": ne * 4, "d2h_bytes_per_step": d2h,
+           "h2d_bytes_per_step": ne * 4, "d2h_bytes_per_step": d2h_packed,
+           "host_bytes_delivered_per_step": d2h_bytes,
            "games_per_step": ne, "steps": e2e_steps,
            "ms_per_step": dt / e2e_steps * 1e3,
-           "pcie": {"d2h_gbs_achieved": d2h * e2e_steps / own_dt / 1e9, "d2h_gbs_one_large_memcpy": best,
-                    "note": "this rank's link; the step is bound by the observation download"},
+           "link": "packed (library default): %d B of bit-packed row per game on PCIe instead of %d B, "
+                   "expanded into the caller's uint8 rows by the host worker pool inside BatchHostWait"
+                   % (4 * Wp, D),
+           "pcie": {"d2h_gbs_achieved": d2h_packed * e2e_steps / own_dt / 1e9,
+                    "d2h_gbs_one_large_memcpy": best,
+                    "host_rows_gbs": ne * D * e2e_steps / own_dt / 1e9,
+                    "note": "this rank's link; with packed rows the step is bound by the host's "
+                            "expansion + policy threads, not by the link"},
            "host_policy_threads": ph.host_policy_threads(),
            "host_cores_of_rank0": ctx.get("cores"),
            "note": "BatchStepEncodeHostRange/BatchHostWait with pinned host buffers, %d ranges per "
                    "step; host random-legal policy (persistent worker pool) inside the timed region, "
-                   "overlapping the transfers of the previous range" % len(ranges),
+                   "overlapping the transfers of the previous range; uint8 observation rows, legal "
+                   "mask, reward, done, player index of every game delivered to host memory every "
+                   "step" % len(ranges),
+           "bytes_link": bytes_link,
            "single_call": single_call}
     del hb
 

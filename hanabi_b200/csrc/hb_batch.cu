@@ -834,6 +834,13 @@ struct Batch {
   cudaEvent_t range_events[kRangeSlots] = {};
   int64_t range_first[kRangeSlots] = {};
   int range_next = 0;
+  // packed link (BatchSetHostLink): byte rows requested by the caller travel bit-packed and are
+  // expanded by the host worker pool when the range is waited for
+  int host_link = -1;  // -1: HANABI_B200_HOST_LINK or the default, 0: byte rows on the link, 1: packed rows
+  uint8_t* h_stage = nullptr;  // pinned host staging of the packed rows, N rows + pad
+  int64_t range_count[kRangeSlots] = {};
+  uint8_t* range_obs[kRangeSlots] = {};    // non-null: the slot's rows still have to be expanded
+  int64_t range_pitch[kRangeSlots] = {};
   // device staging for the host-buffer entry point, allocated on first use
   int32_t* d_actions = nullptr;
   int32_t* d_rewards = nullptr;
@@ -1075,6 +1082,7 @@ void DeleteBatch(pyhanabi_batch_t* h) {
     if (b->range_events[i]) cudaEventDestroy(b->range_events[i]);
   cudaFree(b->d_actions); cudaFree(b->d_rewards); cudaFree(b->d_scores); cudaFree(b->d_cur);
   cudaFree(b->d_dones); cudaFree(b->d_obs); cudaFree(b->d_mask);
+  if (b->h_stage) cudaFreeHost(b->h_stage);
   cudaFree(b->state);
   cudaFree(b->mt);
   cudaFree(b->own_stats);
@@ -1262,14 +1270,43 @@ static int HostSetup(Batch* b) {
   return 0;
 }
 
+// Packed link: whether byte rows asked for by the caller cross PCIe bit-packed (and are expanded
+// by the host worker pool, HostExpandPacked) or as the bytes the kernel's own expansion writes.
+// Default: packed -- the link carries 5.5x fewer bytes per Full-2p game (131 B instead of 720 B),
+// and the expansion runs on the pool while the next ranges are on the link.
+static bool UsePackedLink(Batch* b) {
+  if (b->host_link < 0) {
+    const char* env = std::getenv("HANABI_B200_HOST_LINK");
+    b->host_link = env ? (std::strcmp(env, "bytes") == 0 || std::strcmp(env, "0") == 0 ? 0 : 1) : 1;
+  }
+  return b->host_link == 1;
+}
+static int LinkSetup(Batch* b) {
+  if (b->h_stage) return 0;
+  const size_t row = (size_t)b->packed_words * sizeof(uint32_t);
+  HB_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&b->h_stage), (size_t)b->N * row + 64, cudaHostAllocDefault));
+  return 0;
+}
+// Rows [g0, g1) of the pinned staging -> the caller's byte rows.
+static int ExpandRange(Batch* b, size_t g0, size_t g1, uint8_t* obs, int64_t row_pitch) {
+  const size_t row = (size_t)b->packed_words * sizeof(uint32_t);
+  return HostExpandPacked(reinterpret_cast<const uint32_t*>(b->h_stage + g0 * row), b->packed_words,
+                          b->spec.obs_size, (int64_t)(g1 - g0), obs + g0 * (size_t)row_pitch, row_pitch, 0);
+}
+
 // Enqueues games [g0, g1) on stream s: action upload, the fused kernel, result download.
 // The host pointers are the bases of the whole arrays (indexed by game).
 static int EnqueueHostRange(Batch* b, size_t g0, size_t g1, const int32_t* actions, int32_t* rewards,
                             uint8_t* dones, int32_t* scores, uint8_t* obs, int64_t row_pitch,
                             uint32_t* obs_bits, uint8_t* mask, int32_t* cur_player, int auto_reset,
-                            cudaStream_t s) {
+                            cudaStream_t s, bool packed_link = false) {
   const int D = b->spec.obs_size, A = b->spec.max_moves;
   const size_t n = g1 - g0;
+  if (packed_link && obs) {
+    // the caller's byte rows are produced on the host from the packed rows (ExpandRange)
+    obs = nullptr;
+    obs_bits = reinterpret_cast<uint32_t*>(b->h_stage);
+  }
   HB_CUDA(cudaMemcpyAsync(b->d_actions + g0, actions + g0, n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
   hb::KArgs a = BaseArgs(b);
   a.g_begin = (int64_t)g0; a.g_end = (int64_t)g1;
@@ -1307,17 +1344,31 @@ static int StepHost(pyhanabi_batch_t* h, const int32_t* actions, int32_t* reward
   const size_t N = (size_t)b->N;
   if (HostSetup(b)) return 1;
   HB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  const bool link = obs && UsePackedLink(b);
+  if (link && LinkSetup(b)) return 1;
   int nchunks = (int)((N + 32767) / 32768);
   if (nchunks > 12) nchunks = 12;
   if (nchunks < 1) nchunks = 1;
   size_t cs = (N + nchunks - 1) / nchunks;
   cs = (cs + 127) / 128 * 128;
   int c = 0;
+  cudaEvent_t* ev = b->range_events;  // (synchronous call: the ranged slots are free to borrow)
+  if (BatchHostWait(h, -1)) return 1;  // ranged work still in flight (and its pending expansions) first
   for (size_t g0 = 0; g0 < N; g0 += cs, ++c) {
     const size_t g1 = g0 + cs < N ? g0 + cs : N;
     if (EnqueueHostRange(b, g0, g1, actions, rewards, dones, scores, obs, row_pitch, obs_bits, mask,
-                         cur_player, auto_reset, b->h_streams[c % 3]))
+                         cur_player, auto_reset, b->h_streams[c % 3], link))
       return 1;
+    if (link) HB_CUDA(cudaEventRecord(ev[c], b->h_streams[c % 3]));
+  }
+  if (link) {
+    // the pool expands chunk c while the later chunks are still on the link
+    c = 0;
+    for (size_t g0 = 0; g0 < N; g0 += cs, ++c) {
+      const size_t g1 = g0 + cs < N ? g0 + cs : N;
+      HB_CUDA(cudaEventSynchronize(ev[c]));
+      if (ExpandRange(b, g0, g1, obs, row_pitch)) return 1;
+    }
   }
   for (int i = 0; i < 3; ++i) HB_CUDA(cudaStreamSynchronize(b->h_streams[i]));
   return 0;
@@ -1339,16 +1390,32 @@ static int StepHostRange(pyhanabi_batch_t* h, int64_t first_game, int64_t num_ga
   if (first_game < 0 || num_games <= 0 || first_game + num_games > b->N || (first_game & 127))
     return Fail("BatchStepEncodeHostRange: range must lie in the batch and start at a multiple of 128");
   if (HostSetup(b)) return 1;
+  const bool link = obs && UsePackedLink(b);
+  if (link && LinkSetup(b)) return 1;
+  // a range queued again before anybody waited for it: its earlier rows are superseded
+  for (int i = 0; i < Batch::kRangeSlots; ++i)
+    if (b->range_obs[i] && b->range_first[i] == first_game) b->range_obs[i] = nullptr;
   const int slot = b->range_next++ % Batch::kRangeSlots;
+  if (b->range_obs[slot]) {
+    // the ring wrapped around a range nobody waited for: deliver it before its slot is reused
+    HB_CUDA(cudaEventSynchronize(b->range_events[slot]));
+    if (ExpandRange(b, (size_t)b->range_first[slot], (size_t)(b->range_first[slot] + b->range_count[slot]),
+                    b->range_obs[slot], b->range_pitch[slot]))
+      return 1;
+    b->range_obs[slot] = nullptr;
+  }
   // a range always runs on the same internal stream (chosen by its first game), so consecutive
   // steps of one range are ordered by that stream even if the caller skips BatchHostWait;
   // ranges must not overlap other ranges that are still in flight
   cudaStream_t s = b->h_streams[(first_game >> 7) % 3];
   if (EnqueueHostRange(b, (size_t)first_game, (size_t)(first_game + num_games), actions, rewards, dones,
-                       scores, obs, row_pitch, obs_bits, mask, cur_player, auto_reset, s))
+                       scores, obs, row_pitch, obs_bits, mask, cur_player, auto_reset, s, link))
     return 1;
   HB_CUDA(cudaEventRecord(b->range_events[slot], s));
   b->range_first[slot] = first_game;
+  b->range_count[slot] = num_games;
+  b->range_obs[slot] = link ? obs : nullptr;
+  b->range_pitch[slot] = row_pitch;
   return 0;
 }
 
@@ -1374,19 +1441,48 @@ int BatchStepEncodeHostRangePacked(pyhanabi_batch_t* h, int64_t first_game, int6
 int BatchHostWait(pyhanabi_batch_t* h, int64_t first_game) {
   HB_BATCH(h);
   if (!b->h_streams[0]) return 0;
+  // packed link: the slot's byte rows are expanded here, on the worker pool, once its packed
+  // rows have arrived
+  auto deliver = [&](int slot) -> int {
+    HB_CUDA(cudaEventSynchronize(b->range_events[slot]));
+    if (b->range_obs[slot]) {
+      uint8_t* obs = b->range_obs[slot];
+      b->range_obs[slot] = nullptr;
+      if (ExpandRange(b, (size_t)b->range_first[slot], (size_t)(b->range_first[slot] + b->range_count[slot]),
+                      obs, b->range_pitch[slot]))
+        return 1;
+    }
+    return 0;
+  };
   if (first_game < 0) {
+    // oldest first, so that the pool works on rows that have arrived while the rest still travels
+    for (int k = Batch::kRangeSlots; k >= 1; --k) {
+      if (b->range_next - k < 0) continue;
+      const int slot = (b->range_next - k) % Batch::kRangeSlots;
+      if (b->range_obs[slot] && deliver(slot)) return 1;
+    }
     for (int i = 0; i < 3; ++i) HB_CUDA(cudaStreamSynchronize(b->h_streams[i]));
     return 0;
   }
   for (int k = 1; k <= Batch::kRangeSlots; ++k) {  // newest first
     if (b->range_next - k < 0) break;
     const int slot = (b->range_next - k) % Batch::kRangeSlots;
-    if (b->range_first[slot] == first_game) {
-      HB_CUDA(cudaEventSynchronize(b->range_events[slot]));
-      return 0;
-    }
+    if (b->range_first[slot] == first_game) return deliver(slot);
   }
   return 0;  // nothing queued for that range
+}
+
+// 1: byte rows of the host entry points cross the link bit-packed and are expanded on the host
+// (default), 0: they cross as bytes.  Not while ranges are in flight.
+int BatchSetHostLink(pyhanabi_batch_t* h, int packed) {
+  HB_BATCH(h);
+  if (BatchHostWait(h, -1)) return 1;
+  b->host_link = packed ? 1 : 0;
+  return 0;
+}
+int BatchGetHostLink(pyhanabi_batch_t* h) {
+  HB_BATCH(h);
+  return UsePackedLink(b) ? 1 : 0;
 }
 
 int BatchStepEncodeHost(pyhanabi_batch_t* h, const int32_t* actions, int32_t* rewards,

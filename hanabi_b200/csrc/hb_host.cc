@@ -10,6 +10,9 @@
 // HANABI_B200_HOST_THREADS says otherwise, spin briefly for the next job and
 // then sleep on a condition variable.
 #include <sched.h>
+#if defined(__x86_64__)
+#include <immintrin.h>
+#endif
 #include <stdint.h>
 
 #include <atomic>
@@ -186,5 +189,172 @@ int HostRandomLegalActions(const uint8_t* mask, int n, int num_actions, uint64_t
 }
 
 int HostPolicyThreads(void) { return HostPool::Get().size(); }
+
+}  // extern "C"
+
+// ------------------------------------------------------- packed rows -> bytes
+// The host half of the "packed link" transfer (BatchSetHostLink): the step kernel's
+// bit-packed observation rows cross PCIe (96 B instead of 658 B per Full-2p game) and
+// the worker pool turns them into the caller's uint8 rows of 0/1 -- the same bytes the
+// kernel's own expansion would have written, with 6.9 x fewer bytes on the link.
+namespace {
+
+// Eight bits -> eight bytes of 0/1 (byte i = bit i), portable form.
+inline uint64_t Bits8ToBytes(uint32_t b8) {
+  uint64_t x = ((uint64_t)(b8 & 0xffu) * 0x0101010101010101ull) & 0x8040201008040201ull;
+  return ((x + 0x7f7f7f7f7f7f7f7full) >> 7) & 0x0101010101010101ull;
+}
+
+// 64 bits of row `row` from bit `bit` on (bits beyond the buffer read as zero).
+inline uint64_t LoadBits(const uint8_t* rows, int64_t total_bytes, int64_t row_off, int bit) {
+  const int64_t at = row_off + (bit >> 3);
+  uint64_t w = 0;
+  if (at + 8 <= total_bytes) std::memcpy(&w, rows + at, 8);
+  else if (at < total_bytes) std::memcpy(&w, rows + at, (size_t)(total_bytes - at));
+  return w >> (bit & 7);  // >= 57 valid bits
+}
+
+// Bits [pos, pos + 32) of the dense bit stream "row r = bits [r * dim, (r + 1) * dim)",
+// read from rows of row_bytes bytes; a chunk may straddle two rows (dim >= 32).
+inline uint32_t StreamBits32(const uint8_t* rows, int64_t total_bytes, int row_bytes, int dim,
+                             int64_t r, int bit) {
+  uint64_t w = LoadBits(rows, total_bytes, r * row_bytes, bit);
+  const int avail = dim - bit;
+  if (avail < 32) {
+    const uint64_t next = LoadBits(rows, total_bytes, (r + 1) * row_bytes, 0);
+    w = (w & ((1ull << avail) - 1ull)) | (next << avail);
+  }
+  return (uint32_t)w;
+}
+
+void ExpandDenseScalar(const uint8_t* rows, int64_t total_bytes, int row_bytes, int dim,
+                       uint8_t* out, int64_t lo, int64_t hi) {
+  // bytes [lo, hi) of the dense output; byte j = bit j % dim of row j / dim
+  int64_t r = lo / dim;
+  int bit = (int)(lo - r * dim);
+  int64_t j = lo;
+  while (j < hi) {
+    int run = dim - bit;
+    if ((int64_t)run > hi - j) run = (int)(hi - j);
+    int done = 0;
+    while (done + 8 <= run) {
+      const uint64_t v = Bits8ToBytes((uint32_t)LoadBits(rows, total_bytes, r * row_bytes, bit + done));
+      std::memcpy(out + j + done, &v, 8);
+      done += 8;
+    }
+    if (done < run) {
+      const uint64_t v = Bits8ToBytes((uint32_t)LoadBits(rows, total_bytes, r * row_bytes, bit + done));
+      std::memcpy(out + j + done, &v, (size_t)(run - done));
+    }
+    j += run;
+    bit += run;
+    if (bit == dim) { bit = 0; ++r; }
+  }
+}
+
+#if defined(__x86_64__)
+// Aligned 32-byte chunks [lo, hi) (both multiples of 32, out + lo 32-byte aligned) with
+// non-temporal stores: the rows are written once and read by somebody else, so they
+// should not be read for ownership nor displace the caller's working set.
+__attribute__((target("avx2"))) void ExpandDenseAvx2(const uint8_t* rows, int64_t total_bytes,
+                                                    int row_bytes, int dim, uint8_t* out,
+                                                    int64_t lo, int64_t hi) {
+  const __m256i shuf = _mm256_setr_epi8(0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 1, 1, 1,
+                                        2, 2, 2, 2, 2, 2, 2, 2, 3, 3, 3, 3, 3, 3, 3, 3);
+  const __m256i bitm = _mm256_set1_epi64x((long long)0x8040201008040201ull);
+  const __m256i ones = _mm256_set1_epi8(1);
+  int64_t r = lo / dim;
+  int bit = (int)(lo - r * dim);
+  for (int64_t j = lo; j < hi; j += 32) {
+    const uint32_t bits = StreamBits32(rows, total_bytes, row_bytes, dim, r, bit);
+    __m256i v = _mm256_shuffle_epi8(_mm256_set1_epi32((int)bits), shuf);
+    v = _mm256_min_epu8(_mm256_and_si256(v, bitm), ones);
+    _mm256_stream_si256(reinterpret_cast<__m256i*>(out + j), v);
+    bit += 32;
+    if (bit >= dim) { bit -= dim; ++r; }
+  }
+  _mm_sfence();
+}
+bool HaveAvx2() {
+  static const bool have = __builtin_cpu_supports("avx2");
+  return have;
+}
+#else
+bool HaveAvx2() { return false; }
+void ExpandDenseAvx2(const uint8_t*, int64_t, int, int, uint8_t*, int64_t, int64_t) {}
+#endif
+
+}  // namespace
+
+extern "C" {
+
+// Bit-packed observation rows (HOST, packed_words 32-bit words per row, bit j of a row =
+// observation bit j; what BatchStepEncodeHostPacked delivers) -> HOST rows of obs_size
+// bytes of 0/1, row_pitch bytes apart: the CPU twin of the step kernel's byte expansion,
+// on the worker pool.  `threads` <= 0 uses the pool's size.
+int HostExpandPacked(const uint32_t* obs_bits, int packed_words, int obs_size, int64_t n,
+                     uint8_t* out, int64_t row_pitch, int threads) {
+  if (!obs_bits || !out || n < 0 || packed_words <= 0 || obs_size <= 0 ||
+      obs_size > packed_words * 32 || row_pitch < obs_size)
+    return HbFail("HostExpandPacked: bad argument");
+  if (n == 0) return 0;
+  HostPool& pool = HostPool::Get();
+  if (threads <= 0 || threads > pool.size()) threads = pool.size();
+  const uint8_t* rows = reinterpret_cast<const uint8_t*>(obs_bits);
+  const int row_bytes = packed_words * 4;
+  const int64_t total_bytes = n * (int64_t)row_bytes;
+  if (row_pitch == obs_size && obs_size >= 64) {
+    // dense rows: one contiguous byte range, cut into 32-byte aligned spans
+    const int64_t total = n * (int64_t)obs_size;
+    int parts = threads;
+    if ((int64_t)parts * (1 << 16) > total) parts = (int)(total >> 16) > 0 ? (int)(total >> 16) : 1;
+    const uintptr_t base = reinterpret_cast<uintptr_t>(out);
+    const std::function<void(int)> work = [=](int t) {
+      // span [lo, hi) with both ends rounded to 32-byte aligned ADDRESSES (except the outer ends)
+      auto cut = [&](int k) -> int64_t {
+        if (k <= 0) return 0;
+        if (k >= parts) return total;
+        const int64_t c = total * k / parts;
+        int64_t a = c - (int64_t)((base + (uintptr_t)c) & 31u);
+        return a < 0 ? 0 : a;
+      };
+      const int64_t lo = cut(t), hi = cut(t + 1);
+      if (lo >= hi) return;
+      int64_t a_lo = lo + (int64_t)((32u - ((base + (uintptr_t)lo) & 31u)) & 31u);
+      if (a_lo > hi) a_lo = hi;
+      const int64_t a_hi = a_lo + ((hi - a_lo) & ~(int64_t)31);
+      if (HaveAvx2() && a_hi > a_lo) {
+        ExpandDenseScalar(rows, total_bytes, row_bytes, obs_size, out, lo, a_lo);
+        ExpandDenseAvx2(rows, total_bytes, row_bytes, obs_size, out, a_lo, a_hi);
+        ExpandDenseScalar(rows, total_bytes, row_bytes, obs_size, out, a_hi, hi);
+      } else {
+        ExpandDenseScalar(rows, total_bytes, row_bytes, obs_size, out, lo, hi);
+      }
+    };
+    pool.Run(parts, work);
+    return 0;
+  }
+  // padded rows: row by row
+  int parts = threads;
+  if ((int64_t)parts * 256 > n) parts = (int)(n / 256) > 0 ? (int)(n / 256) : 1;
+  const std::function<void(int)> work = [=](int t) {
+    const int64_t lo = n * t / parts, hi = n * (t + 1) / parts;
+    for (int64_t g = lo; g < hi; ++g) {
+      uint8_t* dst = out + g * row_pitch;
+      int done = 0;
+      while (done + 8 <= obs_size) {
+        const uint64_t v = Bits8ToBytes((uint32_t)LoadBits(rows, total_bytes, g * row_bytes, done));
+        std::memcpy(dst + done, &v, 8);
+        done += 8;
+      }
+      if (done < obs_size) {
+        const uint64_t v = Bits8ToBytes((uint32_t)LoadBits(rows, total_bytes, g * row_bytes, done));
+        std::memcpy(dst + done, &v, (size_t)(obs_size - done));
+      }
+    }
+  };
+  pool.Run(parts, work);
+  return 0;
+}
 
 }  // extern "C"

@@ -993,6 +993,15 @@ class HanabiBatch(object):
         raise RuntimeError("BatchHostWait failed: %s" % encode_ffi_string(lib.BatchLastError()))
     return launch, wait
 
+  def set_host_link(self, packed):
+    """True (default): the uint8 rows of the host entry points cross PCIe bit-packed and are
+    expanded by the host worker pool; False: they cross as bytes (BatchSetHostLink)."""
+    _check(lib.BatchSetHostLink(self._c, int(bool(packed))), "BatchSetHostLink")
+
+  @property
+  def host_link_packed(self):
+    return bool(lib.BatchGetHostLink(self._c))
+
   def reset_host(self, obs=None, mask=None, cur_player=None):
     torch = self._torch
     n = self.num_games
@@ -1309,6 +1318,26 @@ def bind_host_random_legal_actions(mask, seed, out, first_game=0, threads=0):
     if _fn(*(_head + (step,) + _tail)) != 0:
       raise RuntimeError("HostRandomLegalActions failed: %s" % encode_ffi_string(lib.BatchLastError()))
   return run
+
+
+def host_expand_packed(obs_bits, obs_size, out=None, threads=0):
+  """Bit-packed observation rows (CPU int32 [n, packed_words]) -> CPU uint8 rows of 0/1
+  ([n, >= obs_size]) on the host worker pool: the CPU twin of the step kernel's byte
+  expansion (HostExpandPacked), what the packed host link runs behind BatchHostWait."""
+  import torch
+  _require_lib()
+  if obs_bits.is_cuda or obs_bits.dtype != torch.int32 or obs_bits.dim() != 2 or not obs_bits.is_contiguous():
+    raise ValueError("obs_bits must be a contiguous CPU int32 [n, packed_words] tensor")
+  n, words = int(obs_bits.shape[0]), int(obs_bits.shape[1])
+  if out is None:
+    out = torch.empty((n, int(obs_size)), dtype=torch.uint8)
+  if (out.is_cuda or out.dtype != torch.uint8 or out.dim() != 2 or out.stride(1) != 1 or
+      out.shape[0] < n or out.shape[1] < obs_size):
+    raise ValueError("out must be a CPU uint8 [n, >= obs_size] tensor")
+  _check(lib.HostExpandPacked(ffi.cast("uint32_t*", obs_bits.data_ptr()), words, int(obs_size), n,
+                              ffi.cast("uint8_t*", out.data_ptr()), int(out.stride(0)), int(threads)),
+         "HostExpandPacked")
+  return out
 
 
 def host_policy_threads():

@@ -311,6 +311,20 @@ int BatchStepEncodeHostRangePacked(pyhanabi_batch_t* batch, int64_t first_game,
                                    uint8_t* dones, int32_t* scores, uint32_t* obs_bits,
                                    uint8_t* mask, int32_t* cur_player, int auto_reset);
 int BatchHostWait(pyhanabi_batch_t* batch, int64_t first_game);
+/* How the uint8 observation rows of the four host entry points above cross PCIe.
+   1 (default; HANABI_B200_HOST_LINK=bytes selects 0): the kernel writes bit-packed rows,
+   those are downloaded (96 B instead of 658 B per Hanabi-Full 2p game) into a pinned
+   staging buffer of the batch, and the host worker pool expands them into the caller's
+   rows -- inside BatchStepEncodeHost, or inside BatchHostWait for the ranged form, while
+   later ranges are still on the link.  0: the kernel expands, the bytes cross the link.
+   The caller's buffers hold the same bytes either way. */
+int BatchSetHostLink(pyhanabi_batch_t* batch, int packed);
+int BatchGetHostLink(pyhanabi_batch_t* batch);
+/* Bit-packed rows (HOST; what BatchStepEncodeHostPacked delivers: packed_words 32-bit
+   words per row, bit j of a row = observation bit j) -> HOST rows of obs_size bytes of
+   0/1, row_pitch bytes apart, on the host worker pool (threads <= 0: all of it). */
+int HostExpandPacked(const uint32_t* obs_bits, int packed_words, int obs_size, int64_t n,
+                     uint8_t* out, int64_t row_pitch, int threads);
 int BatchResetHost(pyhanabi_batch_t* batch, uint8_t* obs, int64_t row_pitch, uint8_t* mask,
                    int32_t* cur_player, void* stream);
 

@@ -39,7 +39,10 @@ def test_batched_env_matches_reference_semantics():
   assert st["episodes"] > 0
 
 
-def test_host_buffer_entry_points_match_device_path():
+@pytest.mark.parametrize("packed_link", [True, False])
+def test_host_buffer_entry_points_match_device_path(packed_link):
+  """packed_link: the uint8 rows cross PCIe bit-packed and the host pool expands them
+  (BatchSetHostLink(1), the default) or cross as the kernel's bytes (0)."""
   import torch
   from hanabi_b200 import pyhanabi as ph
   n = 70000  # several chunks, ragged last tile
@@ -47,6 +50,9 @@ def test_host_buffer_entry_points_match_device_path():
   seeds = common.seeds_for(n, base=5)
   dev = ph.HanabiBatch(params, n, seeds)
   host = ph.HanabiBatch(params, n, seeds)
+  assert host.host_link_packed  # the default
+  host.set_host_link(packed_link)
+  assert host.host_link_packed == packed_link
   D, A = dev.obs_size, dev.max_moves
   cuda = torch.device("cuda:0")
   d_obs = torch.zeros((n, D), dtype=torch.uint8, device=cuda)
@@ -321,13 +327,17 @@ def test_exported_game_gives_the_reference_observation_dict(players):
       break
 
 
-def test_ranged_async_host_step_matches_the_synchronous_call():
+@pytest.mark.parametrize("links", [(False, True), (True, False), (True, True)])
+def test_ranged_async_host_step_matches_the_synchronous_call(links):
+  """links = (synchronous call, ranged calls): packed host link or bytes on the link."""
   import torch
   from hanabi_b200 import pyhanabi as ph
   n = 40000
   params = CONFIGS["full2"]
   seeds = common.seeds_for(n, base=77)
   a, b = ph.HanabiBatch(params, n, seeds), ph.HanabiBatch(params, n, seeds)
+  a.set_host_link(links[0])
+  b.set_host_link(links[1])
   D, A = a.obs_size, a.max_moves
   pin = lambda *shape, dt: torch.zeros(shape, dtype=dt).pin_memory()
   bufs = []

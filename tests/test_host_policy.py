@@ -73,3 +73,39 @@ def test_host_pool_survives_concurrent_callers(ph):
   for t in threads: t.join()
   assert not errors
   assert ph.host_policy_threads() >= 1
+
+
+# ---- HostExpandPacked: the host half of the packed link (hb_host.cc)
+@pytest.mark.parametrize("dim", [106, 171, 281, 308, 640, 658, 956, 1041, 1280])
+@pytest.mark.parametrize("n", [1, 2, 33, 4099])
+def test_host_expand_packed_matches_unpackbits(ph, dim, n):
+  import torch
+  words = (dim + 127) // 128 * 4
+  rng = np.random.default_rng(dim * 7 + n)
+  bits = rng.integers(0, 2, size=(n, dim), dtype=np.uint8)
+  padded = np.zeros((n, words * 32), dtype=np.uint8)
+  padded[:, :dim] = bits
+  padded[:, dim:] = rng.integers(0, 2, size=(n, words * 32 - dim), dtype=np.uint8)  # padding bits must not leak
+  packed = np.packbits(padded, axis=1, bitorder="little").view(np.int32).reshape(n, words)
+  t = torch.from_numpy(np.ascontiguousarray(packed))
+  # dense rows at every alignment of the first byte (streaming stores need aligned spans)
+  for shift in (0, 1, 2, 13, 31):
+    flat = torch.full((n * dim + 64,), 7, dtype=torch.uint8)
+    out = flat[shift:shift + n * dim].view(n, dim)
+    ph.host_expand_packed(t, dim, out=out)
+    assert (out.numpy() == bits).all()
+    assert (flat[:shift] == 7).all() and (flat[shift + n * dim:] == 7).all()
+  # padded rows
+  wide = torch.full((n, dim + 22), 9, dtype=torch.uint8)
+  ph.host_expand_packed(t, dim, out=wide)
+  assert (wide[:, :dim].numpy() == bits).all() and (wide[:, dim:] == 9).all()
+
+
+def test_host_expand_packed_large_dense_all_threads(ph):
+  import torch
+  dim, n = 658, 70000  # several 64 KB spans per worker
+  rng = np.random.default_rng(5)
+  padded = rng.integers(0, 2, size=(n, 768), dtype=np.uint8)
+  packed = np.packbits(padded, axis=1, bitorder="little").view(np.int32).reshape(n, 24)
+  out = ph.host_expand_packed(torch.from_numpy(np.ascontiguousarray(packed)), dim)
+  assert (out.numpy() == padded[:, :dim]).all()
