@@ -101,7 +101,8 @@ struct KArgs {
 // NET: the instantiation that also writes network-input rows (BatchStepEncodeNet /
 // BatchObserveNet); kept out of the plain kernels so that their code stays as small as it was.
 template <class V, int MODE, bool NET = false>
-__global__ void __launch_bounds__(V::kBlock, kResidentThreads / V::kBlock) k_main(const __grid_constant__ KArgs a) {
+__global__ void __launch_bounds__(V::kBlock, (V::kResident ? V::kResident : kResidentThreads) / V::kBlock)
+k_main(const __grid_constant__ KArgs a) {
   constexpr int kBlock = V::kBlock, kWarps = kBlock / 32;
   constexpr bool kJobs = V::kJobs;  // which re-deal machinery this rule set uses (hb_engine.cuh)
   // finished games (and flushes) a CTA works off through shared memory per launch; the rest
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__(V::kBlock, kResidentThreads / V::kBlock) k_mai
   __shared__ int s_nq;
   __shared__ int s_q_tid[kQueueCap];
   __shared__ uint32_t s_q_meta[kQueueCap];  // jobs: r0 | npend << 10 | nfresh << 14 | slow << 31; serial: mt index
-  __shared__ JobResult s_res[kQueueCap];
+  __shared__ HB_JOBRESULT(V) s_res[kQueueCap];
   constexpr int kItems = HB_ITEMS;  // job path: RNG word pairs per thread in flight in phase B
   __shared__ uint8_t s_qb[kJobs ? kItems * kBlock : 4];  // job path: draw indices of one pass
   __shared__ uint32_t s_spread[32];
@@ -153,7 +154,7 @@ __global__ void __launch_bounds__(V::kBlock, kResidentThreads / V::kBlock) k_mai
     if (threadIdx.x == 0) s_nq = 0;
   }
   __syncthreads();
-  Game G;
+  HB_GAME(V) G;
   Prefetch pre;
   pre.at = -1;
   bool moved_any = false, restarted = false;
@@ -371,7 +372,7 @@ __global__ void __launch_bounds__(V::kBlock, kResidentThreads / V::kBlock) k_mai
           if (!(meta >> 31) && nfresh > 0) {
             uint64_t deck = a.spec.full_deck;
             const uint8_t* qb = s_qb + threadIdx.x * tmax;
-            uint32_t hand = 0;
+            typename V::Word hand = 0;
             int pl = 0, slot_i = 0;
 #pragma unroll 1
             for (int d = 0; d < nfresh; ++d) {
@@ -379,7 +380,7 @@ __global__ void __launch_bounds__(V::kBlock, kResidentThreads / V::kBlock) k_mai
               deck &= ~(1ull << pos);
               int color, rank;
               card_of_position(v, pos, color, rank);
-              hand |= (uint32_t)(color | (rank << 3)) << (6 * slot_i);
+              hand |= (typename V::Word)(uint32_t)(color | (rank << 3)) << (6 * slot_i);
               if (++slot_i == H) {  // player 0's hand first, then player 1's, ... (PlayerToDeal)
                 s_res[e].cards[pl++] = hand;
                 hand = 0;
@@ -628,8 +629,9 @@ __global__ void k_blank(uint4* state, int64_t N, int ncols) {
 }
 
 // Packed state -> canonical unpacked dump (oracle/oracle_api.h layout).
-__device__ void unpack_one(const KArgs& a, int64_t g, int32_t* d, Game& G) {
-  const DView v(a.spec);
+template <class V>
+__device__ void unpack_one(const KArgs& a, int64_t g, int32_t* d, HB_GAME(V)& G) {
+  const V v(a.spec);
   load_game(a.state, a.N, g, v, G);
   for (int i = 0; i < kDumpLen; ++i) d[i] = 0;
   const int C = a.spec.C, R = a.spec.R;
@@ -642,9 +644,12 @@ __device__ void unpack_one(const KArgs& a, int64_t g, int32_t* d, Game& G) {
     if (p < a.spec.P) d[11 + p] = n;
     for (int i = 0; i < 8; ++i) {
       const bool have = i < n;
-      const uint32_t f = have ? G.cards[p] >> (6 * i) : 0;
+      // (narrow hand words hold five slots: shifts stay below the word size)
+      const bool slot = have && i < V::kH;
+      const uint32_t f = slot ? (uint32_t)(G.cards[p] >> (6 * (i < V::kH ? i : 0))) : 0;
       d[16 + p * 8 + i] = have ? (int)(f & 7) * R + (int)((f >> 3) & 7) : -1;
-      const int cm = have ? (G.cpl[p] >> (5 * i)) & 31 : 0, rm = have ? (G.rpl[p] >> (5 * i)) & 31 : 0;
+      const int cm = slot ? (int)(G.cpl[p] >> (5 * (i < V::kH ? i : 0))) & 31 : 0;
+      const int rm = slot ? (int)(G.rpl[p] >> (5 * (i < V::kH ? i : 0))) & 31 : 0;
       d[56 + p * 8 + i] = cm;
       d[96 + p * 8 + i] = rm;
       d[136 + p * 8 + i] = (have && ((G.hw[p] >> i) & 1)) ? 31 - __clz(cm) : -1;
@@ -661,18 +666,20 @@ __device__ void unpack_one(const KArgs& a, int64_t g, int32_t* d, Game& G) {
     }
 }
 
+template <class V>
 __global__ void k_unpack(KArgs a, int32_t* out) {
   const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= a.N) return;
-  Game G;
-  unpack_one(a, g, out + g * (int64_t)kDumpLen, G);
+  HB_GAME(V) G;
+  unpack_one<V>(a, g, out + g * (int64_t)kDumpLen, G);
 }
 
 // One game's dump plus what the dump does not carry (BatchExportGame).
+template <class V>
 __global__ void k_export(KArgs a, int64_t g, int32_t* out) {
   if (blockIdx.x != 0 || threadIdx.x != 0) return;
-  Game G;
-  unpack_one(a, g, out, G);
+  HB_GAME(V) G;
+  unpack_one<V>(a, g, out, G);
   out[kDumpLen + 0] = G.turns;
   out[kDumpLen + 1] = (int32_t)G.last;
   const uint4 h = a.hist ? a.hist[g] : make_uint4(0, 0, 0, 0);
@@ -707,11 +714,13 @@ __global__ void k_errors(uint4* state, int64_t N, int col, int word, int bit, ui
 // Canonical dump -> packed state (keeps each game's RNG position).  The dump does
 // not carry turns_to_play / last action; they arrive in `extra[g*2+{0,1}]`
 // (turns_to_play, packed last-action record or 0).
+template <class V>
 __global__ void k_pack(KArgs a, const int32_t* in, const int32_t* extra) {
+  typedef typename V::Word W;
   const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= a.N) return;
-  const DView v(a.spec);
-  Game G;
+  const V v(a.spec);
+  HB_GAME(V) G;
   load_game(a.state, a.N, g, v, G);
   const int32_t* d = in + g * (int64_t)kDumpLen;
   const int C = a.spec.C, R = a.spec.R;
@@ -725,9 +734,9 @@ __global__ void k_pack(KArgs a, const int32_t* in, const int32_t* extra) {
     G.hw[p] = (uint32_t)n << 16;
     for (int i = 0; i < n; ++i) {
       const int id = d[16 + p * 8 + i];
-      G.cards[p] |= (uint32_t)((id / R) | ((id % R) << 3)) << (6 * i);
-      G.cpl[p] |= (uint32_t)d[56 + p * 8 + i] << (5 * i);
-      G.rpl[p] |= (uint32_t)d[96 + p * 8 + i] << (5 * i);
+      G.cards[p] |= (W)(uint32_t)((id / R) | ((id % R) << 3)) << (6 * i);
+      G.cpl[p] |= (W)(uint32_t)d[56 + p * 8 + i] << (5 * i);
+      G.rpl[p] |= (W)(uint32_t)d[96 + p * 8 + i] << (5 * i);
       if (d[136 + p * 8 + i] >= 0) G.hw[p] |= 1u << i;
       if (d[176 + p * 8 + i] >= 0) G.hw[p] |= 1u << (8 + i);
     }
@@ -985,6 +994,7 @@ cudaError_t Launch(const Batch* b, const hb::KArgs& a, cudaStream_t stream) {
     HB_CASE(2, 2, 1, 5, 3, 1)  // Hanabi-Very-Small 2p
 #undef HB_CASE
   }
+  if (s.H > hb::kMaxHandNarrow) return LaunchOne<hb::WView, MODE>(b, a, stream);  // hands of 6-8 cards
   return LaunchOne<hb::DView, MODE>(b, a, stream);
 }
 
@@ -1022,7 +1032,7 @@ int NewBatch(pyhanabi_batch_t* out, int list_length, const char** param_list, in
   }
   b->device = device;
   b->N = num_games;
-  b->ncols = hb::state_columns(b->spec.P);
+  b->ncols = b->spec.H > hb::kMaxHandNarrow ? hb::state_columns_wide(b->spec.P) : hb::state_columns(b->spec.P);
   b->packed_words = 4 * ((b->spec.obs_size + 127) / 128);
   b->obs_stream_words = b->spec.obs_size > 32 * b->packed_words ? b->spec.obs_size : 32 * b->packed_words;
   b->obs_stream_words = (b->obs_stream_words + 3) & ~3;
@@ -1678,7 +1688,8 @@ int BatchUnpackState(pyhanabi_batch_t* h, int32_t* dump, void* stream) {
   if (!dump) return Fail("BatchUnpackState: dump is null");
   hb::KArgs a = BaseArgs(b);
   const unsigned grid = (unsigned)((b->N + 127) / 128);
-  hb::k_unpack<<<grid, 128, 0, (cudaStream_t)stream>>>(a, dump);
+  if (b->spec.H > hb::kMaxHandNarrow) hb::k_unpack<hb::WView><<<grid, 128, 0, (cudaStream_t)stream>>>(a, dump);
+  else hb::k_unpack<hb::DView><<<grid, 128, 0, (cudaStream_t)stream>>>(a, dump);
   HB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1689,8 +1700,10 @@ int BatchUnpackState(pyhanabi_batch_t* h, int32_t* dump, void* stream) {
 int BatchErrorFlags(pyhanabi_batch_t* h, uint8_t* flags, uint64_t* count, int clear, void* stream) {
   HB_BATCH(h);
   const unsigned grid = (unsigned)((b->N + 127) / 128);
-  const bool compact = hb::state_columns(b->spec.P) == b->spec.P + 1;
-  hb::k_errors<<<grid, 128, 0, (cudaStream_t)stream>>>(b->state, b->N, compact ? b->spec.P : b->spec.P + 1,
+  const bool wide = b->spec.H > hb::kMaxHandNarrow;  // wide layout: column 2 P + 1, x, bit 31
+  const bool compact = !wide && hb::state_columns(b->spec.P) == b->spec.P + 1;
+  hb::k_errors<<<grid, 128, 0, (cudaStream_t)stream>>>(b->state, b->N,
+                                                       wide ? 2 * b->spec.P + 1 : compact ? b->spec.P : b->spec.P + 1,
                                                        compact ? 1 : 0, compact ? 25 : 31, flags, clear,
                                                        reinterpret_cast<unsigned long long*>(count));
   HB_CUDA(cudaGetLastError());
@@ -1709,7 +1722,8 @@ int BatchExportGame(pyhanabi_batch_t* h, int64_t game, int32_t* host_record, voi
   int32_t* d = nullptr;
   HB_CUDA(cudaMallocAsync(&d, sizeof(int32_t) * hb::kExportLen, s));
   hb::KArgs a = BaseArgs(b);
-  hb::k_export<<<1, 32, 0, s>>>(a, game, d);
+  if (b->spec.H > hb::kMaxHandNarrow) hb::k_export<hb::WView><<<1, 32, 0, s>>>(a, game, d);
+  else hb::k_export<hb::DView><<<1, 32, 0, s>>>(a, game, d);
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess)
     e = cudaMemcpyAsync(host_record, d, sizeof(int32_t) * hb::kExportLen, cudaMemcpyDeviceToHost, s);
@@ -1724,7 +1738,8 @@ int BatchPackState(pyhanabi_batch_t* h, const int32_t* dump, const int32_t* extr
   if (!dump) return Fail("BatchPackState: dump is null");
   hb::KArgs a = BaseArgs(b);
   const unsigned grid = (unsigned)((b->N + 127) / 128);
-  hb::k_pack<<<grid, 128, 0, (cudaStream_t)stream>>>(a, dump, extra);
+  if (b->spec.H > hb::kMaxHandNarrow) hb::k_pack<hb::WView><<<grid, 128, 0, (cudaStream_t)stream>>>(a, dump, extra);
+  else hb::k_pack<hb::DView><<<grid, 128, 0, (cudaStream_t)stream>>>(a, dump, extra);
   HB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1755,6 +1770,9 @@ int BatchAgentAct(pyhanabi_batch_t* h, int agent_kind, uint32_t seat_mask, const
   HB_BATCH(h);
   if (!actions) return Fail("BatchAgentAct: actions is null");
   if (agent_kind != 0 && agent_kind != 1) return Fail("BatchAgentAct: agent_kind must be 0 (RuleBasedAgent) or 1 (SimpleAgent)");
+  if (b->spec.H > hb::kMaxHandNarrow)
+    return Fail("BatchAgentAct: the batched agents read hands of up to five cards (rule_based_agent.py:143 "
+                "hard-codes five slots)");
   hb::AgentArgs a;
   std::memset(&a, 0, sizeof(a));
   if (agent_kind == 0) {

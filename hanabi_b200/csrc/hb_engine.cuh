@@ -45,8 +45,11 @@ constexpr int block_for_deal(int cards) { return cards >= 12 ? 256 : 192; }
 template <int P_, int H_, int C_, int R_, int IT_, int LT_>
 struct SView {
   static constexpr bool kStatic = true;
+  static constexpr bool kWide = false;  // 32-bit hand words: up to five cards per hand
+  typedef uint32_t Word;
   static constexpr int kP = P_, kH = H_, kC = C_, kR = R_;
   static constexpr int kBlock = block_for_deal(P_ * H_);
+  static constexpr int kResident = 0;  // resident threads per SM the kernel is built for (0: the default)
   // Re-deal machinery, measured per rule set (profiles/r02i_ab.log): initial deals of 12+ cards
   // go through the job path (one thread per RNG word pair over all jobs of the CTA, serial
   // chain per job, lazy slot regeneration); deals of up to 10 cards keep round 1's serial path.
@@ -65,14 +68,20 @@ struct SView {
   HB_DEV constexpr int bpc() const { return C_ * R_; }
 };
 // Dynamic view: any legal parameter set, loop bounds are the layout maxima.
-struct DView {
+template <bool WIDE> struct WordOf { typedef uint32_t type; };
+template <> struct WordOf<true> { typedef uint64_t type; };
+template <bool WIDE>
+struct DViewT {
   static constexpr bool kStatic = false;
-  static constexpr int kP = kMaxPlayers, kH = kMaxHand, kC = kMaxColors, kR = kMaxRanks;
-  static constexpr int kBlock = block_for_deal(kMaxPlayers * kMaxHand);
+  static constexpr bool kWide = WIDE;
+  typedef typename WordOf<WIDE>::type Word;
+  static constexpr int kP = kMaxPlayers, kH = WIDE ? kMaxHand : kMaxHandNarrow, kC = kMaxColors, kR = kMaxRanks;
+  static constexpr int kBlock = WIDE ? 128 : block_for_deal(kMaxPlayers * kMaxHandNarrow);
+  static constexpr int kResident = WIDE ? 384 : 0;  // the 64-bit hand words cost registers: fewer, fatter threads
   static constexpr bool kJobs = true;
   static constexpr int kPendCap = HB_LAZY_REGEN ? kMaxPend : 0;
   const Spec& s;
-  HB_DEV explicit DView(const Spec& sp) : s(sp) {}
+  HB_DEV explicit DViewT(const Spec& sp) : s(sp) {}
   HB_DEV int P() const { return s.P; }
   HB_DEV int H() const { return s.H; }
   HB_DEV int C() const { return s.C; }
@@ -83,6 +92,12 @@ struct DView {
   HB_DEV int deck_max() const { return s.deck_max; }
   HB_DEV int bpc() const { return s.bits_per_card; }
 };
+typedef DViewT<false> DView;
+// Hands of six to eight cards (the reference allows hand_size * players <= deck,
+// hanabi_game.cc:38,58; its 8-bit hand masks cap a hand at eight, hanabi_state.cc:30,43):
+// the same engine on 64-bit hand words (6-bit card slots, 5-bit knowledge slots x 8) and a
+// state layout of 2 columns per player (load_game).
+typedef DViewT<true> WView;
 
 // ------------------------------------------------------------------- the game
 // Packed HBM layout: columns of uint4, column-major over games (state[col * N + game]) so a
@@ -98,10 +113,11 @@ struct DView {
 //   column P + 1  : x = fireworks 5x3 | info 5 | life 4 | cur 3 | turns_to_play 3 | done | error
 //                   y = deck size 6 | mt19937 index 10 | episode length 12
 //                   z = last non-deal action record, w = spare
-struct Game {
-  uint32_t cards[kMaxPlayers];
-  uint32_t cpl[kMaxPlayers];
-  uint32_t rpl[kMaxPlayers];
+template <class W>
+struct GameT {
+  W cards[kMaxPlayers];
+  W cpl[kMaxPlayers];
+  W rpl[kMaxPlayers];
   uint32_t hw[kMaxPlayers];
   uint64_t deck;  // bit set = that card instance is still in the deck
   uint64_t disc;  // discard thermometers
@@ -112,10 +128,17 @@ struct Game {
   uint32_t last;
   uint32_t spare;
 };
+typedef GameT<uint32_t> Game;
+#define HB_GAME(V) GameT<typename V::Word>
 
 // last-action record fields: kLa* in hb_spec.h
 
-HB_DEV int hand_size(const Game& G, int p_static) { return (G.hw[p_static] >> 16) & 15; }
+template <class W>
+HB_DEV int hand_size(const GameT<W>& G, int p_static) { return (G.hw[p_static] >> 16) & 15; }
+// one bit per 5-bit knowledge slot
+template <class W> HB_DEV constexpr W slot_ones();
+template <> HB_DEV constexpr uint32_t slot_ones<uint32_t>() { return 0x108421u; }
+template <> HB_DEV constexpr uint64_t slot_ones<uint64_t>() { return 0x842108421ull; }
 
 // The packed state is the one array the next step reads again: with
 // HB_STATE_EVICT_LAST its loads and stores carry an L2 evict-last policy so that the
@@ -166,8 +189,15 @@ HB_DEV void st_state(uint4* p, uint4 v) {
 #define HB_COMPACT_STATE 1
 #endif
 constexpr int state_columns(int players) { return HB_COMPACT_STATE ? players + 1 : players + 2; }
+// Wide layout (WView, hands of 6-8 cards), 2 P + 2 columns:
+//   column 2p     : x,y = cards (6-bit slots x 8)   z,w = colour-plausible masks (5-bit slots x 8)
+//   column 2p + 1 : x,y = rank-plausible masks      z = flags | hand size (as above)   w = 0
+//   column 2P     : deck bitmap, discard thermometers
+//   column 2P + 1 : the general layout's column P + 1
+constexpr int state_columns_wide(int players) { return 2 * players + 2; }
 
-HB_DEV void unpack_misc(Game& G, uint32_t x) {
+template <class W>
+HB_DEV void unpack_misc(GameT<W>& G, uint32_t x) {
   G.fw = x & 0x7fffu;
   G.info = (x >> 15) & 31;
   G.life = (x >> 20) & 15;
@@ -178,7 +208,32 @@ HB_DEV void unpack_misc(Game& G, uint32_t x) {
 }
 
 template <class V>
-HB_DEV void load_game(const uint4* __restrict__ st, int64_t N, int64_t g, V v, Game& G) {
+HB_DEV void load_game(const uint4* __restrict__ st, int64_t N, int64_t g, V v, HB_GAME(V)& G) {
+  if constexpr (V::kWide) {
+#pragma unroll
+    for (int p = 0; p < V::kP; ++p) {
+      G.cards[p] = 0; G.cpl[p] = 0; G.rpl[p] = 0; G.hw[p] = 0;
+      if (p < v.P()) {
+        const uint4 a = ld_state(st + (int64_t)(2 * p) * N + g), b = ld_state(st + (int64_t)(2 * p + 1) * N + g);
+        G.cards[p] = (uint64_t)a.x | ((uint64_t)a.y << 32);
+        G.cpl[p] = (uint64_t)a.z | ((uint64_t)a.w << 32);
+        G.rpl[p] = (uint64_t)b.x | ((uint64_t)b.y << 32);
+        G.hw[p] = b.z;
+      }
+    }
+    const uint4 a = ld_state(st + (int64_t)(2 * v.P()) * N + g);
+    G.deck = (uint64_t)a.x | ((uint64_t)a.y << 32);
+    G.disc = (uint64_t)a.z | ((uint64_t)a.w << 32);
+    const uint4 b = ld_state(st + (int64_t)(2 * v.P() + 1) * N + g);
+    unpack_misc(G, b.x);
+    G.deck_size = b.y & 63;
+    G.mti = (b.y >> 6) & 1023;
+    G.eplen = (b.y >> 16) & 255;
+    G.pend = (b.y >> 28) & 15;
+    G.last = b.z;
+    G.spare = b.w;
+    return;
+  } else {
   if (HB_COMPACT_STATE) {
     uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0;
 #pragma unroll
@@ -228,10 +283,30 @@ HB_DEV void load_game(const uint4* __restrict__ st, int64_t N, int64_t g, V v, G
   G.pend = (b.y >> 28) & 15;
   G.last = b.z;
   G.spare = b.w;
+  }
 }
 
 template <class V>
-HB_DEV void store_game(uint4* __restrict__ st, int64_t N, int64_t g, V v, const Game& G) {
+HB_DEV void store_game(uint4* __restrict__ st, int64_t N, int64_t g, V v, const HB_GAME(V)& G) {
+  if constexpr (V::kWide) {
+#pragma unroll
+    for (int p = 0; p < V::kP; ++p) {
+      if (p < v.P()) {
+        st_state(st + (int64_t)(2 * p) * N + g, make_uint4((uint32_t)G.cards[p], (uint32_t)(G.cards[p] >> 32),
+                                                           (uint32_t)G.cpl[p], (uint32_t)(G.cpl[p] >> 32)));
+        st_state(st + (int64_t)(2 * p + 1) * N + g, make_uint4((uint32_t)G.rpl[p], (uint32_t)(G.rpl[p] >> 32), G.hw[p], 0u));
+      }
+    }
+    st_state(st + (int64_t)(2 * v.P()) * N + g, make_uint4((uint32_t)G.deck, (uint32_t)(G.deck >> 32),
+                                                           (uint32_t)G.disc, (uint32_t)(G.disc >> 32)));
+    const uint32_t x = G.fw | ((uint32_t)G.info << 15) | ((uint32_t)G.life << 20) |
+                       ((uint32_t)G.cur << 24) | ((uint32_t)G.turns << 27) | ((uint32_t)G.done << 30) |
+                       ((uint32_t)G.err << 31);
+    const uint32_t y = (uint32_t)G.deck_size | ((uint32_t)G.mti << 6) |
+                       ((uint32_t)(G.eplen > 255 ? 255 : G.eplen) << 16) | ((uint32_t)G.pend << 28);
+    st_state(st + (int64_t)(2 * v.P() + 1) * N + g, make_uint4(x, y, G.last, G.spare));
+    return;
+  } else {
   if (HB_COMPACT_STATE) {
     const uint32_t X = G.fw | ((uint32_t)G.info << 15) | ((uint32_t)G.life << 20) |
                        ((uint32_t)G.cur << 24) | ((uint32_t)G.turns << 27) | ((uint32_t)G.done << 30) |
@@ -270,19 +345,20 @@ HB_DEV void store_game(uint4* __restrict__ st, int64_t N, int64_t g, V v, const 
   uint32_t y = (uint32_t)G.deck_size | ((uint32_t)G.mti << 6) |
                ((uint32_t)(G.eplen > 255 ? 255 : G.eplen) << 16) | ((uint32_t)G.pend << 28);
   st_state(st + (int64_t)(v.P() + 1) * N + g, make_uint4(x, y, G.last, G.spare));
+  }
 }
 
 // Register-array access with a runtime player index: a predicated select chain
 // keeps the arrays in registers (no local memory).
-template <class V>
-HB_DEV uint32_t sel(const uint32_t (&a)[kMaxPlayers], int p) {
-  uint32_t r = a[0];
+template <class V, class T>
+HB_DEV T sel(const T (&a)[kMaxPlayers], int p) {
+  T r = a[0];
 #pragma unroll
   for (int i = 1; i < V::kP; ++i) r = (p == i) ? a[i] : r;
   return r;
 }
-template <class V>
-HB_DEV void put(uint32_t (&a)[kMaxPlayers], int p, uint32_t val) {
+template <class V, class T>
+HB_DEV void put(T (&a)[kMaxPlayers], int p, T val) {
 #pragma unroll
   for (int i = 0; i < V::kP; ++i) a[i] = (p == i) ? val : a[i];
 }
@@ -523,7 +599,7 @@ HB_DEV bool lemire_accept(uint32_t word, uint32_t range, uint32_t& out) {
 
 // -------------------------------------------------------------------- rules
 template <class V>
-HB_DEV bool needs_deal(V v, const Game& G) {
+HB_DEV bool needs_deal(V v, const HB_GAME(V)& G) {
   bool short_hand = false;
 #pragma unroll
   for (int p = 0; p < V::kP; ++p)
@@ -534,7 +610,7 @@ HB_DEV bool needs_deal(V v, const Game& G) {
 // HanabiState::ApplyMove(kDeal) of the card at deck position `pos`
 // (hanabi_state.cc:229-241).
 template <class V>
-HB_DEV void deal_card(V v, Game& G, int pos, int obs_type) {
+HB_DEV void deal_card(V v, HB_GAME(V)& G, int pos, int obs_type) {
   int color, rank;
   card_of_position(v, pos, color, rank);
   bool placed = false;
@@ -544,13 +620,14 @@ HB_DEV void deal_card(V v, Game& G, int pos, int obs_type) {
       const int n = hand_size(G, p);
       if (!placed && n < v.H()) {  // PlayerToDeal: lowest index with a short hand
         placed = true;
-        G.cards[p] |= (uint32_t)(color | (rank << 3)) << (6 * n);
+        typedef typename V::Word W;
+        G.cards[p] |= (W)(uint32_t)(color | (rank << 3)) << (6 * n);
         uint32_t cm = (1u << v.C()) - 1u, rm = (1u << v.R()) - 1u, flags = 0;
         if (obs_type == kSeer) {  // hanabi_state.cc:233-236
           cm = 1u << color; rm = 1u << rank; flags = (1u << n) | (1u << (8 + n));
         }
-        G.cpl[p] |= cm << (5 * n);
-        G.rpl[p] |= rm << (5 * n);
+        G.cpl[p] |= (W)cm << (5 * n);
+        G.rpl[p] |= (W)rm << (5 * n);
         G.hw[p] = (G.hw[p] | flags) + (1u << 16);
       }
     }
@@ -560,7 +637,7 @@ HB_DEV void deal_card(V v, Game& G, int pos, int obs_type) {
 }
 
 template <class V>
-HB_DEV int score_of(V v, const Game& G) {  // hanabi_state.cc:359-364
+HB_DEV int score_of(V v, const HB_GAME(V)& G) {  // hanabi_state.cc:359-364
   if (G.life <= 0) return 0;
   int s = 0;
 #pragma unroll
@@ -570,14 +647,14 @@ HB_DEV int score_of(V v, const Game& G) {  // hanabi_state.cc:359-364
 }
 
 template <class V>
-HB_DEV bool is_terminal(V v, const Game& G) {  // hanabi_state.cc:366-377
+HB_DEV bool is_terminal(V v, const HB_GAME(V)& G) {  // hanabi_state.cc:366-377
   return G.life < 1 || score_of(v, G) >= v.C() * v.R() || G.turns <= 0;
 }
 
 // HanabiState::LegalMoves(cur) as a bitmask over move uids
 // (hanabi_state.cc:166-219,288-304; uid layout hanabi_game.cc:79-95).
 template <class V>
-HB_DEV uint64_t legal_bits(V v, const Game& G) {
+HB_DEV uint64_t legal_bits(V v, const HB_GAME(V)& G) {
   const int n = (int)((sel<V>(G.hw, G.cur) >> 16) & 15);
   const uint64_t hm = (1ull << n) - 1ull;
   uint64_t bits = (G.info < v.IT() ? hm : 0ull) | (hm << v.H());
@@ -592,7 +669,7 @@ HB_DEV uint64_t legal_bits(V v, const Game& G) {
 #pragma unroll
         for (int i = 0; i < V::kH; ++i) {
           if (i < m) {
-            const uint32_t f = G.cards[p] >> (6 * i);
+            const uint32_t f = (uint32_t)(G.cards[p] >> (6 * i));
             cm |= 1u << (f & 7);
             rm |= 1u << ((f >> 3) & 7);
           }
@@ -608,7 +685,7 @@ HB_DEV uint64_t legal_bits(V v, const Game& G) {
 // HanabiState::MoveIsLegal for one move uid of the player to act
 // (hanabi_state.cc:166-219); cheaper than building the whole mask.
 template <class V>
-HB_DEV bool move_is_legal(V v, const Game& G, int uid, int max_moves) {
+HB_DEV bool move_is_legal(V v, const HB_GAME(V)& G, int uid, int max_moves) {
   if (uid < 0 || uid >= max_moves) return false;
   const int P = v.P(), H = v.H(), C = v.C(), R = v.R();
   const int n = (int)((sel<V>(G.hw, G.cur) >> 16) & 15);
@@ -622,19 +699,20 @@ HB_DEV bool move_is_legal(V v, const Game& G, int uid, int max_moves) {
   const int offm1 = u / span, val = u - offm1 * span;
   int t = G.cur + offm1 + 1;
   t -= t >= P ? P : 0;
-  const uint32_t hand = sel<V>(G.cards, t);
+  const typename V::Word hand = sel<V>(G.cards, t);
   const int m = (int)((sel<V>(G.hw, t) >> 16) & 15);
   bool any = false;
 #pragma unroll
   for (int i = 0; i < V::kH; ++i) {
-    const uint32_t f = hand >> (6 * i);
+    const uint32_t f = (uint32_t)(hand >> (6 * i));
     any |= (i < m) && ((int)(is_rank ? ((f >> 3) & 7) : (f & 7)) == val);
   }
   return any;
 }
 
-HB_DEV uint32_t drop_slot(uint32_t w, int idx, int width) {
-  const uint32_t low = (1u << (width * idx)) - 1u;
+template <class T>
+HB_DEV T drop_slot(T w, int idx, int width) {
+  const T low = ((T)1 << (width * idx)) - (T)1;
   return (w & low) | ((w >> width) & ~low);
 }
 
@@ -642,7 +720,7 @@ HB_DEV uint32_t drop_slot(uint32_t w, int idx, int width) {
 // the turn hand-over of AdvanceToNextPlayer (:104-111; pending deals are resolved
 // by the caller's deal loop before anybody observes the state).
 template <class V>
-HB_DEV void apply_move(V v, Game& G, int uid) {
+HB_DEV void apply_move(V v, HB_GAME(V)& G, int uid) {
   const int cur = G.cur;
   const int P = v.P(), H = v.H(), C = v.C(), R = v.R();
   if (G.deck_size == 0) G.turns -= 1;
@@ -650,8 +728,8 @@ HB_DEV void apply_move(V v, Game& G, int uid) {
   if (uid < 2 * H) {
     const bool is_play = uid >= H;
     const int idx = is_play ? uid - H : uid;
-    const uint32_t hand = sel<V>(G.cards, cur);
-    const int color = (hand >> (6 * idx)) & 7, rank = (hand >> (6 * idx + 3)) & 7;
+    const typename V::Word hand = sel<V>(G.cards, cur);
+    const int color = (int)(hand >> (6 * idx)) & 7, rank = (int)(hand >> (6 * idx + 3)) & 7;
     bool to_discard = true, scored = false, token = false;
     if (is_play) {
       const int top = (G.fw >> (3 * color)) & 7;
@@ -676,7 +754,7 @@ HB_DEV void apply_move(V v, Game& G, int uid) {
     put<V>(G.cpl, cur, drop_slot(sel<V>(G.cpl, cur), idx, 5));
     put<V>(G.rpl, cur, drop_slot(sel<V>(G.rpl, cur), idx, 5));
     const uint32_t hw = sel<V>(G.hw, cur);
-    const uint32_t ch = drop_slot(hw & 0xffu, idx, 1), rh = drop_slot((hw >> 8) & 0xffu, idx, 1);
+    const uint32_t ch = drop_slot<uint32_t>(hw & 0xffu, idx, 1), rh = drop_slot<uint32_t>((hw >> 8) & 0xffu, idx, 1);
     put<V>(G.hw, cur, ch | (rh << 8) | ((hw & 0xf0000u) - (1u << 16)));
     la |= (uint32_t)(is_play ? kLaPlay : kLaDiscard) << kLaTypeSh;
     la |= (uint32_t)idx << kLaIdxSh | (uint32_t)color << kLaColSh | (uint32_t)rank << kLaRankSh;
@@ -690,21 +768,23 @@ HB_DEV void apply_move(V v, Game& G, int uid) {
     int t = cur + offm1 + 1;
     t -= t >= P ? P : 0;
     G.info -= 1;
-    const uint32_t hand = sel<V>(G.cards, t);
+    typedef typename V::Word W;
+    const W hand = sel<V>(G.cards, t);
     const uint32_t hw = sel<V>(G.hw, t);
     const int n = (hw >> 16) & 15;
-    uint32_t mm = 0, M = 0;
+    uint32_t mm = 0;
+    W M = 0;
 #pragma unroll
     for (int i = 0; i < V::kH; ++i) {
       if (i < n) {
-        const uint32_t f = hand >> (6 * i);
+        const uint32_t f = (uint32_t)(hand >> (6 * i));
         const int cv = is_rank ? ((f >> 3) & 7) : (f & 7);
-        if (cv == val) { mm |= 1u << i; M |= 31u << (5 * i); }
+        if (cv == val) { mm |= 1u << i; M |= (W)31u << (5 * i); }
       }
     }
     // RevealColor/RevealRank (hanabi_hand.cc:96-126): matching cards become
     // exactly {val} and are flagged hinted; the others lose val.
-    const uint32_t all = (1u << val) * 0x108421u;
+    const W all = (W)(1u << val) * slot_ones<W>();
     if (is_rank) {
       put<V>(G.rpl, t, (sel<V>(G.rpl, t) & ~all & ~M) | (all & M));
       put<V>(G.hw, t, hw | (mm << 8));
@@ -713,7 +793,8 @@ HB_DEV void apply_move(V v, Game& G, int uid) {
       put<V>(G.hw, t, hw | mm);
     }
     la |= (uint32_t)(is_rank ? kLaRevealRank : kLaRevealColor) << kLaTypeSh;
-    la |= (uint32_t)(offm1 + 1) << kLaOffSh | (uint32_t)val << kLaValSh | mm << kLaRevealSh;
+    la |= (uint32_t)(offm1 + 1) << kLaOffSh | (uint32_t)val << kLaValSh |
+          (V::kWide ? la_pack_reveal(mm) : mm << kLaRevealSh);
   }
   G.last = la;
   G.cur = cur + 1 == P ? 0 : cur + 1;
@@ -722,7 +803,7 @@ HB_DEV void apply_move(V v, Game& G, int uid) {
 
 // Fresh game before any deal (HanabiState ctor, hanabi_state.cc:90-102).
 template <class V>
-HB_DEV void init_fresh(V v, const Spec& spec, Game& G, int start_player) {
+HB_DEV void init_fresh(V v, const Spec& spec, HB_GAME(V)& G, int start_player) {
 #pragma unroll
   for (int p = 0; p < V::kP; ++p) { G.cards[p] = 0; G.cpl[p] = 0; G.rpl[p] = 0; G.hw[p] = 0; }
   G.deck = spec.full_deck;
@@ -747,7 +828,7 @@ HB_DEV void init_fresh(V v, const Spec& spec, Game& G, int start_player) {
 // game carries fewer than lazy_cap pending pairs; a restart always regenerates at once
 // (callers flush first).
 template <class V>
-HB_DEV void deal_loop(V v, const Spec& spec, Game& G, bool restart, int64_t g, uint32_t* mt_all,
+HB_DEV void deal_loop(V v, const Spec& spec, HB_GAME(V)& G, bool restart, int64_t g, uint32_t* mt_all,
                       int sampler_mode, Prefetch& pre, int lazy_cap = 0) {
   uint32_t* x = mt_all + g * (int64_t)kMtN;
   for (;;) {
@@ -791,11 +872,13 @@ HB_DEV void deal_loop(V v, const Spec& spec, Game& G, bool restart, int64_t g, u
 // initial deal is a >= 2-type draw) and a running game whose pending pairs reach the cap
 // enqueue a JOB in shared memory; after a CTA barrier all threads work the jobs off, one
 // thread per RNG word pair (k_main, phase B).  The result of a re-deal job:
-struct JobResult {
-  uint32_t cards[kMaxPlayers];  // the new hands
+template <class W>
+struct JobResultT {
+  W cards[kMaxPlayers];         // the new hands
   uint32_t deck_lo, deck_hi;    // deck bitmap after the initial deal
 };
-typedef JobResult ResetResult;
+typedef JobResultT<uint32_t> JobResult;
+#define HB_JOBRESULT(V) JobResultT<typename V::Word>
 
 // Draws the initial deal of one game.  Draw r (deck size deck_max - r) comes with
 // its precomputed index qa[r] = floor(u_r * size) | ambiguous << 8 and its tempered
@@ -804,7 +887,8 @@ typedef JobResult ResetResult;
 // hand is filled first, then player 1's, ... (PlayerToDeal, hanabi_state.cc:157-164).
 template <class V>
 HB_DEV void reset_draw(V v, const Spec& spec, const uint32_t* qa, const uint32_t* lo,
-                       const uint32_t* hi, int sampler_mode, ResetResult& out) {
+                       const uint32_t* hi, int sampler_mode, HB_JOBRESULT(V)& out) {
+  typedef typename V::Word W;
   uint64_t deck = spec.full_deck;
   int n = v.deck_max();
   const int H = v.H(), total = v.P() * H;
@@ -819,9 +903,9 @@ HB_DEV void reset_draw(V v, const Spec& spec, const uint32_t* qa, const uint32_t
       pos = pick_exact(v, deck, n, lo[r], hi[r]);
     int color, rank;
     card_of_position(v, pos, color, rank);
-    const uint32_t card = (uint32_t)(color | (rank << 3)) << (6 * i);
+    const W card = (W)(uint32_t)(color | (rank << 3)) << (6 * i);
 #pragma unroll
-    for (int k = 0; k < V::kP; ++k) out.cards[k] |= (k == p) ? card : 0u;
+    for (int k = 0; k < V::kP; ++k) out.cards[k] |= (k == p) ? card : (W)0;
     deck &= ~(1ull << pos);
     --n;
     if (++i == H) { i = 0; ++p; }
@@ -832,14 +916,15 @@ HB_DEV void reset_draw(V v, const Spec& spec, const uint32_t* qa, const uint32_t
 
 // Installs a drawn initial deal as the lane's new game.
 template <class V>
-HB_DEV void reset_apply(V v, const Spec& spec, Game& G, const ResetResult& res) {
+HB_DEV void reset_apply(V v, const Spec& spec, HB_GAME(V)& G, const HB_JOBRESULT(V)& res) {
+  typedef typename V::Word W;
   init_fresh(v, spec, G, 0);
   const int H = v.H();
   const bool seer = spec.obs_type == kSeer;
-  uint32_t call = 0, rall = 0;
+  W call = 0, rall = 0;
 #pragma unroll
   for (int i = 0; i < V::kH; ++i)
-    if (i < H) { call |= ((1u << v.C()) - 1u) << (5 * i); rall |= ((1u << v.R()) - 1u) << (5 * i); }
+    if (i < H) { call |= (W)((1u << v.C()) - 1u) << (5 * i); rall |= (W)((1u << v.R()) - 1u) << (5 * i); }
   const uint32_t flags = (1u << H) - 1u;
 #pragma unroll
   for (int p = 0; p < V::kP; ++p) {
@@ -849,13 +934,13 @@ HB_DEV void reset_apply(V v, const Spec& spec, Game& G, const ResetResult& res) 
       G.rpl[p] = rall;
       G.hw[p] = (uint32_t)H << 16;
       if (seer) {  // hanabi_state.cc:233-236: knowledge starts as the card itself
-        uint32_t c1 = 0, r1 = 0;
+        W c1 = 0, r1 = 0;
 #pragma unroll
         for (int i = 0; i < V::kH; ++i)
           if (i < H) {
-            const uint32_t f = res.cards[p] >> (6 * i);
-            c1 |= (1u << (f & 7)) << (5 * i);
-            r1 |= (1u << ((f >> 3) & 7)) << (5 * i);
+            const uint32_t f = (uint32_t)(res.cards[p] >> (6 * i));
+            c1 |= (W)(1u << (f & 7)) << (5 * i);
+            r1 |= (W)(1u << ((f >> 3) & 7)) << (5 * i);
           }
         G.cpl[p] = c1;
         G.rpl[p] = r1;
@@ -938,7 +1023,7 @@ HB_DEV uint32_t spread_entry(int cm, int C, int R) {
 }
 
 template <class V>
-HB_DEV void encode_obs(V v, const Spec& spec, const Game& G, int observer, uint32_t* stream,
+HB_DEV void encode_obs(V v, const Spec& spec, const HB_GAME(V)& G, int observer, uint32_t* stream,
                        int lane, const uint32_t* spread, int slice_bits) {
   const int P = v.P(), H = v.H(), C = v.C(), R = v.R(), bpc = v.bpc();
   // slice_bits = distance between two lanes' slices in the stream: obs_size for
@@ -951,14 +1036,14 @@ HB_DEV void encode_obs(V v, const Spec& spec, const Game& G, int observer, uint3
     if (q < P) {
       int p = observer + q;
       p -= p >= P ? P : 0;
-      const uint32_t hand = sel<V>(G.cards, p);
+      const typename V::Word hand = sel<V>(G.cards, p);
       const int n = (int)((sel<V>(G.hw, p) >> 16) & 15);
       short_bits |= (uint32_t)(n < H) << q;
       if (q >= 1) {
 #pragma unroll
         for (int i = 0; i < V::kH; ++i) {
           if (i < H) {
-            const uint32_t f = hand >> (6 * i);
+            const uint32_t f = (uint32_t)(hand >> (6 * i));
             const int id = (int)(f & 7) * R + (int)((f >> 3) & 7);
             bw.put(i < n ? (1u << id) : 0u, bpc);
           }
@@ -998,7 +1083,7 @@ HB_DEV void encode_obs(V v, const Spec& spec, const Game& G, int observer, uint3
     const int val = (la >> kLaValSh) & 7;
     bw.put((valid && type == kLaRevealColor) ? (1u << val) : 0u, C);
     bw.put((valid && type == kLaRevealRank) ? (1u << val) : 0u, R);
-    bw.put(is_hint ? ((la >> kLaRevealSh) & 31u) : 0u, H);
+    bw.put(is_hint ? (V::kWide ? la_reveal(la) : ((la >> kLaRevealSh) & 31u)) : 0u, H);
     bw.put(is_card ? (1u << ((la >> kLaIdxSh) & 7)) : 0u, H);
     const int id = (int)((la >> kLaColSh) & 7) * R + (int)((la >> kLaRankSh) & 7);
     bw.put(is_card ? (1u << id) : 0u, bpc);
@@ -1011,12 +1096,13 @@ HB_DEV void encode_obs(V v, const Spec& spec, const Game& G, int observer, uint3
       if (q < P) {
         int p = observer + q;
         p -= p >= P ? P : 0;
-        const uint32_t cpl = sel<V>(G.cpl, p), rpl = sel<V>(G.rpl, p), hw = sel<V>(G.hw, p);
+        const typename V::Word cpl = sel<V>(G.cpl, p), rpl = sel<V>(G.rpl, p);
+        const uint32_t hw = sel<V>(G.hw, p);
         const int n = (int)((hw >> 16) & 15);
 #pragma unroll
         for (int i = 0; i < V::kH; ++i) {
           if (i < H) {
-            const uint32_t cm = (cpl >> (5 * i)) & 31u, rm = (rpl >> (5 * i)) & 31u;
+            const uint32_t cm = (uint32_t)(cpl >> (5 * i)) & 31u, rm = (uint32_t)(rpl >> (5 * i)) & 31u;
             const uint32_t plaus = spread[cm] * rm;  // rm < 2^R: the products do not overlap
             const bool have = i < n;
             bw.put(have ? plaus : 0u, bpc);

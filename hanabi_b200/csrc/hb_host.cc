@@ -134,6 +134,75 @@ class HostPool {
   std::atomic<uint64_t> ticket_{0};  // generation << 32 | next part of that generation
 };
 
+// ------------------------------------------------------- random legal policy rows
+// actions[g] for rows [lo, hi): the legal bytes of a row gathered into a bit set, then the
+// (rank)-th set bit for the draw of hb_policy_rng.h.
+void PolicyRowsScalar(const uint8_t* mask, int lo, int hi, int num_actions, uint64_t seed,
+                      uint64_t step, int64_t first_game_index, int32_t* actions) {
+  for (int g = lo; g < hi; ++g) {
+    const uint8_t* m = mask + (int64_t)g * num_actions;
+    // eight mask bytes per step: any non-zero byte -> 1, then the eight low bits gathered
+    // with one multiply
+    uint64_t legal = 0;
+    int a = 0;
+    for (; a + 8 <= num_actions; a += 8) {
+      uint64_t x;
+      std::memcpy(&x, m + a, 8);
+      x |= x >> 4; x |= x >> 2; x |= x >> 1;
+      x &= 0x0101010101010101ull;
+      legal |= ((x * 0x0102040810204080ull) >> 56) << a;
+    }
+    for (; a < num_actions; ++a) legal |= (uint64_t)(m[a] != 0) << a;
+    const int n_legal = __builtin_popcountll(legal);
+    int choice = -1;
+    if (n_legal > 0) {
+      const uint64_t bits = hbp::policy_bits(seed, step, (uint64_t)(first_game_index + g));
+      int k = hbp::random_legal_rank(bits, n_legal);
+      while (k-- > 0) legal &= legal - 1;
+      choice = __builtin_ctzll(legal);
+    }
+    actions[g] = choice;
+  }
+}
+
+#if defined(__x86_64__)
+// Same rows with one or two 32-byte loads per row (compare + movemask) and the k-th set bit
+// by pdep: no data-dependent loop, no branch on the mask's contents.
+__attribute__((target("avx2,bmi2"))) void PolicyRowsAvx2(const uint8_t* mask, int lo, int hi, int n,
+                                                       int num_actions, uint64_t seed, uint64_t step,
+                                                       int64_t first_game_index, int32_t* actions) {
+  // rows whose 64-byte window would run past the end of the array take the scalar path
+  const int64_t total = (int64_t)n * num_actions;
+  int safe_hi = hi;
+  while (safe_hi > lo && (int64_t)(safe_hi - 1) * num_actions + 64 > total) --safe_hi;
+  const __m256i zero = _mm256_setzero_si256();
+  const uint64_t keep = num_actions >= 64 ? ~0ull : ((1ull << num_actions) - 1ull);
+  for (int g = lo; g < safe_hi; ++g) {
+    const uint8_t* m = mask + (int64_t)g * num_actions;
+    const __m256i v0 = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(m));
+    uint64_t legal = (uint32_t)~_mm256_movemask_epi8(_mm256_cmpeq_epi8(v0, zero));
+    if (num_actions > 32) {
+      const __m256i v1 = _mm256_loadu_si256(reinterpret_cast<const __m256i*>(m + 32));
+      legal |= (uint64_t)(uint32_t)~_mm256_movemask_epi8(_mm256_cmpeq_epi8(v1, zero)) << 32;
+    }
+    legal &= keep;
+    const int n_legal = __builtin_popcountll(legal);
+    const uint64_t bits = hbp::policy_bits(seed, step, (uint64_t)(first_game_index + g));
+    const int k = hbp::random_legal_rank(bits, n_legal > 0 ? n_legal : 1);
+    const uint64_t pick = _pdep_u64(1ull << k, legal);  // the k-th set bit of legal (0 when none)
+    actions[g] = n_legal > 0 ? (int32_t)__builtin_ctzll(pick) : -1;
+  }
+  PolicyRowsScalar(mask, safe_hi, hi, num_actions, seed, step, first_game_index, actions);
+}
+bool HaveAvx2Bmi2() {
+  static const bool have = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("bmi2");
+  return have;
+}
+#else
+bool HaveAvx2Bmi2() { return false; }
+void PolicyRowsAvx2(const uint8_t*, int, int, int, int, uint64_t, uint64_t, int64_t, int32_t*) {}
+#endif
+
 }  // namespace
 
 extern "C" {
@@ -154,30 +223,8 @@ int HostRandomLegalActionsAt(const uint8_t* mask, int n, int num_actions, uint64
   if ((int64_t)parts * 2048 > n) parts = n / 2048 > 0 ? n / 2048 : 1;
   const std::function<void(int)> work = [=](int t) {
     const int lo = (int)((int64_t)n * t / parts), hi = (int)((int64_t)n * (t + 1) / parts);
-    for (int g = lo; g < hi; ++g) {
-      const uint8_t* m = mask + (int64_t)g * num_actions;
-      // eight mask bytes per step: any non-zero byte -> 1, then the eight low bits gathered
-      // with one multiply
-      uint64_t legal = 0;
-      int a = 0;
-      for (; a + 8 <= num_actions; a += 8) {
-        uint64_t x;
-        std::memcpy(&x, m + a, 8);
-        x |= x >> 4; x |= x >> 2; x |= x >> 1;
-        x &= 0x0101010101010101ull;
-        legal |= ((x * 0x0102040810204080ull) >> 56) << a;
-      }
-      for (; a < num_actions; ++a) legal |= (uint64_t)(m[a] != 0) << a;
-      const int n_legal = __builtin_popcountll(legal);
-      int choice = -1;
-      if (n_legal > 0) {
-        const uint64_t bits = hbp::policy_bits(seed, step, (uint64_t)(first_game_index + g));
-        int k = hbp::random_legal_rank(bits, n_legal);
-        while (k-- > 0) legal &= legal - 1;
-        choice = __builtin_ctzll(legal);
-      }
-      actions[g] = choice;
-    }
+    if (HaveAvx2Bmi2()) PolicyRowsAvx2(mask, lo, hi, n, num_actions, seed, step, first_game_index, actions);
+    else PolicyRowsScalar(mask, lo, hi, num_actions, seed, step, first_game_index, actions);
   };
   pool.Run(parts, work);
   return 0;

@@ -828,7 +828,7 @@ void StateFromBatchGame(pyhanabi_game_t* game, const int32_t* rec, pyhanabi_stat
       const int off = (la >> hb::kLaOffSh) & 7, val = (la >> hb::kLaValSh) & 7;
       h.move = type == hb::kLaRevealColor ? Move(kRevealColor, -1, off, val, -1)
                                           : Move(kRevealRank, -1, off, -1, val);
-      h.reveal_bitmask = (uint8_t)((la >> hb::kLaRevealSh) & 31);
+      h.reveal_bitmask = (uint8_t)hb::la_reveal(la);
       h.newly_revealed_bitmask = h.reveal_bitmask;
     }
     st->history.push_back(h);

@@ -21,7 +21,9 @@ namespace hb {
 constexpr int kMaxPlayers = 5;
 constexpr int kMaxColors = 5;
 constexpr int kMaxRanks = 5;
-constexpr int kMaxHand = 5;      // packed layout: 6-bit card slots, 5-bit knowledge slots
+constexpr int kMaxHand = 8;        // the reference's 8-bit hand masks (hanabi_state.cc:30,43)
+constexpr int kMaxHandNarrow = 5;  // 32-bit hand words: 6-bit card slots, 5-bit knowledge slots x 5;
+                                   // larger hands use the 64-bit words of the wide view (hb_engine.cuh)
 constexpr int kMaxInfo = 31;     // 5-bit field
 constexpr int kMaxLife = 15;     // 4-bit field
 constexpr int kMtN = 624;
@@ -50,7 +52,15 @@ enum LaType { kLaPlay = 0, kLaDiscard = 1, kLaRevealColor = 2, kLaRevealRank = 3
 // information token gained.
 constexpr int kLaValid = 0, kLaTypeSh = 1, kLaActorSh = 3, kLaOffSh = 6, kLaValSh = 9,
               kLaIdxSh = 12, kLaColSh = 15, kLaRankSh = 18, kLaRevealSh = 21, kLaScoredSh = 26,
-              kLaInfoSh = 27;
+              kLaInfoSh = 27, kLaRevealHiSh = 28;
+// The reveal bitmask of a hint: cards 0-4 in bits [21,26), cards 5-7 (hands of six to eight
+// cards) in bits [28,31) -- records of hands up to five cards keep their 28-bit form.
+HB_HD uint32_t la_pack_reveal(uint32_t mask) {
+  return ((mask & 31u) << kLaRevealSh) | ((mask >> 5) << kLaRevealHiSh);
+}
+HB_HD uint32_t la_reveal(uint32_t la) {
+  return ((la >> kLaRevealSh) & 31u) | (((la >> kLaRevealHiSh) & 7u) << 5);
+}
 // BatchExportGame: canonical dump (272 ints, oracle/oracle_api.h layout) followed by
 // [272] turns_to_play [273] last-move record [274..277] the four records before it, newest
 // first (0 unless BatchEnableHistory) [278] done flag [279] episode length
@@ -133,7 +143,7 @@ inline const char* SpecError(int code) {
     case 1: return "players must be in [2,5] (hanabi_game.cc:33)";
     case 2: return "colors must be in [1,5] (hanabi_game.cc:35)";
     case 3: return "ranks must be in [1,5] (hanabi_game.cc:37)";
-    case 4: return "hand_size must be in [1,5] for the packed batch layout";
+    case 4: return "hand_size must be in [1,8] (hanabi_state.cc:30,43: 8-bit hand masks)";
     case 5: return "max_information_tokens must be in [0,31] for the packed batch layout";
     case 6: return "max_life_tokens must be in [1,15] for the packed batch layout";
     case 7: return "observation_type must be 0 (minimal), 1 (card knowledge) or 2 (seer)";

@@ -23,6 +23,12 @@ CONFIGS = {
                       max_life_tokens=1),
     "odd": dict(players=3, colors=4, ranks=3, hand_size=3, max_information_tokens=5,
                 max_life_tokens=2),
+    # hands of six to eight cards (hanabi_game.cc:38,58: hand_size * players <= deck; the
+    # reference's 8-bit hand masks cap a hand at eight): the engine's 64-bit hand words
+    "wide6": dict(players=2, hand_size=6),
+    "wide8": dict(players=3, hand_size=8),
+    "wide7seer": dict(players=5, hand_size=7, observation_type=2),
+    "wide8dealt": dict(players=5, colors=4, ranks=5, hand_size=8, max_life_tokens=2),  # 40 of 40 cards dealt
 }
 EXPECTED_SHAPES = {  # (obs_dim, num_moves)
     "full2": (658, 20), "full3": (956, 30), "full4": (1041, 38), "full5": (1280, 48),

@@ -107,7 +107,8 @@ def test_host_buffer_entry_points_match_device_path(packed_link):
 def test_new_batch_rejects_bad_parameters():
   from hanabi_b200 import pyhanabi as ph
   with pytest.raises(RuntimeError, match="hand_size"):
-    ph.HanabiBatch(dict(players=2, hand_size=7), 4, [1, 2, 3, 4])
+    ph.HanabiBatch(dict(players=2, hand_size=9), 4, [1, 2, 3, 4])  # 8-bit hand masks: hanabi_state.cc:30,43
+  assert ph.HanabiBatch(dict(players=2, hand_size=8), 4, [1, 2, 3, 4]).max_moves == 26
   with pytest.raises(RuntimeError, match="players"):
     ph.HanabiBatch(dict(players=6), 4, [1, 2, 3, 4])
   with pytest.raises(RuntimeError, match="deck"):

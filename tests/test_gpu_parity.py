@@ -45,7 +45,8 @@ def test_random_policy_lockstep(name):
   assert eps > 100
 
 
-@pytest.mark.parametrize("name", ["full2", "full4", "full5", "small2", "seer3", "dealt_out"])
+@pytest.mark.parametrize("name", ["full2", "full4", "full5", "small2", "seer3", "dealt_out", "wide6", "wide8",
+                                  "wide8dealt"])
 def test_keep_alive_policy_lockstep(name):
   n = 256
   seeds = common.seeds_for(n, base=9000)
