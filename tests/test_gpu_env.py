@@ -434,3 +434,89 @@ def test_device_recorder_posts_the_reference_trajectories(players, game):
     assert (next_legal[i] == 0).astype(np.uint8).tobytes() == want[i + 1][4], i
   pri = mem.get_priority(idx).cpu().numpy()
   assert (pri == 100.0).all()
+
+
+@pytest.mark.parametrize("cfg", [dict(players=2, hand_size=7), dict(players=4, hand_size=8, observation_type=2)])
+def test_wide_hands_through_every_view(cfg):
+  """Hands of six to eight cards (the engine's 64-bit hand words): the single-game view of a
+  batched game with history (dict keys, discard order, last_moves incl. reveal bitmasks of
+  cards 5-7), the checkpoint blob, the bit-packed rows and the host-buffer path -- against
+  the single-game HanabiEnv on the same seeds and moves."""
+  import torch
+  from hanabi_b200 import pyhanabi as ph, rl_env
+  n, probe = 70, [0, 33, 69]
+  base = dict(colors=5, ranks=5, max_information_tokens=8, max_life_tokens=3, observation_type=1)
+  base.update(cfg)
+  env = rl_env.BatchedHanabiEnv(dict(base, seed=500), n)
+  env.batch.enable_history()
+  singles = {}
+  for i in probe:
+    singles[i] = rl_env.HanabiEnv(dict(base, seed=500 + i))
+    singles[i].reset()
+  obs = env.reset()
+  H = base["hand_size"]
+  D, A, W = env.batch.obs_size, env.batch.max_moves, env.batch.packed_words
+  bits = torch.zeros((n, W), dtype=torch.int32, device=env.device)
+  rng = np.random.default_rng(21)
+  alive = set(probe)
+  hints_seen = 0
+  for t in range(50):
+    mask = obs["legal_moves_mask"].cpu().numpy()
+    env.batch.observe_packed(bits)
+    raw = np.unpackbits(bits.cpu().numpy().view(np.uint8).reshape(n, W * 4), axis=1, bitorder="little")
+    common.assert_same(obs["vectorized"].cpu().numpy(), raw[:, :D], "packed rows @%d" % t)
+    for i in sorted(alive):
+      got = env.game_observations(i)
+      want = singles[i]._make_observation_all_players()
+      assert got["current_player"] == want["current_player"]
+      for pg, pw in zip(got["player_observations"], want["player_observations"]):
+        for key in pw:
+          if key != "pyhanabi":
+            assert pg[key] == pw[key], (i, t, key)
+        mine = [_move_item_tuple(m) for m in pg["pyhanabi"].last_moves()]
+        ref = [_move_item_tuple(m) for m in pw["pyhanabi"].last_moves()]
+        assert mine == ref, (i, t)
+        hints_seen += sum(1 for m in pw["pyhanabi"].last_moves() if m.card_info_revealed())
+    if t == 20:  # checkpoint round trip in the middle of the episodes
+      blob = env.batch.get_state()
+      again = ph.HanabiBatch(env.config, n, [1] * n)
+      again.enable_history()
+      again.set_state(blob)
+      o2 = torch.zeros((n, D), dtype=torch.uint8, device=env.device)
+      m2 = torch.zeros((n, A), dtype=torch.uint8, device=env.device)
+      c2 = torch.zeros(n, dtype=torch.int32, device=env.device)
+      again.observe(o2, m2, c2)
+      assert torch.equal(o2, obs["vectorized"]) and torch.equal(m2, obs["legal_moves_mask"])
+    a = common.choose_actions(None, mask, rng, False, 5, H)
+    obs, reward, done, _ = env.step(torch.as_tensor(a, device=env.device))
+    for i in sorted(alive):
+      _, r, d, _ = singles[i].step(int(a[i]))
+      assert r == int(reward[i]) and d == bool(done[i])
+      if d:
+        alive.discard(i)
+    if not alive:
+      break
+  assert hints_seen > 0
+  # the host-buffer path (packed link: HostExpandPacked on rows of this width) against the device rows
+  hb = ph.HanabiBatch(env.config, n, [500 + i for i in range(n)])
+  dv = ph.HanabiBatch(env.config, n, [500 + i for i in range(n)])
+  pin = lambda *shape, dt: torch.zeros(shape, dtype=dt).pin_memory()
+  h_obs, h_mask, h_cur = pin(n, D, dt=torch.uint8), pin(n, A, dt=torch.uint8), pin(n, dt=torch.int32)
+  h_rew, h_done, h_act = pin(n, dt=torch.int32), pin(n, dt=torch.uint8), pin(n, dt=torch.int32)
+  d_obs = torch.zeros((n, D), dtype=torch.uint8, device=env.device)
+  d_mask = torch.zeros((n, A), dtype=torch.uint8, device=env.device)
+  d_cur = torch.zeros(n, dtype=torch.int32, device=env.device)
+  d_rew = torch.zeros(n, dtype=torch.int32, device=env.device)
+  d_done = torch.zeros(n, dtype=torch.uint8, device=env.device)
+  hb.reset_host(h_obs, h_mask, h_cur)
+  dv.reset(); dv.observe(d_obs, d_mask, d_cur)
+  for t in range(12):
+    assert torch.equal(d_obs.cpu(), h_obs) and torch.equal(d_mask.cpu(), h_mask)
+    ph.host_random_legal_actions(h_mask, seed=9, step=t, out=h_act)
+    hb.step_encode_host(h_act, h_rew, h_done, h_obs, h_mask, h_cur)
+    dv.step_encode(h_act.to(env.device), d_rew, d_done, d_obs, d_mask, d_cur)
+    assert torch.equal(d_rew.cpu(), h_rew) and torch.equal(d_done.cpu(), h_done)
+  # illegal actions are flagged per game in the wide layout's scalar column too
+  bad = torch.full((n,), 999, dtype=torch.int32, device=env.device)
+  dv.step_encode(bad, d_rew, d_done, d_obs, d_mask, d_cur)
+  assert bool(dv.error_flags(clear=True).all()) and not bool(dv.error_flags().any())
