@@ -30,6 +30,38 @@ CONFIGS = {
     "wide7seer": dict(players=5, hand_size=7, observation_type=2),
     "wide8dealt": dict(players=5, colors=4, ranks=5, hand_size=8, max_life_tokens=2),  # 40 of 40 cards dealt
 }
+
+
+def fuzz_rule_sets(count=40, seed=2024):
+  """Deterministic random rule sets over everything the reference's HanabiGame constructor
+  accepts (hanabi_game.cc:29-58: 2-5 players, 1-5 colours, 1-5 ranks, hand_size * players <=
+  deck, any token maxima, the three observation types, random start player), plus the corners:
+  one colour, one rank, no information tokens, hands of one and of eight cards, decks dealt out
+  completely by the initial deal."""
+  rng = np.random.default_rng(seed)
+  out = [
+      dict(players=2, colors=1, ranks=1, hand_size=1, max_information_tokens=1, max_life_tokens=1),
+      dict(players=3, colors=1, ranks=5, hand_size=3, max_information_tokens=0, max_life_tokens=2),
+      dict(players=5, colors=5, ranks=1, hand_size=3, max_information_tokens=4, max_life_tokens=1),
+      dict(players=5, colors=5, ranks=5, hand_size=8, max_information_tokens=8, max_life_tokens=3,
+           observation_type=2, random_start_player="true"),
+      dict(players=2, colors=5, ranks=5, hand_size=8, observation_type=0),
+      dict(players=4, colors=3, ranks=4, hand_size=6, max_information_tokens=3, max_life_tokens=4),  # 24 of 24 dealt
+      dict(players=2, colors=2, ranks=2, hand_size=4, max_information_tokens=2, max_life_tokens=1),  # 8 of 8 dealt
+  ]
+  while len(out) < count:
+    P, C, R = int(rng.integers(2, 6)), int(rng.integers(1, 6)), int(rng.integers(1, 6))
+    per_color = sum(3 if r == 0 else (1 if r == R - 1 else 2) for r in range(R))
+    hmax = min(8, per_color * C // P)
+    if hmax < 1:
+      continue
+    out.append(dict(players=P, colors=C, ranks=R, hand_size=int(rng.integers(1, hmax + 1)),
+                    max_information_tokens=int(rng.integers(0, 10)), max_life_tokens=int(rng.integers(1, 6)),
+                    observation_type=int(rng.integers(0, 3)),
+                    random_start_player="true" if rng.random() < 0.3 else "false"))
+  return out
+
+
 EXPECTED_SHAPES = {  # SURVEY.md section 8: (obs_dim, num_moves)
     "full2": (658, 20), "full3": (956, 30), "full4": (1041, 38), "full5": (1280, 48),
     "small2": (171, 11), "small4": (281, 25), "vsmall2": (106, 10), "minimal2": (308, 20),

@@ -60,6 +60,22 @@ def test_keep_alive_policy_lockstep(name):
     assert max_score >= 15
 
 
+@pytest.mark.parametrize("index", range(0, 40, 5))
+def test_fuzzed_rule_sets_lockstep(index):
+  """Random rule sets over everything the reference's constructor accepts (common.fuzz_rule_sets:
+  1-5 colours and ranks, hands of 1-8 cards, token maxima from 0, all observation types, random
+  start player, decks dealt out by the initial deal) in lock-step with the compiled reference:
+  the runtime-parameter kernels (DView, WView) on rule sets nobody wrote a case for."""
+  for k, params in enumerate(common.fuzz_rule_sets()[index:index + 5]):
+    n = 200
+    seeds = common.seeds_for(n, base=7000 + 10 * (index + k))
+    cpu = _checker(params, n, seeds)
+    gpu = GpuBatch(params, n, seeds)
+    cpu.reset(); gpu.reset()
+    common.lockstep(cpu, gpu, 64, np.random.default_rng(index + k), bool(k & 1), params, dump_every=8,
+                    check_all_observers_every=16)
+
+
 @pytest.mark.parametrize("name", ["small2", "full4"])
 def test_rng_stream_across_block_wraps(name):
   """Long lock-step run: every game takes several thousand mt19937 words, i.e. its

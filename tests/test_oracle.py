@@ -182,6 +182,21 @@ def test_oracle_vs_reference_keep_alive_policy(name):
 
 
 @needs_ref
+@pytest.mark.parametrize("index", range(0, 40, 4))
+def test_oracle_vs_reference_fuzzed_rule_sets(index):
+  """The C restatement against the compiled reference on random rule sets (a slice of the list
+  the GPU engine is run against in tests/test_gpu_parity.py)."""
+  for params in common.fuzz_rule_sets()[index:index + 4]:
+    n = 24
+    seeds = common.seeds_for(n, base=400 + index)
+    ref = O.CpuBatch("ref", params, n, seeds)
+    orc = O.CpuBatch("oracle", params, n, seeds)
+    ref.reset(); orc.reset()
+    common.lockstep(ref, orc, 40, np.random.default_rng(index), False, params, dump_every=8,
+                    check_all_observers_every=10)
+
+
+@needs_ref
 def test_no_auto_reset_and_illegal_actions():
   n = 16
   p = CONFIGS["small2"]
