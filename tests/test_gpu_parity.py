@@ -120,7 +120,7 @@ def test_full2_at_survey_size():
   assert eps > 10000
 
 
-@pytest.mark.parametrize("name", ["full2", "full5", "ppo_sweep"])
+@pytest.mark.parametrize("name", ["full2", "full5", "ppo_sweep", "wide8dealt"])
 def test_split_kernels_and_padded_pitch(name):
   """BatchStep + BatchObserve (unfused) and obs rows with a 16-byte padded pitch
   and with an odd pitch give the same bytes as the fused dense path."""
@@ -325,7 +325,7 @@ def test_unaligned_output_buffer_takes_the_byte_path():
     assert bool((store[:shift] == 9).all()) and bool((store[shift + n * D:] == 9).all())
 
 
-@pytest.mark.parametrize("name", ["full2", "full5", "small2", "vsmall2", "odd"])
+@pytest.mark.parametrize("name", ["full2", "full5", "small2", "vsmall2", "odd", "wide6", "wide7seer"])
 def test_packed_observations_match_byte_form(name):
   """Bit-packed rows (BatchStepEncodePacked / BatchObservePacked) unpack to exactly
   the byte-per-bit observations, padding bits are zero, for full and ragged tiles."""
@@ -373,7 +373,7 @@ def test_packed_observations_match_byte_form(name):
     common.assert_same(obs.cpu().numpy(), raw[:, :D], "packed observation of player %d" % observer)
 
 
-@pytest.mark.parametrize("name", ["full2", "full5", "small4"])
+@pytest.mark.parametrize("name", ["full2", "full5", "small4", "wide8"])
 def test_no_write_outside_the_output_buffers(name):
   """compute-sanitizer is not available on this pool: every output buffer of every step
   flavour sits between canary regions inside one allocation, with a ragged number of games;

@@ -110,7 +110,7 @@ def test_c51_target_distribution_fused():
   np.testing.assert_allclose(got.cpu().numpy()[same], want[same], rtol=1e-5, atol=1e-6)
 
 
-@pytest.mark.parametrize("name", ["full2", "small2", "full4"])
+@pytest.mark.parametrize("name", ["full2", "small2", "full4", "wide8dealt"])
 def test_fused_random_policy_equals_the_select_kernel(name):
   """BatchStepEncodeRandom leaves in `actions` exactly what BatchSelectAction (epsilon >= 1,
   same seed/step) picks from the mask of the same call; the rollout it drives is legal."""
@@ -200,7 +200,7 @@ def test_expand_packed_and_c51_select_on_gemm_outputs(dtype_name):
 
 
 @pytest.mark.parametrize("dtype_name,name", [("bfloat16", "full2"), ("float32", "full2"), ("float16", "small2"),
-                                             ("bfloat16", "full5")])
+                                             ("bfloat16", "full5"), ("bfloat16", "wide8"), ("float32", "wide7seer")])
 def test_step_kernel_writes_the_network_input(dtype_name, name):
   """BatchStepEncodeNet / BatchObserveNet: the step kernel's own 0/1 rows in the GEMM's element
   type (K zero-padded) equal the byte observation of a twin batch, step after step; the packed
