@@ -227,3 +227,20 @@ def test_two_gpu_shards_equal_one_gpu_run():
   b = _fused_rollout(ph, torch, params, seeds[n // 2:], n // 2, steps, device=1)
   for k in range(len(whole)):
     assert torch.equal(torch.cat([a[k], b[k].to("cuda:0")]), whole[k])
+
+
+@pytest.mark.parametrize("name,steps", [("full2", 3000), ("small2", 3000), ("full4", 2000)])
+def test_long_soak_lockstep(name, steps):
+  """Soak: 1 024 games in lock-step with the compiled reference for thousands of steps -- several
+  hundred episodes per game on the small rule set, every game's mt19937 block regenerated many
+  times over, the re-deal queues of every CTA exercised at all fill levels (serial path for two
+  players, job path with lazy regeneration for four)."""
+  n = 1024
+  seeds = common.seeds_for(n, base=424242)
+  params = common.CONFIGS[name]
+  cpu = O.CpuBatch("ref" if O.have_ref() else "oracle", params, n, seeds)
+  gpu = common.GpuBatch(params, n, seeds)
+  cpu.reset(); gpu.reset()
+  eps, _ = common.lockstep(cpu, gpu, steps, np.random.default_rng(99), False, params, dump_every=250,
+                           check_all_observers_every=500)
+  assert eps > n * steps // 40
