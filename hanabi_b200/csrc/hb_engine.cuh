@@ -142,14 +142,15 @@ template <class W> HB_DEV constexpr W slot_ones();
 template <> HB_DEV constexpr uint32_t slot_ones<uint32_t>() { return 0x108421u; }
 template <> HB_DEV constexpr uint64_t slot_ones<uint64_t>() { return 0x842108421ull; }
 
-// The packed state is the one array the next step reads again.  Where it pays, its loads and
-// stores carry the L2 evict-last policy, so that the streaming observation stores (evict-first)
-// do not push it out of the 126 MB L2.  Measured per rule set on B200, 2^20 games
-// (profiles/r02ae_ab_evict.log, r02af_*, r02ag_*): Full 2p +2.3 % (also at 2^22 games, where the
-// state is larger than the L2), Small 2p / 4p +1.2 % / +1.3 %, Full 4p -0.2 %, Full 5p -1.3 % --
-// hence a property of the view (kKeepState).  The same hint on the RNG words gains the same
-// 2.4 % on Full 2p alone and loses it together with the state (the L2 cannot keep both), on the
-// action buffer it changes nothing.  HB_STATE_EVICT_LAST = 0 / 1 forces it off / on everywhere.
+// The packed state is the one array the next step reads again.  Where it pays, its STORES carry
+// the L2 evict-last policy, so that the streaming observation stores (evict-first) do not push it
+// out of the 126 MB L2.  Measured per rule set on B200, 2^20 games (profiles/r02ae_exp_ab_evict.log,
+// r02af_*, r02ag_*, r02aj_*, r02ak_*): Full 2p +2.2 % (also at 2^22 games, where the state is
+// larger than the L2), Small 2p / 4p +2.1 % / +2.5 %, Full 4p -0.2...-1.5 %, Full 5p -1.3...-4 % --
+// hence a property of the view (kKeepState).  The hint on the state's loads adds nothing (and
+// costs 0.5-1 % next to the stores'); on the RNG words alone it gains the same 2.4 % on Full 2p
+// and loses it together with the state (the L2 cannot keep both); on the action buffer it
+// changes nothing.  HB_STATE_EVICT_LAST = 0 / 1 forces it off / on everywhere.
 #ifndef HB_STATE_EVICT_LAST
 #define HB_STATE_EVICT_LAST -1
 #endif
@@ -162,17 +163,10 @@ HB_DEV uint64_t state_policy() {
   asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
   return pol;
 }
+// (the hint on the LOADS adds nothing: stores only, profiles/r02aj_exp_ab_ldst.log)
 template <bool KEEP>
 HB_DEV uint4 ld_state(const uint4* p) {
-  if constexpr (KEEP) {
-    uint4 v;
-    asm volatile("ld.global.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
-                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-                 : "l"(p), "l"(state_policy()));
-    return v;
-  } else {
-    return *p;
-  }
+  return *p;
 }
 template <bool KEEP>
 HB_DEV void st_state(uint4* p, uint4 v) {
