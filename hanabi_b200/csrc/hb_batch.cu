@@ -552,9 +552,16 @@ k_main(const __grid_constant__ KArgs a) {
     if (a.mask) pack_mask_stream(mask_stream, a.spec.max_moves, legal, valid, lane);
   }
   __syncwarp();
-  if (a.obs)
-    expand_stream(obs_stream, a.spec.obs_size, a.obs + tile0 * a.obs_pitch, a.obs_pitch, n_valid,
-                  lane, s_nib);
+  // streaming (evict-first) stores for long rows, plain L2 stores for short ones (store_out)
+  const bool stream_out = V::kStreamOut < 0 ? a.spec.obs_size >= 512 : V::kStreamOut != 0;
+  if (a.obs) {
+    if (stream_out)
+      expand_stream<true>(obs_stream, a.spec.obs_size, a.obs + tile0 * a.obs_pitch, a.obs_pitch, n_valid,
+                          lane, s_nib);
+    else
+      expand_stream<false>(obs_stream, a.spec.obs_size, a.obs + tile0 * a.obs_pitch, a.obs_pitch, n_valid,
+                           lane, s_nib);
+  }
   if (a.obs_bits)
     store_packed_rows(obs_stream, a.packed_words, a.obs_bits + tile0 * a.packed_words, n_valid, lane);
   if (NET) {
@@ -562,9 +569,14 @@ k_main(const __grid_constant__ KArgs a) {
     expand_net_rows(obs_stream, a.packed_words, static_cast<uint8_t*>(a.net_in) + tile0 * a.net_pitch * esz,
                     a.net_pitch, a.net_chunks, a.net_magic, n_valid, lane, s_net_lut, a.net_dtype == 0);
   }
-  if (a.mask)
-    expand_stream(mask_stream, a.spec.max_moves, a.mask + tile0 * a.spec.max_moves,
-                  a.spec.max_moves, n_valid, lane, s_nib);
+  if (a.mask) {
+    if (stream_out)
+      expand_stream<true>(mask_stream, a.spec.max_moves, a.mask + tile0 * a.spec.max_moves,
+                          a.spec.max_moves, n_valid, lane, s_nib);
+    else
+      expand_stream<false>(mask_stream, a.spec.max_moves, a.mask + tile0 * a.spec.max_moves,
+                           a.spec.max_moves, n_valid, lane, s_nib);
+  }
 }
 
 // std::mt19937::seed(value) per game followed by the first block regeneration

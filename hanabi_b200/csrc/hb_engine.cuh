@@ -50,7 +50,8 @@ struct SView {
   static constexpr int kP = P_, kH = H_, kC = C_, kR = R_;
   static constexpr int kBlock = block_for_deal(P_ * H_);
   static constexpr int kResident = 0;  // resident threads per SM the kernel is built for (0: the default)
-  static constexpr bool kKeepState = P_ == 2 || H_ <= 2;  // L2 evict-last on the packed state (ld_state)
+  static constexpr bool kKeepState = P_ == 2 || H_ <= 2;  // L2 evict-last on the packed state's stores (st_state)
+  static constexpr int kStreamOut = C_ * R_ * H_ >= 100 ? 1 : 0;  // streaming stores for long rows (store_out)
   // Re-deal machinery, measured per rule set (profiles/r02i_ab.log): initial deals of 12+ cards
   // go through the job path (one thread per RNG word pair over all jobs of the CTA, serial
   // chain per job, lazy slot regeneration); deals of up to 10 cards keep round 1's serial path.
@@ -80,6 +81,7 @@ struct DViewT {
   static constexpr int kBlock = WIDE ? 128 : block_for_deal(kMaxPlayers * kMaxHandNarrow);
   static constexpr int kResident = WIDE ? 384 : 0;  // the 64-bit hand words cost registers: fewer, fatter threads
   static constexpr bool kKeepState = false;
+  static constexpr int kStreamOut = -1;  // decided by the rule set's row length at run time
   static constexpr bool kJobs = true;
   static constexpr int kPendCap = HB_LAZY_REGEN ? kMaxPend : 0;
   const Spec& s;
@@ -1127,17 +1129,19 @@ HB_DEV void encode_obs(V v, const Spec& spec, const HB_GAME(V)& G, int observer,
   }
 }
 
-// The observation / mask rows are written once and never read back by the engine:
-// streaming (evict-first) stores keep them from displacing the game state in L2.
+// The observation / mask rows are written once and never read back by the engine.  Long rows
+// (the full game's 658+ bytes: a warp's tile is 20+ KB) go out with streaming, evict-first stores
+// so that they do not displace the game state in L2 -- without them Full 4p is 9 % slower.
+// Short rows (the small games' 171 / 281 bytes: 5-9 KB per tile, every tile edge a 128-byte line
+// shared with the neighbouring warp) are 2.7 % faster with plain L2 stores: an evict-first line
+// leaves the L2 before the neighbour has completed it (profiles/r02al_exp_ab_out.log).
 #ifndef HB_STREAM_STORES
-#define HB_STREAM_STORES 1
+#define HB_STREAM_STORES -1  // -1: by row length (view / rule set), 0: never, 1: always
 #endif
+template <bool STREAM = true>
 HB_DEV void store_out(uint4* p, uint4 v) {
-#if HB_STREAM_STORES
-  __stcs(p, v);
-#else
-  *p = v;
-#endif
+  if constexpr (HB_STREAM_STORES != 0 && (STREAM || HB_STREAM_STORES == 1)) __stcs(p, v);
+  else __stcg(p, v);
 }
 
 // Bit-packed observation rows: copies the tile's stream (n_valid rows of
@@ -1216,6 +1220,7 @@ HB_DEV uint4 bits16_to_bytes(uint32_t bits) {
 #ifndef HB_EXPAND_LUT16
 #define HB_EXPAND_LUT16 0  // 1: nibble -> four bytes through a 16-word shared-memory table (experiment)
 #endif
+template <bool STREAM = true>
 HB_DEV void expand_stream(const uint32_t* stream, int dim, uint8_t* out, int64_t pitch,
                           int n_valid, int lane, const uint32_t* nib = nullptr) {
   const bool aligned = (reinterpret_cast<uintptr_t>(out) & 15) == 0;
@@ -1234,11 +1239,11 @@ HB_DEV void expand_stream(const uint32_t* stream, int dim, uint8_t* out, int64_t
 #pragma unroll kUnroll
     for (int k = lane; k < full_chunks; k += 32) {
       const uint32_t b = half[k];
-      store_out(dst + k, make_uint4(nib[b & 15u], nib[(b >> 4) & 15u], nib[(b >> 8) & 15u], nib[b >> 12]));
+      store_out<STREAM>(dst + k, make_uint4(nib[b & 15u], nib[(b >> 4) & 15u], nib[(b >> 8) & 15u], nib[b >> 12]));
     }
 #else
 #pragma unroll kUnroll
-    for (int k = lane; k < full_chunks; k += 32) store_out(dst + k, bits16_to_bytes(half[k]));
+    for (int k = lane; k < full_chunks; k += 32) store_out<STREAM>(dst + k, bits16_to_bytes(half[k]));
 #endif
     for (int b = (full_chunks << 4) + lane; b < total; b += 32)  // ragged tail of a partial tile
       out[b] = (uint8_t)((stream[b >> 5] >> (b & 31)) & 1u);
@@ -1252,7 +1257,7 @@ HB_DEV void expand_stream(const uint32_t* stream, int dim, uint8_t* out, int64_t
           __funnelshift_r(stream[pos >> 5], stream[(pos >> 5) + 1], pos & 31) & 0xffffu;
       uint8_t* d = out + (int64_t)g * pitch + o;
       if (avail >= 16) {
-        store_out(reinterpret_cast<uint4*>(d), bits16_to_bytes(bits));
+        store_out<STREAM>(reinterpret_cast<uint4*>(d), bits16_to_bytes(bits));
       } else {
         for (int i = 0; i < avail; ++i) d[i] = (uint8_t)((bits >> i) & 1u);
       }
