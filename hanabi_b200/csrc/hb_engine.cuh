@@ -50,7 +50,7 @@ struct SView {
   static constexpr int kP = P_, kH = H_, kC = C_, kR = R_;
   static constexpr int kBlock = block_for_deal(P_ * H_);
   static constexpr int kResident = 0;  // resident threads per SM the kernel is built for (0: the default)
-  static constexpr bool kKeepState = P_ == 2 || H_ <= 2;  // L2 evict-last on the packed state's stores (st_state)
+  static constexpr int kStatePolicy = (P_ == 2 || H_ <= 2) ? 1 : 2;  // L2 policy of the packed state (st_state)
   static constexpr int kStreamOut = C_ * R_ * H_ >= 100 ? 1 : 0;  // streaming stores for long rows (store_out)
   // Re-deal machinery, measured per rule set (profiles/r02i_ab.log): initial deals of 12+ cards
   // go through the job path (one thread per RNG word pair over all jobs of the CTA, serial
@@ -80,7 +80,7 @@ struct DViewT {
   static constexpr int kP = kMaxPlayers, kH = WIDE ? kMaxHand : kMaxHandNarrow, kC = kMaxColors, kR = kMaxRanks;
   static constexpr int kBlock = WIDE ? 128 : block_for_deal(kMaxPlayers * kMaxHandNarrow);
   static constexpr int kResident = WIDE ? 384 : 0;  // the 64-bit hand words cost registers: fewer, fatter threads
-  static constexpr bool kKeepState = false;
+  static constexpr int kStatePolicy = 0;
   static constexpr int kStreamOut = -1;  // decided by the rule set's row length at run time
   static constexpr bool kJobs = true;
   static constexpr int kPendCap = HB_LAZY_REGEN ? kMaxPend : 0;
@@ -149,33 +149,39 @@ template <> HB_DEV constexpr uint64_t slot_ones<uint64_t>() { return 0x842108421
 // out of the 126 MB L2.  Measured per rule set on B200, 2^20 games (profiles/r02ae_exp_ab_evict.log,
 // r02af_*, r02ag_*, r02aj_*, r02ak_*): Full 2p +2.2 % (also at 2^22 games, where the state is
 // larger than the L2), Small 2p / 4p +2.1 % / +2.5 %, Full 4p -0.2...-1.5 %, Full 5p -1.3...-4 % --
-// hence a property of the view (kKeepState).  The hint on the state's loads adds nothing (and
+// hence a property of the view (kStatePolicy).  The hint on the state's loads adds nothing (and
 // costs 0.5-1 % next to the stores'); on the RNG words alone it gains the same 2.4 % on Full 2p
 // and loses it together with the state (the L2 cannot keep both); on the action buffer it
-// changes nothing.  HB_STATE_EVICT_LAST = 0 / 1 forces it off / on everywhere.
-#ifndef HB_STATE_EVICT_LAST
-#define HB_STATE_EVICT_LAST -1
+// changes nothing.
+// The rule sets whose state the L2 cannot keep anyway (Full 3p / 4p / 5p: 64-96 B per game) do
+// best with STREAMING loads and stores of the state (ld.cs / st.cs: +0.5 % Full 4p, +0.9 % Full 5p,
+// profiles/r02an_exp_ab_stcs.log).  kStatePolicy of the view: 0 plain, 1 keep (evict-last stores),
+// 2 stream.  HB_STATE_POLICY >= 0 forces one policy everywhere.
+#ifndef HB_STATE_POLICY
+#define HB_STATE_POLICY -1
 #endif
 template <class V>
-constexpr bool keep_state() {
-  return HB_STATE_EVICT_LAST < 0 ? V::kKeepState : HB_STATE_EVICT_LAST != 0;
+constexpr int state_policy_of() {
+  return HB_STATE_POLICY < 0 ? V::kStatePolicy : HB_STATE_POLICY;
 }
 HB_DEV uint64_t state_policy() {
   uint64_t pol;
   asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
   return pol;
 }
-// (the hint on the LOADS adds nothing: stores only, profiles/r02aj_exp_ab_ldst.log)
-template <bool KEEP>
+template <int POLICY>
 HB_DEV uint4 ld_state(const uint4* p) {
-  return *p;
+  if constexpr (POLICY == 2) return __ldcs(p);
+  else return *p;
 }
-template <bool KEEP>
+template <int POLICY>
 HB_DEV void st_state(uint4* p, uint4 v) {
-  if constexpr (KEEP) {
+  if constexpr (POLICY == 1) {
     asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;"
                  :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(state_policy())
                  : "memory");
+  } else if constexpr (POLICY == 2) {
+    __stcs(p, v);
   } else {
     *p = v;
   }
@@ -223,17 +229,17 @@ HB_DEV void load_game(const uint4* __restrict__ st, int64_t N, int64_t g, V v, H
     for (int p = 0; p < V::kP; ++p) {
       G.cards[p] = 0; G.cpl[p] = 0; G.rpl[p] = 0; G.hw[p] = 0;
       if (p < v.P()) {
-        const uint4 a = ld_state<keep_state<V>()>(st + (int64_t)(2 * p) * N + g), b = ld_state<keep_state<V>()>(st + (int64_t)(2 * p + 1) * N + g);
+        const uint4 a = ld_state<state_policy_of<V>()>(st + (int64_t)(2 * p) * N + g), b = ld_state<state_policy_of<V>()>(st + (int64_t)(2 * p + 1) * N + g);
         G.cards[p] = (uint64_t)a.x | ((uint64_t)a.y << 32);
         G.cpl[p] = (uint64_t)a.z | ((uint64_t)a.w << 32);
         G.rpl[p] = (uint64_t)b.x | ((uint64_t)b.y << 32);
         G.hw[p] = b.z;
       }
     }
-    const uint4 a = ld_state<keep_state<V>()>(st + (int64_t)(2 * v.P()) * N + g);
+    const uint4 a = ld_state<state_policy_of<V>()>(st + (int64_t)(2 * v.P()) * N + g);
     G.deck = (uint64_t)a.x | ((uint64_t)a.y << 32);
     G.disc = (uint64_t)a.z | ((uint64_t)a.w << 32);
-    const uint4 b = ld_state<keep_state<V>()>(st + (int64_t)(2 * v.P() + 1) * N + g);
+    const uint4 b = ld_state<state_policy_of<V>()>(st + (int64_t)(2 * v.P() + 1) * N + g);
     unpack_misc(G, b.x);
     G.deck_size = b.y & 63;
     G.mti = (b.y >> 6) & 1023;
@@ -248,12 +254,12 @@ HB_DEV void load_game(const uint4* __restrict__ st, int64_t N, int64_t g, V v, H
 #pragma unroll
     for (int p = 0; p < V::kP; ++p) {
       uint4 c = make_uint4(0, 0, 0, 0);
-      if (p < v.P()) c = ld_state<keep_state<V>()>(st + (int64_t)p * N + g);
+      if (p < v.P()) c = ld_state<state_policy_of<V>()>(st + (int64_t)p * N + g);
       if (p == 0) c0 = c;
       if (p == 1) c1 = c;
       G.cards[p] = c.x & 0x3fffffffu; G.cpl[p] = c.y & 0x1ffffffu; G.rpl[p] = c.z & 0x1ffffffu; G.hw[p] = c.w & 0xfffffu;
     }
-    const uint4 c2 = ld_state<keep_state<V>()>(st + (int64_t)v.P() * N + g);
+    const uint4 c2 = ld_state<state_policy_of<V>()>(st + (int64_t)v.P() * N + g);
     G.deck = (uint64_t)c2.x | ((uint64_t)(c2.y & 0x3ffffu) << 32);
     G.disc = (uint64_t)c2.z | ((uint64_t)(c2.w & 0x3ffffu) << 32);
     unpack_misc(G, (c0.w >> 20) | ((c1.w >> 20) << 12) | (((c2.y >> 18) & 0xffu) << 24));
@@ -269,16 +275,16 @@ HB_DEV void load_game(const uint4* __restrict__ st, int64_t N, int64_t g, V v, H
 #pragma unroll
   for (int p = 0; p < V::kP; ++p) {
     if (p < v.P()) {
-      uint4 c = ld_state<keep_state<V>()>(st + (int64_t)p * N + g);
+      uint4 c = ld_state<state_policy_of<V>()>(st + (int64_t)p * N + g);
       G.cards[p] = c.x; G.cpl[p] = c.y; G.rpl[p] = c.z; G.hw[p] = c.w;
     } else {
       G.cards[p] = 0; G.cpl[p] = 0; G.rpl[p] = 0; G.hw[p] = 0;
     }
   }
-  uint4 a = ld_state<keep_state<V>()>(st + (int64_t)v.P() * N + g);
+  uint4 a = ld_state<state_policy_of<V>()>(st + (int64_t)v.P() * N + g);
   G.deck = (uint64_t)a.x | ((uint64_t)a.y << 32);
   G.disc = (uint64_t)a.z | ((uint64_t)a.w << 32);
-  uint4 b = ld_state<keep_state<V>()>(st + (int64_t)(v.P() + 1) * N + g);
+  uint4 b = ld_state<state_policy_of<V>()>(st + (int64_t)(v.P() + 1) * N + g);
   G.fw = b.x & 0x7fffu;
   G.info = (b.x >> 15) & 31;
   G.life = (b.x >> 20) & 15;
@@ -301,19 +307,19 @@ HB_DEV void store_game(uint4* __restrict__ st, int64_t N, int64_t g, V v, const 
 #pragma unroll
     for (int p = 0; p < V::kP; ++p) {
       if (p < v.P()) {
-        st_state<keep_state<V>()>(st + (int64_t)(2 * p) * N + g, make_uint4((uint32_t)G.cards[p], (uint32_t)(G.cards[p] >> 32),
+        st_state<state_policy_of<V>()>(st + (int64_t)(2 * p) * N + g, make_uint4((uint32_t)G.cards[p], (uint32_t)(G.cards[p] >> 32),
                                                            (uint32_t)G.cpl[p], (uint32_t)(G.cpl[p] >> 32)));
-        st_state<keep_state<V>()>(st + (int64_t)(2 * p + 1) * N + g, make_uint4((uint32_t)G.rpl[p], (uint32_t)(G.rpl[p] >> 32), G.hw[p], 0u));
+        st_state<state_policy_of<V>()>(st + (int64_t)(2 * p + 1) * N + g, make_uint4((uint32_t)G.rpl[p], (uint32_t)(G.rpl[p] >> 32), G.hw[p], 0u));
       }
     }
-    st_state<keep_state<V>()>(st + (int64_t)(2 * v.P()) * N + g, make_uint4((uint32_t)G.deck, (uint32_t)(G.deck >> 32),
+    st_state<state_policy_of<V>()>(st + (int64_t)(2 * v.P()) * N + g, make_uint4((uint32_t)G.deck, (uint32_t)(G.deck >> 32),
                                                            (uint32_t)G.disc, (uint32_t)(G.disc >> 32)));
     const uint32_t x = G.fw | ((uint32_t)G.info << 15) | ((uint32_t)G.life << 20) |
                        ((uint32_t)G.cur << 24) | ((uint32_t)G.turns << 27) | ((uint32_t)G.done << 30) |
                        ((uint32_t)G.err << 31);
     const uint32_t y = (uint32_t)G.deck_size | ((uint32_t)G.mti << 6) |
                        ((uint32_t)(G.eplen > 255 ? 255 : G.eplen) << 16) | ((uint32_t)G.pend << 28);
-    st_state<keep_state<V>()>(st + (int64_t)(2 * v.P() + 1) * N + g, make_uint4(x, y, G.last, G.spare));
+    st_state<state_policy_of<V>()>(st + (int64_t)(2 * v.P() + 1) * N + g, make_uint4(x, y, G.last, G.spare));
     return;
   } else {
   if (HB_COMPACT_STATE) {
@@ -333,27 +339,27 @@ HB_DEV void store_game(uint4* __restrict__ st, int64_t N, int64_t g, V v, const 
         if (p == 1) {
           c.x |= ((L >> 21) & 1u) << 30; c.y |= ((m >> 14) & 0x7fu) << 25; c.z |= ((L >> 14) & 0x7fu) << 25; c.w |= ((X >> 12) & 0xfffu) << 20;
         }
-        st_state<keep_state<V>()>(st + (int64_t)p * N + g, c);
+        st_state<state_policy_of<V>()>(st + (int64_t)p * N + g, c);
       }
     }
     const uint32_t dh = (uint32_t)(G.deck >> 32) & 0x3ffffu, sh = (uint32_t)(G.disc >> 32) & 0x3ffffu;
-    st_state<keep_state<V>()>(st + (int64_t)v.P() * N + g,
+    st_state<state_policy_of<V>()>(st + (int64_t)v.P() * N + g,
              make_uint4((uint32_t)G.deck, dh | (((X >> 24) & 0xffu) << 18) | (((L >> 22) & 0x3fu) << 26),
                         (uint32_t)G.disc, sh | ((L & 0x3fffu) << 18)));
     return;
   }
 #pragma unroll
   for (int p = 0; p < V::kP; ++p) {
-    if (p < v.P()) st_state<keep_state<V>()>(st + (int64_t)p * N + g, make_uint4(G.cards[p], G.cpl[p], G.rpl[p], G.hw[p]));
+    if (p < v.P()) st_state<state_policy_of<V>()>(st + (int64_t)p * N + g, make_uint4(G.cards[p], G.cpl[p], G.rpl[p], G.hw[p]));
   }
-  st_state<keep_state<V>()>(st + (int64_t)v.P() * N + g, make_uint4((uint32_t)G.deck, (uint32_t)(G.deck >> 32),
+  st_state<state_policy_of<V>()>(st + (int64_t)v.P() * N + g, make_uint4((uint32_t)G.deck, (uint32_t)(G.deck >> 32),
                                                    (uint32_t)G.disc, (uint32_t)(G.disc >> 32)));
   uint32_t x = G.fw | ((uint32_t)G.info << 15) | ((uint32_t)G.life << 20) |
                ((uint32_t)G.cur << 24) | ((uint32_t)G.turns << 27) | ((uint32_t)G.done << 30) |
                ((uint32_t)G.err << 31);
   uint32_t y = (uint32_t)G.deck_size | ((uint32_t)G.mti << 6) |
                ((uint32_t)(G.eplen > 255 ? 255 : G.eplen) << 16) | ((uint32_t)G.pend << 28);
-  st_state<keep_state<V>()>(st + (int64_t)(v.P() + 1) * N + g, make_uint4(x, y, G.last, G.spare));
+  st_state<state_policy_of<V>()>(st + (int64_t)(v.P() + 1) * N + g, make_uint4(x, y, G.last, G.spare));
   }
 }
 
