@@ -27,6 +27,7 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     "hanabi_full_2p": dict(players=2),
+    "hanabi_full_3p": dict(players=3),
     "hanabi_full_4p": dict(players=4),
     "hanabi_full_5p": dict(players=5),
     "hanabi_small_2p": dict(players=2, colors=2, ranks=5, hand_size=2, max_information_tokens=3,
@@ -37,7 +38,7 @@ WORKLOADS = {
 }
 # Algorithmic bytes per env-step (SURVEY.md section 8d / BASELINE.md section 4):
 # obs_dim + A (uint8 mask) + 4 (reward) + 1 (done) + 4 (action) + 2 * S (packed state r+w).
-ALGO_BYTES = {"hanabi_full_2p": 815, "hanabi_full_4p": 1248, "hanabi_full_5p": 1529,
+ALGO_BYTES = {"hanabi_full_2p": 815, "hanabi_full_3p": 1155, "hanabi_full_4p": 1248, "hanabi_full_5p": 1529,
               "hanabi_small_2p": 255, "hanabi_small_4p": 411}
 POLICY_SEED = 7
 INIT_POLICY_STEP = 1 << 40  # key of the rollout's first actions (the steps count from 0)
