@@ -1,6 +1,11 @@
-// hb_host.cc -- host-side helpers of the batched C-ABI that run on CPU threads:
-// the uniform-random-legal policy for HOST masks (the host twin of the device
-// select kernels) on a persistent worker pool.
+// hb_host.cc -- host-side helpers of the batched C-ABI that run on CPU threads, on one
+// persistent worker pool:
+//   * the uniform-random-legal policy for HOST masks (the host twin of the device select
+//     kernels; AVX2 + BMI2 where the CPU has them);
+//   * HostExpandPacked, the host half of the packed link: bit-packed observation rows
+//     (what crosses PCIe) -> the caller's uint8 rows of 0/1 (AVX2, non-temporal stores).
+// Nothing here computes game logic: both are transport / consumer-side helpers of the
+// host-buffer entry points.
 //
 // The pool exists because a host consumer of BatchStepEncodeHostRange calls the
 // policy once per range of games, several thousand times a second: spawning
