@@ -77,6 +77,7 @@ struct KArgs {
   // `actions` (every thread reads its action before it writes the next one)
   int32_t* random_actions;
   uint64_t policy_seed, policy_step;
+  uint64_t policy_key;     // hbp::policy_step_key(policy_seed, policy_step), computed once on the host
   int64_t game_base;  // global index of this batch's game 0 (BatchSetGameIndexBase): the policy key's game
   unsigned long long* stats;
   uint4* hist;  // optional: the 4 non-deal moves before `last`, newest first (BatchEnableHistory)
@@ -546,7 +547,7 @@ k_main(const __grid_constant__ KArgs a) {
     const uint64_t legal = legal_bits(v, G);
     if (a.random_actions && valid) {
       const int n_legal = __popcll(legal);
-      const uint64_t bits = hbp::policy_bits(a.policy_seed, a.policy_step, (uint64_t)(g + a.game_base));
+      const uint64_t bits = hbp::policy_bits_keyed(a.policy_key, (uint64_t)(g + a.game_base));
       a.random_actions[g] = n_legal > 0 ? select64(legal, hbp::random_legal_rank(bits, n_legal)) : -1;
     }
     if (a.mask) pack_mask_stream(mask_stream, a.spec.max_moves, legal, valid, lane);
@@ -1235,6 +1236,7 @@ int BatchStepEncodeRandom(pyhanabi_batch_t* h, const int32_t* actions, int32_t* 
   a.obs = obs; a.obs_pitch = row_pitch; a.mask = mask; a.cur_player = cur_player;
   a.auto_reset = auto_reset;
   a.random_actions = random_actions; a.policy_seed = seed; a.policy_step = step;
+  a.policy_key = hbp::policy_step_key(seed, step);
   HB_CUDA(Launch<hb::kModeStep>(b, a, (cudaStream_t)stream));
   return 0;
 }
@@ -1260,6 +1262,7 @@ int BatchRandomLegalActions(pyhanabi_batch_t* h, uint64_t seed, uint64_t step, i
   if (!actions) return Fail("BatchRandomLegalActions: actions is null");
   hb::KArgs a = BaseArgs(b);
   a.random_actions = actions; a.policy_seed = seed; a.policy_step = step;
+  a.policy_key = hbp::policy_step_key(seed, step);
   HB_CUDA(Launch<hb::kModeObserve>(b, a, (cudaStream_t)stream));
   return 0;
 }

@@ -711,7 +711,8 @@ HB_DEV bool move_is_legal(V v, const HB_GAME(V)& G, int uid, int max_moves) {
   const bool is_rank = u >= (P - 1) * C;
   if (is_rank) u -= (P - 1) * C;
   const int span = is_rank ? R : C;
-  const int offm1 = u / span, val = u - offm1 * span;
+  // (two divisions by the view's constants instead of one by their runtime selection)
+  const int offm1 = is_rank ? u / R : u / C, val = u - offm1 * span;
   int t = G.cur + offm1 + 1;
   t -= t >= P ? P : 0;
   const typename V::Word hand = sel<V>(G.cards, t);
@@ -779,7 +780,7 @@ HB_DEV void apply_move(V v, HB_GAME(V)& G, int uid) {
     const bool is_rank = u >= (P - 1) * C;
     if (is_rank) u -= (P - 1) * C;
     const int span = is_rank ? R : C;
-    const int offm1 = u / span, val = u - offm1 * span;
+    const int offm1 = is_rank ? u / R : u / C, val = u - offm1 * span;
     int t = cur + offm1 + 1;
     t -= t >= P ? P : 0;
     G.info -= 1;

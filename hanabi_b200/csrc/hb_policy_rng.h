@@ -21,8 +21,14 @@ HBP_HD uint64_t mix64(uint64_t z) {
 // reference uses Python's `random` and numpy's global RNG (dqn_agent.py:409-412),
 // which cannot be reproduced on a device; only the distribution is matched (uniform
 // over legal moves with probability epsilon).
+HBP_HD uint64_t policy_step_key(uint64_t seed, uint64_t step) {  // the part that is the same for every game
+  return mix64(seed ^ (step * 0xD1B54A32D192ED03ull));
+}
+HBP_HD uint64_t policy_bits_keyed(uint64_t step_key, uint64_t game) {
+  return mix64(step_key ^ (game * 0x8CB92BA72F3D8DD7ull));
+}
 HBP_HD uint64_t policy_bits(uint64_t seed, uint64_t step, uint64_t game) {
-  return mix64(mix64(seed ^ (step * 0xD1B54A32D192ED03ull)) ^ (game * 0x8CB92BA72F3D8DD7ull));
+  return policy_bits_keyed(policy_step_key(seed, step), game);
 }
 
 // Index (0-based, among n_legal legal moves in ascending uid order) of the uniformly
