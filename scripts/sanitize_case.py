@@ -5,7 +5,7 @@ sys.path.insert(0, ".")
 from hanabi_b200 import pyhanabi as ph
 dev = torch.device("cuda:0")
 for params in (dict(players=2), dict(players=5), dict(players=3, colors=4, ranks=3, hand_size=3, max_information_tokens=5, max_life_tokens=2),
-               dict(players=4, random_start_player="true")):
+               dict(players=4, random_start_player="true"), dict(players=3, hand_size=7, observation_type=2)):
     n = 203
     b = ph.HanabiBatch(params, n, list(range(1, n + 1)))
     b.enable_history()
@@ -16,7 +16,7 @@ for params in (dict(players=2), dict(players=5), dict(players=3, colors=4, ranks
     b.reset(); b.observe(obs, mask, cur)
     for t in range(40):
         ph.select_action(None, mask, 1.0, seed=3, step=t, out=act)
-        if t % 2: b.agent_act(0 if b.num_players >= 2 and b.obs_size > 0 and params.get("hand_size", 4) <= 5 and not (params.get("hand_size") == 3 and False) else 1, 0b10, act, agent_state=st)
+        if t % 2 and params.get("hand_size", 4) <= 5: b.agent_act(0 if b.num_players >= 2 and b.obs_size > 0 and params.get("hand_size", 4) <= 5 and not (params.get("hand_size") == 3 and False) else 1, 0b10, act, agent_state=st)
         b.step_encode(act, rew, done, obs, mask, cur, scores=sc)
     b.step(act, rew, done, sc, auto_reset=False); b.encode(obs, 0); b.legal_mask(mask); b.unpack_state()
     blob = b.get_state(); b.set_state(blob)
